@@ -1,0 +1,386 @@
+// C ABI of libcoalgpu.so (declared in include/coalgpu.h). Host orchestration only: validate the
+// problem, build the HMM tables (coal_tables.cpp), upload, launch the kernels of coal_kernels.cu.
+// CUDA-only by design: no CPU fallback exists behind these entry points.
+#include "coal_kernels.cu"
+#include "coal_tables.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace coalgpu;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU_OK(expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? COALGPU_ENODEV : COALGPU_ECUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+        }                                                                                        \
+    } while (0)
+
+template <class T>
+int upload(const std::vector<T>& v, T** out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU_OK(cudaMalloc((void**)out, bytes));
+    if (!v.empty()) CU_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace
+
+struct coalgpu_sampler {
+    int device = 0;
+    int T = 0, LA = 0, LB = 0, G = 0;
+    DevProblem P{};
+    HostTables tab;
+    std::vector<void*> allocs;
+    unsigned long long* d_counters = nullptr;
+    double* d_block_partials = nullptr;
+    size_t block_partials_cap = 0;
+    int warp_bytes = 0, warps_per_cta = 4, grid = 0;
+    size_t smem_bytes = 0;
+    unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
+    // K2 scratch smem
+    size_t k2_smem = 0;
+};
+
+extern "C" {
+
+const char* coalgpu_last_error(void) { return g_err.c_str(); }
+const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
+uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
+
+void coalgpu_destroy(coalgpu_sampler* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->d_block_partials) cudaFree(s->d_block_partials);
+    delete s;
+}
+
+int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
+    if (!p || !out) return fail(COALGPU_EINVAL, "null argument");
+    *out = nullptr;
+    if (Q != 16) return fail(COALGPU_EINVAL, "only 16 quadrature points are supported (main.cpp:103 hard-codes 16)");
+    if (p->T < 1 || p->LA < 1 || p->LB < 1 || p->LA + p->LB > 64) return fail(COALGPU_EINVAL, "need T >= 1, LA, LB >= 1 and LA + LB <= 64");
+    if (p->n_mu < 1 || p->n_rho < 1 || p->n_lambda < 1) return fail(COALGPU_EINVAL, "empty target grid");
+    if (!(p->tau > 0) || !(p->driving_mu > 0) || !(p->driving_lambda > 0) || !(p->driving_rho > 0)) return fail(COALGPU_EINVAL, "driving values and tau must be positive (main.cpp:147-150)");
+    for (int t = 1; t < p->T; t++) if (!(p->times[t] > p->times[t - 1])) return fail(COALGPU_EINVAL, "sampling times must be strictly ascending");
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) return fail(COALGPU_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(COALGPU_ENODEV, "device index out of range");
+    CU_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
+
+    coalgpu_sampler* s = new coalgpu_sampler;
+    s->device = device; s->T = p->T; s->LA = p->LA; s->LB = p->LB;
+    s->G = p->n_mu * p->n_rho * p->n_lambda;
+    const int T = p->T, LA = p->LA, LB = p->LB, G = s->G;
+    const uint64_t maskA = (LA == 64) ? ~0ull : ((1ull << LA) - 1);
+    const uint64_t maskB = ((LB == 64) ? ~0ull : ((1ull << LB) - 1)) << LA;
+
+    // merge duplicate input types per sampling time, keep insertion order; bound the lineage count:
+    // every sampled two-locus lineage can split once into an A and a B lineage
+    std::vector<int> type_off(T + 1, 0);
+    std::vector<unsigned long long> type_w;
+    std::vector<unsigned int> type_cg;
+    long long n_bound = 0;
+    double perm = 0.0;
+    for (int t = 0; t < T; t++) {
+        const size_t start = type_w.size();
+        for (int k = p->type_offsets[t]; k < p->type_offsets[t + 1]; k++) {
+            const int g = p->type_gamma[k];
+            const uint64_t w = p->type_words[k];
+            const unsigned int c = p->type_counts[k];
+            if (g > 2 || c == 0) { delete s; return fail(COALGPU_EINVAL, "bad type record"); }
+            const uint64_t allowed = g == COALGPU_GAMMA_A ? maskA : (g == COALGPU_GAMMA_B ? maskB : (maskA | maskB));
+            if (w & ~allowed) { delete s; return fail(COALGPU_EINVAL, "haplotype word has bits outside its loci"); }
+            bool hit = false;
+            for (size_t i = start; i < type_w.size(); i++)
+                if (type_w[i] == w && (int)(type_cg[i] >> 30) == g) { type_cg[i] += c; hit = true; break; }
+            if (!hit) { type_w.push_back(w); type_cg.push_back(((unsigned int)g << 30) | c); }
+            n_bound += (g == COALGPU_GAMMA_C) ? 2ll * c : c;
+        }
+        type_off[t + 1] = (int)type_w.size();
+        // probabilitySamplePermutation, ProposalEngine.cpp:88-118
+        for (int g = 0; g < 3; g++) {
+            unsigned int tot = 0;
+            for (size_t i = start; i < type_w.size(); i++) if ((int)(type_cg[i] >> 30) == g) { const unsigned int c = type_cg[i] & 0x3fffffffu; tot += c; perm += std::lgamma((double)c + 1.0); }
+            perm -= std::lgamma((double)tot + 1.0);
+        }
+    }
+    if (type_off[1] == 0) { delete s; return fail(COALGPU_EINVAL, "first sampling time has no sequences"); }
+    if (n_bound < 1 || n_bound > 60000) { delete s; return fail(COALGPU_EINVAL, "lineage bound out of range (1..60000)"); }
+    const int n_max = (int)n_bound;
+
+    // HMM constants per (epoch, lineage count): ImportanceSampler.cpp:69-76, ConditionalSamplingHMM.cpp:36-226
+    std::vector<double> thetas(T), rrates(T);
+    for (int c = 0; c < T; c++) {
+        thetas[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_mu;
+        rrates[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_rho;
+    }
+    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, s->tab)) { delete s; return fail(COALGPU_EINVAL, "table construction failed"); }
+
+    std::vector<EpochConst> ep(T);
+    for (int c = 0; c < T; c++) {
+        const double V = p->viral[c];
+        EpochConst e{};
+        e.dN = p->driving_lambda * V;                 // ProposalEngine.cpp:657-663
+        e.dtheta = 4 * p->driving_mu * e.dN;
+        e.drho = 4 * p->driving_rho * e.dN;
+        e.dthA = e.dtheta * LA; e.dthB = e.dtheta * LB;
+        e.inv2Ntau = 1.0 / (2 * e.dN * p->tau);
+        ep[c] = e;
+    }
+    std::vector<GridConst> grid((size_t)T * G);
+    for (int c = 0; c < T; c++) {
+        const double V = p->viral[c];
+        size_t g = 0;
+        for (int i = 0; i < p->n_mu; i++) for (int j = 0; j < p->n_rho; j++) for (int z = 0; z < p->n_lambda; z++, g++) {
+            GridConst gc;
+            const double N = p->lambda[z] * V;        // ProposalEngine.cpp:462-464
+            gc.theta = 4 * p->mu[i] * p->lambda[z] * V;
+            gc.rho = 4 * p->rho[j] * p->lambda[z] * V;
+            gc.inv2Ntau = 1.0 / (2 * N * p->tau);
+            gc.log_theta = std::log(gc.theta); gc.log_rho = std::log(gc.rho); gc.log_2Ntau = std::log(2 * N * p->tau);
+            grid[(size_t)c * G + g] = gc;
+        }
+    }
+    std::vector<double> lfact(n_max + 2);
+    for (int i = 0; i < n_max + 2; i++) lfact[i] = std::lgamma((double)i + 1.0);
+    std::vector<double> times(p->times, p->times + T);
+
+    DevProblem& P = s->P;
+    const TableLayout& lay = s->tab.lay;
+    P.T = T; P.LA = LA; P.LB = LB; P.Ltot = LA + LB; P.G = G;
+    P.n_max = n_max;
+    P.kmax = ((n_max + 2 + 31) / 32) * 32;
+    P.pvmax = std::max(LA + LB + 4, std::max(LA, LB) + P.kmax + 1);
+    P.pvmax = (P.pvmax + 1) & ~1;
+    P.row_doubles = lay.row_doubles;
+    P.off_yw = lay.off_yw; P.off_zlow = lay.off_zlow; P.off_g = lay.off_g; P.off_zdiag = lay.off_zdiag;
+    P.off_EA = lay.off_EA; P.off_EB = lay.off_EB; P.off_wEA = lay.off_wEA; P.off_wEB = lay.off_wEB;
+    P.maskA = maskA; P.maskB = maskB;
+    P.perm_const = perm;
+    P.pow2negLA = std::ldexp(1.0, -LA); P.pow2negLB = std::ldexp(1.0, -LB); P.pow2negL = std::ldexp(1.0, -(LA + LB));
+    double wsum = 0; for (int i = 0; i < kQ; i++) wsum += s->tab.w[i];
+    P.wsum = wsum;
+
+    int rc = 0;
+    double* d_rows; int* d_set; double* d_times; EpochConst* d_ep; GridConst* d_grid; double* d_lf; int* d_toff;
+    unsigned long long* d_tw; unsigned int* d_tcg;
+#define UP(vec, ptr) do { rc = upload(vec, &ptr); if (rc) { coalgpu_destroy(s); return rc; } s->allocs.push_back(ptr); } while (0)
+    UP(s->tab.rows, d_rows); UP(s->tab.set_of_epoch, d_set); UP(times, d_times); UP(ep, d_ep); UP(grid, d_grid);
+    UP(lfact, d_lf); UP(type_off, d_toff); UP(type_w, d_tw); UP(type_cg, d_tcg);
+#undef UP
+    P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf;
+    P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
+    CU_OK(cudaMemcpyToSymbol(c_w, s->tab.w.data(), sizeof(double) * kQ));
+    CU_OK(cudaMalloc((void**)&s->d_counters, 4 * sizeof(unsigned long long)));
+    s->allocs.push_back(s->d_counters);
+    CU_OK(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
+
+    // launch geometry: persistent CTAs of 4 warps, as many as shared memory and registers allow
+    s->warp_bytes = (int)history_warp_bytes(P.kmax, P.pvmax, P.Ltot);
+    s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta;
+    while (s->smem_bytes > 227 * 1024 && s->warps_per_cta > 1) { s->warps_per_cta /= 2; s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta; }
+    if (s->smem_bytes > 227 * 1024) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for one warp's shared-memory state"); }
+    CU_OK(cudaFuncSetAttribute(history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    int occ = 0;
+    CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, history_kernel, s->warps_per_cta * 32, s->smem_bytes));
+    if (occ < 1) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, "history kernel does not fit on an SM"); }
+    s->grid = prop.multiProcessorCount * occ;
+    s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
+    *out = s;
+    return 0;
+}
+
+int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
+                   double* d_weights, double* d_tmrca, double* d_lineages, uint32_t* d_nevents,
+                   coalgpu_event* d_events, uint32_t* d_event_counts, uint32_t n_trace, uint32_t max_events) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
+    if (n == 0) return 0;
+    CU_OK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_OK(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st));
+    SampleArgs a{};
+    a.seed = seed; a.first = first; a.n = n;
+    a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
+    a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
+    a.counters = s->d_counters;
+    const unsigned long long warps_needed = n;
+    int grid = s->grid;
+    const unsigned long long ctas_needed = (warps_needed + s->warps_per_cta - 1) / s->warps_per_cta;
+    if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
+    history_kernel<<<grid, s->warps_per_cta * 32, s->smem_bytes, st>>>(s->P, a, s->warp_bytes);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    return 0;
+}
+
+int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
+    CU_OK(cudaSetDevice(s->device));
+    unsigned long long h[4];
+    CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    if (n_events) *n_events = h[1];
+    if (n_pismc) *n_pismc = h[2];
+    if (n_overflow) *n_overflow = h[3];
+    return 0;
+}
+
+int coalgpu_partials(coalgpu_sampler* s, uint64_t n, void* stream, const double* d_weights, const double* d_tmrca,
+                     const double* d_lineages, double* d_partials) {
+    if (!s || !d_weights || !d_tmrca || !d_lineages || !d_partials) return fail(COALGPU_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nstat = 3 + s->T;
+    int nb = (int)std::min<uint64_t>((n + 255) / 256, 64);
+    if (nb < 1) nb = 1;
+    const size_t need = (size_t)nstat * s->G * nb * 2 * sizeof(double);
+    if (need > s->block_partials_cap) {
+        if (s->d_block_partials) CU_OK(cudaFree(s->d_block_partials));
+        s->d_block_partials = nullptr; s->block_partials_cap = 0;
+        CU_OK(cudaMalloc((void**)&s->d_block_partials, need));
+        s->block_partials_cap = need;
+    }
+    dim3 grid(nb, s->G, nstat);
+    lse_partial_kernel<<<grid, 256, 0, st>>>(n, s->G, s->T, d_weights, d_tmrca, d_lineages, s->d_block_partials);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    const int total = nstat * s->G;
+    lse_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(nb, total, s->d_block_partials, d_partials);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    return 0;
+}
+
+int coalgpu_finalize(int32_t G, int32_t T, const double* hp, coalgpu_result* r) {
+    if (!hp || !r || !r->likelihood || !r->likelihood_sq || !r->tmrca || !r->lineages) return fail(COALGPU_EINVAL, "null argument");
+    auto lse = [&](int stat, int g) { const double* q = hp + ((size_t)stat * G + g) * 2; return q[0] + std::log(q[1]); };
+    for (int g = 0; g < G; g++) {
+        const double like = lse(0, g);
+        r->likelihood[g] = like;                      // log SUM (SamplerOutput.cpp:131 subtracts num_samples == 0)
+        r->likelihood_sq[g] = lse(1, g);
+        r->tmrca[g] = lse(2, g) - like;               // SamplerOutput.cpp:120-121
+        for (int l = 0; l < T; l++) r->lineages[(size_t)l * G + g] = lse(3 + l, g) - like;   // :126-129
+        if (r->ess) r->ess[g] = std::exp(2 * like - r->likelihood_sq[g]);
+    }
+    return 0;
+}
+
+int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
+    if (!problem || !result) return fail(COALGPU_EINVAL, "null argument");
+    if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
+    coalgpu_sampler* s = nullptr;
+    int rc = coalgpu_create(problem, Q, device, &s);
+    if (rc) return rc;
+    const int G = s->G, T = s->T, nstat = 3 + T;
+    // chunk the batch so that the per-history weight matrix stays below ~2 GiB
+    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n_samples, (2ull << 30) / ((size_t)(G + T + 1) * 8)));
+    double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<double> hp((size_t)nstat * G * 2), acc((size_t)nstat * G * 2);
+    for (size_t i = 0; i < acc.size(); i += 2) { acc[i] = -INFINITY; acc[i + 1] = 0.0; }
+    auto cleanup = [&]() {
+        if (d_w) cudaFree(d_w); if (d_t) cudaFree(d_t); if (d_l) cudaFree(d_l); if (d_p) cudaFree(d_p);
+        if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+        coalgpu_destroy(s);
+    };
+#define RS_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return fail(COALGPU_ECUDA, m); } } while (0)
+    RS_OK(cudaMalloc((void**)&d_w, chunk * G * sizeof(double)));
+    RS_OK(cudaMalloc((void**)&d_t, chunk * sizeof(double)));
+    RS_OK(cudaMalloc((void**)&d_l, chunk * T * sizeof(double)));
+    RS_OK(cudaMalloc((void**)&d_p, hp.size() * sizeof(double)));
+    RS_OK(cudaEventCreate(&e0)); RS_OK(cudaEventCreate(&e1));
+    RS_OK(cudaEventRecord(e0, 0));
+    for (uint64_t first = 0; first < n_samples; first += chunk) {
+        const uint64_t n = std::min<uint64_t>(chunk, n_samples - first);
+        rc = coalgpu_sample(s, seed, first, n, nullptr, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0);
+        if (!rc) rc = coalgpu_partials(s, n, nullptr, d_w, d_t, d_l, d_p);
+        if (rc) { std::string m = g_err; cleanup(); return fail(rc, m); }
+        RS_OK(cudaMemcpy(hp.data(), d_p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < acc.size(); i += 2) {   // (max, sum) merge
+            const double m1 = acc[i], m2 = hp[i], mm = std::max(m1, m2);
+            if (mm > -INFINITY) acc[i + 1] = acc[i + 1] * std::exp(m1 - mm) + hp[i + 1] * std::exp(m2 - mm);
+            acc[i] = mm;
+        }
+    }
+    RS_OK(cudaEventRecord(e1, 0));
+    RS_OK(cudaEventSynchronize(e1));
+    float ms = 0; RS_OK(cudaEventElapsedTime(&ms, e0, e1));
+#undef RS_OK
+    uint64_t nev = 0, npi = 0, nov = 0;
+    rc = coalgpu_counters(s, &nev, &npi, &nov);
+    if (!rc) rc = coalgpu_finalize(G, T, acc.data(), result);
+    result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
+    std::string m = g_err;
+    cleanup();
+    if (rc) return fail(rc, m);
+    if (nov) return fail(COALGPU_EOVERFLOW, "a history outgrew the type-store capacity");
+    return 0;
+}
+
+int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* w, double* y, double* z, double* EA, double* EB) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
+    if (time_idx < 0 || time_idx >= s->T || n_all < 1 || n_all > s->tab.n_max) return fail(COALGPU_EINVAL, "table index out of range");
+    const TableLayout& lay = s->tab.lay;
+    const int set = s->tab.set_of_epoch[time_idx];
+    const double* row = s->tab.row(set, n_all);
+    const double* yy = s->tab.y.data() + ((size_t)set * s->tab.n_max + (n_all - 1)) * kQ;
+    if (w) std::memcpy(w, s->tab.w.data(), sizeof(double) * kQ);
+    if (y) std::memcpy(y, yy, sizeof(double) * kQ);
+    if (z) for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
+        z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? s->tab.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
+    if (EA) std::memcpy(EA, row + lay.off_EA, sizeof(double) * kQ * (s->LA + 1));
+    if (EB) std::memcpy(EB, row + lay.off_EB, sizeof(double) * kQ * (s->LB + 1));
+    return 0;
+}
+
+int coalgpu_pismc_classes(coalgpu_sampler* s, int64_t nq, const uint8_t* gamma, const int32_t* n_all, const int32_t* time_idx,
+                          const int64_t* offs, const int32_t* counts, const int32_t* dA, const int32_t* dB, double* out_pi) {
+    if (!s || !gamma || !n_all || !time_idx || !offs || !out_pi) return fail(COALGPU_EINVAL, "null argument");
+    if (nq <= 0) return 0;
+    for (int64_t q = 0; q < nq; q++) {
+        if (offs[q + 1] - offs[q] > s->LA + s->LB + 2) return fail(COALGPU_EINVAL, "more classes than dA+dB sums");
+        if (time_idx[q] < 0 || time_idx[q] >= s->T || n_all[q] < 1 || n_all[q] > s->tab.n_max) return fail(COALGPU_EINVAL, "query outside the table range");
+        if (gamma[q] > 2) return fail(COALGPU_EINVAL, "bad gamma");
+    }
+    CU_OK(cudaSetDevice(s->device));
+    const int64_t ncls = offs[nq];
+    unsigned char* d_g = nullptr; int *d_n = nullptr, *d_t = nullptr, *d_c = nullptr, *d_a = nullptr, *d_b = nullptr; long long* d_o = nullptr; double* d_out = nullptr;
+    std::vector<void*> tmp;
+    auto freeall = [&]() { for (void* p : tmp) cudaFree(p); };
+#define TMP(ptr, bytes, src) do { cudaError_t _e = cudaMalloc((void**)&ptr, std::max<size_t>(bytes, 8)); if (_e == cudaSuccess) { tmp.push_back(ptr); if (src) _e = cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); } if (_e != cudaSuccess) { freeall(); return fail(COALGPU_ECUDA, cudaGetErrorString(_e)); } } while (0)
+    TMP(d_g, (size_t)nq, gamma); TMP(d_n, (size_t)nq * 4, n_all); TMP(d_t, (size_t)nq * 4, time_idx);
+    TMP(d_o, (size_t)(nq + 1) * 8, offs); TMP(d_c, (size_t)ncls * 4, counts); TMP(d_a, (size_t)ncls * 4, dA); TMP(d_b, (size_t)ncls * 4, dB);
+    TMP(d_out, (size_t)nq * 8, (const void*)nullptr);
+#undef TMP
+    const int grid = (int)std::min<int64_t>((nq + 7) / 8, 148 * 8);
+    pismc_classes_kernel<<<grid, 128, s->k2_smem>>>(s->P, (long long)nq, d_g, d_n, d_t, d_o, d_c, d_a, d_b, d_out);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out_pi, d_out, (size_t)nq * 8, cudaMemcpyDeviceToHost);
+    freeall();
+    if (e != cudaSuccess) return fail(COALGPU_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Device-side data layout and kernels of the importance-sampling likelihood path (sm_100a).
+//
+// One WARP draws one coalescent history (ProposalEngine::calculateLikelihood,
+// /root/reference/src/ProposalEngine.cpp:643-861). The ancestral configuration (TypeContainer,
+// TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed haplotypes; the
+// candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:
+//  * marginal (one-locus) conditional sampling probabilities collapse to a dot product of a distance
+//    histogram with a precomputed weight vector (ConditionalSamplingHMM.cpp:332-370),
+//  * two-locus ones run the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) with the
+//    interval axis split over a power-of-two lane group and the structured transition matrix folded
+//    into running prefix sums exchanged by warp shuffles.
+// fp64 throughout; no tensor cores (the recursion is a diagonal + rank-1 update, not a contraction).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/coalgpu.h"
+
+namespace coalgpu {
+
+constexpr int kQd = 16;
+constexpr unsigned kFull = 0xffffffffu;
+
+// per-epoch driving constants (ProposalEngine.cpp:657-665, 759-765)
+struct EpochConst {
+    double dN, dtheta, drho, dthA, dthB, inv2Ntau;   // inv2Ntau = 1/(2*dN*tau)
+    double pad0, pad1;
+};
+
+// per (epoch, grid point) target constants (ProposalEngine.cpp:462-465)
+struct GridConst {
+    double theta, rho, inv2Ntau, log_theta, log_rho, log_2Ntau;
+};
+
+struct DevProblem {
+    int T, LA, LB, Ltot, G;
+    int n_max, kmax, row_doubles, pvmax;
+    int off_yw, off_zlow, off_g, off_zdiag, off_EA, off_EB, off_wEA, off_wEB;
+    unsigned long long maskA, maskB;
+    double perm_const;        // sum_t probabilitySamplePermutation (ProposalEngine.cpp:88-118,822-828)
+    double pow2negLA, pow2negLB, pow2negL, wsum;
+    const double* rows;       // [n_sets][n_max][row_doubles]
+    const int* set_of_epoch;  // [T]
+    const double* times;      // [T]
+    const EpochConst* ep;     // [T]
+    const GridConst* grid;    // [T][G]
+    const double* lfact;      // [n_max+2] log factorials
+    const int* type_off;      // [T+1]
+    const unsigned long long* type_w;
+    const unsigned int* type_cg;   // count | gamma << 30, duplicates merged, insertion order
+};
+
+struct SampleArgs {
+    unsigned long long seed, first, n;
+    double* weights;          // [n][G]
+    double* tmrca;            // [n]
+    double* lineages;         // [n][T]
+    unsigned int* nevents;    // [n]
+    coalgpu_event* events;    // [n_trace][max_events]
+    unsigned int* event_counts;
+    unsigned int n_trace, max_events;
+    unsigned long long* counters;   // [0] next history, [1] events, [2] pismc, [3] overflow
+};
+
+__constant__ double c_w[kQd];   // interval weights (ConditionalSamplingHMM.cpp:63-71)
+
+// ---- Philox4x32-10 ------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_block(unsigned long long seed, unsigned long long hist, unsigned long long blk, unsigned int out[4]) {
+    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+    unsigned int c0 = (unsigned int)hist, c1 = (unsigned int)(hist >> 32), c2 = (unsigned int)blk, c3 = (unsigned int)(blk >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// draw k of history hist -> (0,1), 53 bits
+__device__ __forceinline__ double philox_uniform(unsigned long long seed, unsigned long long hist, unsigned long long k) {
+    unsigned int o[4];
+    philox_block(seed, hist, k >> 1, o);
+    const unsigned int lo = (k & 1) ? o[2] : o[0], hi = (k & 1) ? o[3] : o[1];
+    const unsigned long long bits = (((unsigned long long)hi << 32) | lo) >> 11;
+    return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ---- warp helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned int warp_sum_u(unsigned int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace coalgpu

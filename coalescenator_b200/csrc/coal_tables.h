@@ -1,0 +1,46 @@
+// Host-side construction of the conditional-sampling HMM constants, in the layout the kernels read.
+// Follows ConditionalSamplingHMM.cpp:36-226 of the reference in the same floating-point operation
+// order, so the emission tables are bit-identical to the reference's; the transition
+// matrix is kept in the structured form z(i,j) = {zlow[j] (i>j), w[j]*g[i] (i<j), zdiag[i]} that the
+// reference's formulas have (ConditionalSamplingHMM.cpp:110-173), which turns the interval-to-interval
+// step of the forward pass from O(Q^2) into O(Q).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace coalgpu {
+
+constexpr int kQ = 16;   // quadrature intervals (main.cpp:103 hard-codes 16)
+
+struct TableLayout {
+    int LA = 0, LB = 0;
+    int off_yw = 0, off_zlow = kQ, off_g = 2 * kQ, off_zdiag = 3 * kQ;
+    int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;
+    int row_doubles = 0;   // multiple of 2 (16-byte rows for bulk copies)
+    void init(int la, int lb) {
+        LA = la; LB = lb;
+        off_EB = off_EA + kQ * (LA + 1);
+        off_wEA = off_EB + kQ * (LB + 1);
+        off_wEB = off_wEA + (LA + 1);
+        row_doubles = off_wEB + (LB + 1);
+        row_doubles = (row_doubles + 1) & ~1;
+    }
+};
+
+struct HostTables {
+    TableLayout lay;
+    int n_max = 0;                 // rows for n_all = 1..n_max
+    int n_sets = 0;                // distinct (theta, r) epochs
+    std::vector<int> set_of_epoch; // [T]
+    std::vector<double> w;         // [kQ] interval weights
+    std::vector<double> quad;      // [kQ+1]
+    std::vector<double> rows;      // [n_sets][n_max][row_doubles]
+    std::vector<double> y;         // [n_sets][n_max][kQ] plain y (for coalgpu_tables)
+    const double* row(int set, int n_all) const { return rows.data() + ((size_t)set * n_max + (n_all - 1)) * lay.row_doubles; }
+};
+
+// thetas[c] = 4*lambda_d*V[c]*mu_d, r_rates[c] = 4*lambda_d*V[c]*rho_d (ImportanceSampler.cpp:69-76)
+bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
+                  const std::vector<double>& r_rates, HostTables& out);
+
+}  // namespace coalgpu

@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference's sampler interface, bound to libcoalgpu.so over its C ABI.
+
+Reference interface mirrored here (same names, argument meaning and result fields):
+  ImportanceSampler::runSampler(Sample*, ModelParameters, num_iterations, num_threads,
+                                quadrature_points, seed) -> SamplerOutput<double>
+      /root/reference/src/ImportanceSampler.hpp:53, ImportanceSampler.cpp:110-145
+  SamplerOutput<double>::likelihood() / likelihoodSq() / tmrca() / lineages_remaining()
+      /root/reference/src/SamplerOutput.hpp:44-52, read at main.cpp:285-306
+
+There is no CPU path: if the CUDA library is missing or no B200 is visible these calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from .problem import Problem
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcoalgpu.so")
+
+EVENT_DTYPE = np.dtype([("chosen_word", "<u8"), ("aux_word", "<u8"), ("chosen_gamma", "u1"), ("kind", "u1"),
+                        ("epoch", "u1"), ("site", "u1"), ("n_before", "<u4")])
+
+
+class CoalGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"coalgpu error {code}: {msg}")
+        self.code = code
+
+
+class _CProblem(C.Structure):
+    _fields_ = [("T", C.c_int32), ("LA", C.c_int32), ("LB", C.c_int32),
+                ("times", C.POINTER(C.c_double)), ("viral", C.POINTER(C.c_double)),
+                ("tau", C.c_double), ("driving_mu", C.c_double), ("driving_lambda", C.c_double), ("driving_rho", C.c_double),
+                ("n_mu", C.c_int32), ("n_rho", C.c_int32), ("n_lambda", C.c_int32),
+                ("mu", C.POINTER(C.c_double)), ("rho", C.POINTER(C.c_double)), ("lam", C.POINTER(C.c_double)),
+                ("type_offsets", C.POINTER(C.c_int32)), ("type_gamma", C.POINTER(C.c_uint8)),
+                ("type_words", C.POINTER(C.c_uint64)), ("type_counts", C.POINTER(C.c_uint32))]
+
+
+class _CResult(C.Structure):
+    _fields_ = [("likelihood", C.POINTER(C.c_double)), ("likelihood_sq", C.POINTER(C.c_double)),
+                ("tmrca", C.POINTER(C.c_double)), ("lineages", C.POINTER(C.c_double)), ("ess", C.POINTER(C.c_double)),
+                ("n_histories", C.c_uint64), ("n_events", C.c_uint64), ("n_pismc", C.c_uint64),
+                ("seconds_device", C.c_double)]
+
+
+_lib = None
+
+EXPORTS = ["coalgpu_run_sampler", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
+           "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
+           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version"]
+
+
+def load_library():
+    """dlopen libcoalgpu.so; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.coalgpu_last_error.restype = C.c_char_p
+        L.coalgpu_version.restype = C.c_char_p
+        L.coalgpu_launch_count.restype = C.c_uint64
+        L.coalgpu_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.coalgpu_partials.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.coalgpu_create.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.coalgpu_destroy.argtypes = [C.c_void_p]
+        L.coalgpu_destroy.restype = None
+        L.coalgpu_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.coalgpu_run_sampler.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
+        L.coalgpu_finalize.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.coalgpu_tables.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
+        L.coalgpu_pismc_classes.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CoalGpuError(rc, load_library().coalgpu_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class _PackedProblem:
+    """numpy arrays behind a coalgpu_problem struct (kept alive for the duration of the calls)."""
+
+    def __init__(self, p: Problem):
+        self.times = np.asarray(p.times, dtype=np.float64)
+        self.viral = np.asarray(p.viral, dtype=np.float64)
+        self.mu = np.asarray(p.target_mu, dtype=np.float64)
+        self.rho = np.asarray(p.target_rho, dtype=np.float64)
+        self.lam = np.asarray(p.target_lambda, dtype=np.float64)
+        offs, g, w, c = [0], [], [], []
+        for tp in p.types:
+            for (gg, ww, cc) in tp:
+                g.append(gg); w.append(ww); c.append(cc)
+            offs.append(len(g))
+        self.offs = np.asarray(offs, dtype=np.int32)
+        self.g = np.asarray(g, dtype=np.uint8)
+        self.w = np.asarray(w, dtype=np.uint64)
+        self.c = np.asarray(c, dtype=np.uint32)
+        self.struct = _CProblem(p.T, p.LA, p.LB, _dp(self.times), _dp(self.viral), p.tau, p.driving_mu,
+                                p.driving_lambda, p.driving_rho, len(self.mu), len(self.rho), len(self.lam),
+                                _dp(self.mu), _dp(self.rho), _dp(self.lam),
+                                self.offs.ctypes.data_as(C.POINTER(C.c_int32)), self.g.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                self.w.ctypes.data_as(C.POINTER(C.c_uint64)), self.c.ctypes.data_as(C.POINTER(C.c_uint32)))
+
+
+@dataclasses.dataclass
+class SamplerOutput:
+    """SamplerOutput<double> of the reference (SamplerOutput.hpp:40-69), log domain, arrays shaped
+    (n_mu, n_rho, n_lambda); lineages_remaining has a leading axis over sampling times."""
+    likelihood: np.ndarray
+    likelihoodSq: np.ndarray
+    tmrca: np.ndarray
+    lineages_remaining: np.ndarray
+    ess: np.ndarray
+    n_histories: int = 0
+    n_events: int = 0
+    n_pismc: int = 0
+    seconds_device: float = 0.0
+
+    def standard_error(self):
+        """Monte-Carlo standard error of `likelihood` (log domain, delta method) from the two sums the
+        reference prints (main.cpp:240,306): var(log mean w) ~ (sum w^2 / (sum w)^2 - 1/N)."""
+        rel = np.exp(self.likelihoodSq - 2 * self.likelihood) - 1.0 / max(self.n_histories, 1)
+        return np.sqrt(np.maximum(rel, 0.0))
+
+
+def _result_arrays(p: Problem):
+    G, T = p.G, p.T
+    return (np.zeros(G), np.zeros(G), np.zeros(G), np.zeros(T * G), np.zeros(G))
+
+
+def _to_output(p: Problem, arrs, res: Optional[_CResult] = None) -> SamplerOutput:
+    shape = (len(p.target_mu), len(p.target_rho), len(p.target_lambda))
+    like, likesq, tm, lin, ess = arrs
+    out = SamplerOutput(like.reshape(shape), likesq.reshape(shape), tm.reshape(shape), lin.reshape((p.T,) + shape), ess.reshape(shape))
+    if res is not None:
+        out.n_histories, out.n_events, out.n_pismc = int(res.n_histories), int(res.n_events), int(res.n_pismc)
+        out.seconds_device = float(res.seconds_device)
+    return out
+
+
+class ImportanceSampler:
+    """Drop-in for the reference's ImportanceSampler (ImportanceSampler.hpp:42-53)."""
+
+    def run_sampler(self, sample: Problem, num_iterations: int, num_threads: int = 1, quadrature_points: int = 16,
+                    seed: int = 0, device: int = 0) -> SamplerOutput:
+        """runSampler (ImportanceSampler.cpp:110-145) through the C ABI: host buffers in and out, blocking.
+        `num_threads` is accepted for signature parity and ignored (the GPU draws all histories)."""
+        L = load_library()
+        pk = _PackedProblem(sample)
+        arrs = _result_arrays(sample)
+        res = _CResult(_dp(arrs[0]), _dp(arrs[1]), _dp(arrs[2]), _dp(arrs[3]), _dp(arrs[4]), 0, 0, 0, 0.0)
+        _check(L.coalgpu_run_sampler(C.byref(pk.struct), int(num_iterations), int(quadrature_points), int(seed), int(device), C.byref(res)))
+        return _to_output(sample, arrs, res)
+
+    runSampler = run_sampler
+
+
+class DeviceSampler:
+    """Staged API: tables + problem resident on one GPU; histories stay in HBM as torch tensors."""
+
+    def __init__(self, problem: Problem, quadrature_points: int = 16, device: int = 0):
+        self.L = load_library()
+        self.problem = problem
+        self.device = int(device)
+        self._pk = _PackedProblem(problem)
+        h = C.c_void_p()
+        _check(self.L.coalgpu_create(C.byref(self._pk.struct), int(quadrature_points), self.device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.coalgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def alloc(self, n: int, n_trace: int = 0, max_events: int = 0):
+        import torch
+        dev = torch.device("cuda", self.device)
+        p = self.problem
+        buf = dict(weights=torch.empty((n, p.G), dtype=torch.float64, device=dev),
+                   tmrca=torch.empty((n,), dtype=torch.float64, device=dev),
+                   lineages=torch.empty((n, p.T), dtype=torch.float64, device=dev),
+                   nevents=torch.zeros((n,), dtype=torch.int32, device=dev),
+                   partials=torch.empty((3 + p.T, p.G, 2), dtype=torch.float64, device=dev))
+        if n_trace:
+            buf["events"] = torch.zeros((n_trace, max_events, EVENT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+            buf["event_counts"] = torch.zeros((n_trace,), dtype=torch.int32, device=dev)
+        return buf
+
+    def sample(self, buf, seed: int, first: int, n: int, stream=None):
+        """Draw histories [first, first+n) into buf (asynchronous on `stream` / torch's current stream)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        ev = buf.get("events")
+        _check(self.L.coalgpu_sample(self._h, int(seed), int(first), int(n), C.c_void_p(stream),
+                                     buf["weights"].data_ptr(), buf["tmrca"].data_ptr(), buf["lineages"].data_ptr(),
+                                     buf["nevents"].data_ptr(), ev.data_ptr() if ev is not None else None,
+                                     buf["event_counts"].data_ptr() if ev is not None else None,
+                                     ev.shape[0] if ev is not None else 0, ev.shape[1] if ev is not None else 0))
+
+    def partials(self, buf, n: int, stream=None):
+        """(max, sum exp) partials of the n histories in buf -> buf['partials'] ([3+T, G, 2], on device)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self.L.coalgpu_partials(self._h, int(n), C.c_void_p(stream), buf["weights"].data_ptr(), buf["tmrca"].data_ptr(),
+                                       buf["lineages"].data_ptr(), buf["partials"].data_ptr()))
+        return buf["partials"]
+
+    def finalize(self, partials_host: np.ndarray, n_histories: int = 0) -> SamplerOutput:
+        p = self.problem
+        hp = np.ascontiguousarray(partials_host, dtype=np.float64)
+        arrs = _result_arrays(p)
+        res = _CResult(_dp(arrs[0]), _dp(arrs[1]), _dp(arrs[2]), _dp(arrs[3]), _dp(arrs[4]), 0, 0, 0, 0.0)
+        _check(self.L.coalgpu_finalize(p.G, p.T, hp.ctypes.data_as(C.c_void_p), C.byref(res)))
+        out = _to_output(p, arrs)
+        out.n_histories = n_histories
+        return out
+
+    def counters(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.L.coalgpu_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value)
+
+    def events(self, buf) -> List[np.ndarray]:
+        """Traced event records per history (the integer history encoding)."""
+        ev = buf["events"].cpu().numpy()
+        cnt = buf["event_counts"].cpu().numpy()
+        out = []
+        for h in range(ev.shape[0]):
+            rec = ev[h].reshape(-1).view(EVENT_DTYPE)
+            out.append(rec[:min(int(cnt[h]), ev.shape[1])].copy())
+        return out
+
+    def tables(self, n_all: int, time_idx: int):
+        p = self.problem
+        Q = 16
+        w = np.zeros(Q); y = np.zeros(Q); z = np.zeros((Q, Q)); EA = np.zeros((Q, p.LA + 1)); EB = np.zeros((Q, p.LB + 1))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _check(self.L.coalgpu_tables(self._h, int(n_all), int(time_idx), vp(w), vp(y), vp(z), vp(EA), vp(EB)))
+        return dict(w=w, y=y, z=z, EA=EA, EB=EB)
+
+    def pismc_classes(self, gamma, n_all, time_idx, class_offsets, counts, dA, dB) -> np.ndarray:
+        """Batched piSMC from getDifferences output (ConditionalSamplingHMM.cpp:265-448) on the GPU."""
+        g = np.ascontiguousarray(gamma, dtype=np.uint8); n = np.ascontiguousarray(n_all, dtype=np.int32)
+        t = np.ascontiguousarray(time_idx, dtype=np.int32); o = np.ascontiguousarray(class_offsets, dtype=np.int64)
+        c = np.ascontiguousarray(counts, dtype=np.int32); a = np.ascontiguousarray(dA, dtype=np.int32); b = np.ascontiguousarray(dB, dtype=np.int32)
+        out = np.zeros(len(g), dtype=np.float64)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        _check(self.L.coalgpu_pismc_classes(self._h, len(g), vp(g), vp(n), vp(t), vp(o), vp(c), vp(a), vp(b), vp(out)))
+        return out
+
+
+def launch_count() -> int:
+    return int(load_library().coalgpu_launch_count())

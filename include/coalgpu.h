@@ -1,0 +1,143 @@
+/* coalgpu.h — C ABI of the B200 importance-sampling likelihood path.
+ *
+ * Drop-in boundary: the reference has no FFI layer; its seam is the C++ call
+ *     SamplerOutput<double> ImportanceSampler::runSampler(Sample*, ModelParameters,
+ *         uint num_iterations, uint num_threads, uint quadrature_points, uint seed);
+ *     (/root/reference/src/ImportanceSampler.hpp:53, ImportanceSampler.cpp:110; called once per
+ *      locus pair at main.cpp:281-283, results read at main.cpp:285-306)
+ * `coalgpu_run_sampler` replaces exactly that call. Everything else here is the same work split
+ * into stages so a caller can keep histories on the device, shard them over GPUs and combine the
+ * per-GPU partial sums itself (coalescenator_b200/distributed.py does it with one NCCL exchange).
+ *
+ * Plain C types only. All functions return 0 on success or a negative COALGPU_E* code and never
+ * abort; coalgpu_last_error() describes the last failure on the calling thread. The library is
+ * CUDA-only: without a usable device every compute entry point fails with COALGPU_ENODEV — there
+ * is no CPU fallback.
+ */
+#ifndef COALGPU_H
+#define COALGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COALGPU_EINVAL   (-1)   /* bad argument / unsupported problem shape          */
+#define COALGPU_ENODEV   (-2)   /* no CUDA device / wrong architecture               */
+#define COALGPU_ECUDA    (-3)   /* CUDA runtime error (see coalgpu_last_error)       */
+#define COALGPU_ENOMEM   (-4)
+#define COALGPU_EOVERFLOW (-5)  /* a history outgrew the per-history state capacity  */
+
+#define COALGPU_GAMMA_A 0       /* lineage ancestral at locus A only  (i,*) */
+#define COALGPU_GAMMA_B 1       /* lineage ancestral at locus B only  (*,j) */
+#define COALGPU_GAMMA_C 2       /* lineage ancestral at both loci     (i,j) */
+
+/* One locus pair: the reference's Sample (Sample.hpp:44-63) + ModelParameters (Utils.hpp:157-166),
+ * flattened. Haplotypes are bit-packed: locus A site s = bit s, locus B site s = bit LA+s
+ * (LA+LB <= 64); the reference keeps vector<bool> with locus A first (ProposalEngine.cpp:596-640). */
+typedef struct coalgpu_problem {
+    int32_t T, LA, LB;             /* sampling times, segregating sites per locus                */
+    const double* times;           /* [T] ascending; times[0] is unused (ProposalEngine.cpp:694) */
+    const double* viral;           /* [T] viral loads; N = lambda * viral (main.cpp:229)          */
+    double tau;                    /* generation time                                            */
+    double driving_mu, driving_lambda, driving_rho;
+    int32_t n_mu, n_rho, n_lambda; /* target grid; G = n_mu*n_rho*n_lambda                        */
+    const double* mu;              /* [n_mu]                                                     */
+    const double* rho;             /* [n_rho] already multiplied by distance+1 (main.cpp:260-271) */
+    const double* lambda;          /* [n_lambda]                                                 */
+    const int32_t* type_offsets;   /* [T+1] ranges of the arrays below per sampling time         */
+    const uint8_t* type_gamma;     /* COALGPU_GAMMA_*                                            */
+    const uint64_t* type_words;
+    const uint32_t* type_counts;
+} coalgpu_problem;
+
+/* What SamplerOutput<double> holds after sumSamples (SamplerOutput.cpp:115-133), log domain, grid
+ * index g = (i_mu*n_rho + i_rho)*n_lambda + i_lambda (the loop order of main.cpp:288-306):
+ *   likelihood[g]   = log sum_h w_h            (a log SUM, not a mean: ImportanceSampler.cpp:141)
+ *   likelihood_sq[g]= log sum_h w_h^2
+ *   tmrca[g]        = log( sum_h w_h t_h / sum_h w_h )
+ *   lineages[l*G+g] = log( sum_h w_h n_{h,l} / sum_h w_h ),  l < T
+ * plus diagnostics the reference leaves to the user: ess[g] = exp(2*likelihood - likelihood_sq). */
+typedef struct coalgpu_result {
+    double* likelihood;     /* [G]   caller-allocated */
+    double* likelihood_sq;  /* [G]   */
+    double* tmrca;          /* [G]   */
+    double* lineages;       /* [T*G] */
+    double* ess;            /* [G]   may be NULL */
+    uint64_t n_histories;   /* out */
+    uint64_t n_events;      /* out: backward events drawn over all histories */
+    uint64_t n_pismc;       /* out: pi_SMC evaluations */
+    double seconds_device;  /* out: CUDA-event time of the sampling + reduction kernels */
+} coalgpu_result;
+
+/* Integer history encoding: one record per backward event of a traced history.
+ * Same layout as the oracle's coalo_event. */
+typedef struct coalgpu_event {
+    uint64_t chosen_word;
+    uint64_t aux_word;
+    uint8_t chosen_gamma;
+    uint8_t kind;      /* 0 mutation, 1 coalescence within class, 2 C^A, 3 C^B, 4 recombination, 5 A^B */
+    uint8_t epoch;
+    uint8_t site;
+    uint32_t n_before;
+} coalgpu_event;
+
+typedef struct coalgpu_sampler coalgpu_sampler;
+
+/* ---- the drop-in: replaces ImportanceSampler::runSampler (ImportanceSampler.cpp:110-145) -------
+ * Blocking; host buffers in and out; uses CUDA device `device`. num_threads has no counterpart.
+ * Histories h = 0..n_samples-1 use Philox4x32-10 streams keyed by (seed, h). */
+int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t quadrature_points,
+                        uint64_t seed, int device, coalgpu_result* result);
+
+/* ---- staged API --------------------------------------------------------------------------------*/
+/* Build the HMM tables on the host (ConditionalSamplingHMM.cpp:36-226, same operation order),
+ * upload problem + tables to `device`. */
+int coalgpu_create(const coalgpu_problem* problem, uint32_t quadrature_points, int device, coalgpu_sampler** out);
+void coalgpu_destroy(coalgpu_sampler* s);
+
+/* Draw histories [first, first+n) on the sampler's device, asynchronously on `stream`
+ * (a cudaStream_t cast to void*, NULL = default stream). Device outputs (any may be NULL):
+ *   d_weights[n*G], d_tmrca[n], d_lineages[n*T], d_nevents[n] (uint32)
+ * Optional event trace for the first n_trace histories of this call: d_events[n_trace*max_events],
+ * d_event_counts[n_trace] (uint32). Replaces ProposalEngine::calculateLikelihood
+ * (ProposalEngine.cpp:643-861) + SamplerOutput::addSample (SamplerOutput.cpp:76-93). */
+int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
+                   double* d_weights, double* d_tmrca, double* d_lineages, uint32_t* d_nevents,
+                   coalgpu_event* d_events, uint32_t* d_event_counts, uint32_t n_trace, uint32_t max_events);
+
+/* Per-device partial log-sum-exp of n histories: d_partials[(3+T)*G*2] = (max, sum exp(x-max)) for
+ * the statistics w, 2w, w+log t, w+log n_l (SamplerOutput.cpp:76-93), layout [stat][g][2]. */
+int coalgpu_partials(coalgpu_sampler* s, uint64_t n, void* stream, const double* d_weights,
+                     const double* d_tmrca, const double* d_lineages, double* d_partials);
+
+/* Host-side finish: (max, sum) partials of ALL histories -> result grids (SamplerOutput.cpp:115-133). */
+int coalgpu_finalize(int32_t G, int32_t T, const double* h_partials, coalgpu_result* result);
+
+/* Work counters accumulated by coalgpu_sample since creation: events, pi_SMC evaluations, and the
+ * number of histories that overflowed the type-store capacity (must be 0). */
+int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow);
+
+/* ---- inner seams used by the parity tests ------------------------------------------------------*/
+/* Host copy of the table row for (n_all, time_idx): y[Q], z[Q*Q] (expanded from the structured
+ * form the kernels use), EA[Q*(LA+1)], EB[Q*(LB+1)], w[Q]. Any output may be NULL. */
+int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* w, double* y, double* z,
+                   double* EA, double* EB);
+
+/* Batched pi_SMC from class vectors (the output of TypeContainer::getDifferences,
+ * TypeContainer.cpp:748-894): query q has classes [class_offsets[q], class_offsets[q+1]).
+ * Host buffers; replaces ConditionalSamplingHMM::piSMC (ConditionalSamplingHMM.cpp:265-448). */
+int coalgpu_pismc_classes(coalgpu_sampler* s, int64_t n_queries, const uint8_t* gamma, const int32_t* n_all,
+                          const int32_t* time_idx, const int64_t* class_offsets, const int32_t* counts,
+                          const int32_t* dA, const int32_t* dB, double* out_pi);
+
+/* Kernel launches issued by this library on the calling process so far (bench.py's gpu_launches). */
+uint64_t coalgpu_launch_count(void);
+const char* coalgpu_last_error(void);
+const char* coalgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

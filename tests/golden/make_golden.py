@@ -1,0 +1,62 @@
+"""Generates the golden fixtures in this directory by RUNNING THE COMPILED, UNMODIFIED REFERENCE
+(oracle/_ref/coalref and coalref_trace, built from /root/reference/src by oracle/Makefile).
+Run here (the container that has /root/reference); the fixtures are committed, the reference is not.
+
+  python tests/golden/make_golden.py
+
+Fixtures:
+  <name>.coalprob        the problem (text format of coalescenator_b200/problem.py)
+  <name>.trace.gz        ld --wrap trace of the first few histories (oracle/README.md format):
+                         every getDifferences -> piSMC record, every lineage choice, every net state
+                         change, every per-history weight vector
+  <name>.result.json     ImportanceSampler::runSampler output for N histories, 1 thread, fixed seed
+"""
+import gzip
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from coalescenator_b200.problem import (make_config, sub_problem, synth_alignment, tile_loci, locus_pairs, grid_cfg3)  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+
+def cases():
+    out = {}
+    aln, loci, pairs = make_config(1)
+    out["cfg1_pair0"] = (sub_problem(aln, loci, *pairs[0]), 2, 300, 42)
+    aln, loci, pairs = make_config(2)
+    out["cfg2_pair0"] = (sub_problem(aln, loci, *pairs[0]), 1, 40, 7)
+    mu, rho, lam = grid_cfg3()
+    out["grid_pair5"] = (sub_problem(aln, loci, *pairs[5], target_mu=mu[::8], target_rho=[1e-5, 5e-5], target_lambda=lam[::8]), 1, 40, 9)
+    alnm, locim, pairsm = make_config(1, seed=3, p_missing=0.4)
+    out["missing_pair3"] = (sub_problem(alnm, locim, *pairsm[3]), 2, 200, 14)
+    aln5 = synth_alignment(5, 3, 4, 600, 20)
+    aln5.viral = [100.0, 37.0, 250.0]
+    l5 = tile_loci(aln5, 100)
+    pr5 = locus_pairs(l5)
+    # driving rho chosen so that 4*lambda*V*rho == 8 exactly in epoch 0: exercises the r == n branch
+    out["varV_req_n"] = (sub_problem(aln5, l5, *pr5[0], driving=(2.5e-5, 1000.0, 8.0 / (4 * 1000 * 100 * (pr5[0][2] + 1)))), 1, 60, 5)
+    return out
+
+
+def main():
+    for name, (p, n_trace, n_run, seed) in cases().items():
+        p.save(os.path.join(HERE, name + ".coalprob"))
+        tmp = os.path.join(HERE, name + ".trace")
+        O.run_reference(p, n_trace, seed, trace_path=tmp, trace_max=n_trace)
+        with open(tmp, "rb") as fi, gzip.GzipFile(tmp + ".gz", "wb", mtime=0) as fo:
+            fo.write(fi.read())
+        os.unlink(tmp)
+        res = O.run_reference(p, n_run, seed)
+        res.pop("seconds", None)
+        with open(os.path.join(HERE, name + ".result.json"), "w") as fh:
+            json.dump(res, fh, indent=0)
+        print(name, "LA", p.LA, "LB", p.LB, "T", p.T, "n", p.n_lineages(), "G", p.G, os.path.getsize(tmp + ".gz"), "bytes")
+
+
+if __name__ == "__main__":
+    main()

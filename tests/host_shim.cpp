@@ -1,0 +1,74 @@
+// CPU-side harness around the product's host code and the arithmetic cores its kernels use
+// (coalescenator_b200/csrc/coal_tables.cpp, coal_math.h), so they can be checked against the oracle
+// where no GPU exists. The lane-group split of the forward pass is emulated by evaluating the chunks
+// one after another and passing the prefixes along, exactly as the warp shuffles do.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../coalescenator_b200/csrc/coal_math.h"
+#include "../coalescenator_b200/csrc/coal_tables.h"
+
+using namespace coalgpu;
+
+extern "C" {
+
+struct hs_tables_t { HostTables tab; };
+
+void* hs_build(int LA, int LB, int n_max, int T, const double* thetas, const double* rrates) {
+    hs_tables_t* h = new hs_tables_t;
+    std::vector<double> th(thetas, thetas + T), rr(rrates, rrates + T);
+    if (!build_tables(16, LA, LB, n_max, th, rr, h->tab)) { delete h; return nullptr; }
+    return h;
+}
+void hs_free(void* p) { delete (hs_tables_t*)p; }
+
+int hs_tables(void* hp, int n_all, int time_idx, double* w, double* y, double* z, double* EA, double* EB) {
+    const HostTables& t = ((hs_tables_t*)hp)->tab;
+    const TableLayout& lay = t.lay;
+    const int set = t.set_of_epoch[time_idx];
+    const double* row = t.row(set, n_all);
+    std::memcpy(w, t.w.data(), sizeof(double) * kQ);
+    std::memcpy(y, t.y.data() + ((size_t)set * t.n_max + (n_all - 1)) * kQ, sizeof(double) * kQ);
+    for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
+        z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? t.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
+    std::memcpy(EA, row + lay.off_EA, sizeof(double) * kQ * (lay.LA + 1));
+    std::memcpy(EB, row + lay.off_EB, sizeof(double) * kQ * (lay.LB + 1));
+    return t.n_sets;
+}
+
+// pi_SMC from class vectors with the forward pass split into p chunks (p in {1,2,4,8,16})
+double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int32_t* cnt, const int32_t* dA, const int32_t* dB, int p) {
+    const HostTables& t = ((hs_tables_t*)hp)->tab;
+    const TableLayout& lay = t.lay;
+    const double* row = t.row(t.set_of_epoch[time_idx], n_all);
+    const double p2A = 1.0 / (double)(1ull << lay.LA), p2B = 1.0 / (double)(1ull << lay.LB);
+    double wsum = 0; for (int i = 0; i < kQ; i++) wsum += t.w[i];
+    if (gamma != 2) {
+        double num = 0; uint32_t ncomp = 0;
+        for (int k = 0; k < nH; k++) {
+            const int d = gamma == 0 ? dA[k] : dB[k];
+            if (d >= 0) { num += (double)cnt[k] * row[(gamma == 0 ? lay.off_wEA : lay.off_wEB) + d]; ncomp += cnt[k]; }
+        }
+        return marginal_finish(num, ncomp, nH > 0 ? (uint32_t)n_all : 0u, gamma == 0 ? p2A : p2B, wsum);
+    }
+    if (nH == 0) return p2A * p2B;
+    std::vector<uint32_t> cls(nH);
+    ClassTotals tot{0, 0, 0};
+    for (int k = 0; k < nH; k++) {
+        cls[k] = pack_class((uint32_t)cnt[k], dA[k], dB[k]);
+        tot.n += cnt[k]; if (dA[k] >= 0) tot.ncompA += cnt[k]; if (dB[k] >= 0) tot.ncompB += cnt[k];
+    }
+    auto ld = [row](int off) { return row[off]; };
+    const int per = kQ / p;
+    double pre = 0, preB = 0, acc = 0, acc2 = 0;
+    for (int r = 0; r < p; r++) {
+        ChunkPartial cp = chunk_forward(ld, t.w.data(), lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB,
+                                        lay.LA, lay.LB, cls.data(), 1, nH, tot, p2A, p2B, r * per, r * per + per);
+        acc += chunk_finish(cp, pre, preB); acc2 += cp.acc2;
+        pre += cp.pre; preB += cp.preB;
+    }
+    return pismc_finish(acc, acc2, tot.n);
+}
+
+}  // extern "C"

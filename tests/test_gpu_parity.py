@@ -1,0 +1,153 @@
+"""GPU parity tests proper (run with -m gpu on the B200 box). Everything goes through the C ABI of
+libcoalgpu.so; the oracle is only the checker.
+
+ (1) HMM values: the batched piSMC kernel on the class vectors recorded from the compiled reference
+     (getDifferences output) matches the reference's values to 1e-9 relative (fp64).
+ (2) Integer history encodings: with the proposal draws fixed (same Philox stream) the event sequence of
+     every history is bit-identical to the oracle's CANONICAL mode.
+ (3) Likelihood: log-weights per history agree to 1e-9 relative; reduced estimates agree with the
+     reference's own output within Monte-Carlo error.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, parse_pismc_records
+
+pytestmark = pytest.mark.gpu
+
+RTOL_HMM = 1e-9      # north_star: HMM forward probabilities within 1e-9 relative error in fp64
+RTOL_WEIGHT = 1e-9   # per-history log-weights
+
+
+def _sampler(p):
+    import coalescenator_b200 as cb
+    return cb.DeviceSampler(p)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_tables_on_device_library_match_oracle(oracle, cuda_lib, name):
+    p, _, _ = load_golden(name)
+    s = _sampler(p)
+    for c in range(p.T):
+        for n in (1, 3, 7):
+            mine, ref = s.tables(n, c), oracle.tables(p, n, c)
+            assert np.array_equal(mine["EA"], ref["EA"]) and np.array_equal(mine["EB"], ref["EB"])
+            assert np.array_equal(mine["y"], ref["y"])
+            np.testing.assert_allclose(mine["z"], ref["z"], rtol=1e-15)
+    s.close()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_pismc_kernel_matches_reference_values(cuda_lib, name):
+    p, trace, _ = load_golden(name)
+    recs = parse_pismc_records(trace)
+    s = _sampler(p)
+    offs = np.zeros(len(recs) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum([len(r["cnt"]) for r in recs])
+    cat = lambda k: np.concatenate([np.asarray(r[k], dtype=np.int32) for r in recs])
+    pi = s.pismc_classes([r["gamma"] for r in recs], [r["n"] for r in recs], [r["c"] for r in recs], offs, cat("cnt"), cat("dA"), cat("dB"))
+    ref = np.array([r["pi"] for r in recs])
+    rel = np.abs(pi - ref) / ref
+    print(name, len(recs), "piSMC records, worst rel err", rel.max())
+    assert rel.max() < RTOL_HMM
+    s.close()
+
+
+def _compare_histories(oracle, p, n, seed, first=0, n_trace=None, max_events=8192):
+    import torch
+    n_trace = n if n_trace is None else n_trace
+    s = _sampler(p)
+    buf = s.alloc(n, n_trace=n_trace, max_events=max_events)
+    s.sample(buf, seed, first, n)
+    torch.cuda.synchronize()
+    assert s.counters()["n_overflow"] == 0
+    ref = oracle.run(p, n, seed, mode=oracle.MODE_CANONICAL, first=first, n_event_hist=n_trace, max_events=max_events)
+    ev = s.events(buf)
+    for h in range(n_trace):
+        a, b = ev[h], ref["events"][h]
+        if len(a) != len(b) or not np.array_equal(a, b):
+            k = next((i for i in range(min(len(a), len(b))) if a[i] != b[i]), min(len(a), len(b)))
+            raise AssertionError(f"history {h}: event {k} differs (gpu {len(a)} events, oracle {len(b)}):\n gpu    {a[k] if k < len(a) else None}\n oracle {b[k] if k < len(b) else None}")
+    w = buf["weights"].cpu().numpy()
+    assert np.isfinite(w).all()
+    np.testing.assert_array_equal(buf["nevents"].cpu().numpy(), ref["n_events"])
+    np.testing.assert_allclose(w, ref["weights"], rtol=RTOL_WEIGHT)
+    np.testing.assert_allclose(buf["tmrca"].cpu().numpy(), ref["tmrca"], rtol=1e-12)
+    np.testing.assert_array_equal(buf["lineages"].cpu().numpy(), ref["lineages"])
+    cnt = s.counters()
+    assert cnt["n_events"] == ref["n_events"].sum()
+    assert cnt["n_pismc"] == ref["n_pismc"].sum()
+    rel = np.abs(w - ref["weights"]) / np.abs(ref["weights"])
+    print(p.name.split("/")[-1], "histories", n, "events/history %.1f" % ref["n_events"].mean(), "worst weight rel err", rel.max())
+    s.close()
+    return buf, ref
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_history_events_bit_exact_and_weights(oracle, cuda_lib, name):
+    p, _, _ = load_golden(name)
+    _compare_histories(oracle, p, 96, seed=123)
+
+
+def test_history_offset_streams(oracle, cuda_lib):
+    """History h of a run is a function of (seed, h) only: drawing [1000, 1040) alone equals the oracle's."""
+    p, _, _ = load_golden("cfg1_pair0")
+    _compare_histories(oracle, p, 40, seed=77, first=1000)
+
+
+def test_single_time_point_and_tiny_samples(oracle, cuda_lib):
+    from coalescenator_b200.problem import Problem
+    p, _, _ = load_golden("cfg1_pair0")
+    one = Problem(p.LA, p.LB, p.times[:1], p.viral[:1], p.tau, p.driving_mu, p.driving_lambda, p.driving_rho,
+                  p.target_mu, p.target_rho, p.target_lambda, [p.types[0] + p.types[1]], name="T1")
+    _compare_histories(oracle, one, 64, seed=5)
+    # fewer than six lineages after the last collection: no event is drawn there (ProposalEngine.cpp:792)
+    tiny = Problem(p.LA, p.LB, p.times, p.viral, p.tau, p.driving_mu, p.driving_lambda, p.driving_rho,
+                   p.target_mu, p.target_rho, p.target_lambda, [p.types[0][:1], p.types[1][:1]], name="tiny")
+    _compare_histories(oracle, tiny, 64, seed=6)
+
+
+def test_long_loci(oracle, cuda_lib):
+    """LA + LB = 24 segregating sites: more candidates than lanes per two-locus batch boundary cases."""
+    from coalescenator_b200.problem import synth_alignment, tile_loci, locus_pairs, sub_problem
+    aln = synth_alignment(9, 2, 6, 400, 60)
+    loci = tile_loci(aln, 80)
+    pairs = locus_pairs(loci)
+    best = max(pairs, key=lambda t: (loci[t[0]][3] - loci[t[0]][2]) + (loci[t[1]][3] - loci[t[1]][2]))
+    p = sub_problem(aln, loci, *best)
+    assert p.LA + p.LB >= 20
+    _compare_histories(oracle, p, 24, seed=8, max_events=16384)
+
+
+@pytest.mark.parametrize("name", ["cfg1_pair0", "grid_pair5"])
+def test_reduction_matches_oracle_and_reference(oracle, cuda_lib, name):
+    """K3 + finalize vs SamplerOutput::sumSamples semantics (sorted descending logAddition) on the same
+    weights, and run_sampler end to end vs the compiled reference's output within Monte-Carlo error."""
+    import torch
+    import coalescenator_b200 as cb
+    p, _, result = load_golden(name)
+    n = 2000
+    s = _sampler(p)
+    buf = s.alloc(n)
+    s.sample(buf, 99, 0, n)
+    part = s.partials(buf, n).cpu().numpy()
+    torch.cuda.synchronize()
+    out = s.finalize(part, n)
+    red = oracle.reduce(buf["weights"].cpu().numpy(), buf["tmrca"].cpu().numpy(), buf["lineages"].cpu().numpy())
+    np.testing.assert_allclose(out.likelihood.ravel(), red["likelihood"], rtol=1e-12)
+    np.testing.assert_allclose(out.likelihoodSq.ravel(), red["likelihoodSq"], rtol=1e-12)
+    np.testing.assert_allclose(out.tmrca.ravel(), red["tmrca"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out.lineages_remaining.reshape(p.T, -1), red["lineages"], rtol=1e-10, atol=1e-12)
+    s.close()
+    # end to end through the drop-in entry point (host buffers)
+    res = cb.ImportanceSampler().run_sampler(p, n, seed=99)
+    np.testing.assert_allclose(res.likelihood.ravel(), out.likelihood.ravel(), rtol=1e-12)
+    assert res.n_histories == n and res.n_events > 0
+    # vs the reference's own numbers: log mean weight within 5 standard errors (both estimates are noisy)
+    n_ref = result["n_samples"]
+    ref_like = np.array(result["likelihood"]) - np.log(n_ref)
+    ref_se = np.sqrt(np.maximum(np.exp(np.array(result["likelihoodSq"]) - 2 * np.array(result["likelihood"])) - 1.0 / n_ref, 0))
+    mine = res.likelihood.ravel() - np.log(n)
+    se = np.hypot(res.standard_error().ravel(), ref_se)
+    print(name, "log mean w: gpu", mine[:3], "reference", ref_like[:3], "combined SE", se[:3])
+    assert (np.abs(mine - ref_like) < 5 * se + 0.1).all()
