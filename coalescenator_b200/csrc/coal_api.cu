@@ -229,6 +229,8 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     int grid = s->grid;
     const unsigned long long ctas_needed = (warps_needed + s->warps_per_cta - 1) / s->warps_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
+    // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
+    CU_OK(cudaFuncSetAttribute(history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     history_kernel<<<grid, s->warps_per_cta * 32, s->smem_bytes, st>>>(s->P, a, s->warp_bytes);
     g_launches++;
     CU_OK(cudaGetLastError());

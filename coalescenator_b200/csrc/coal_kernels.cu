@@ -242,12 +242,13 @@ __device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int 
             if (dB >= 0) tot.ncompB += cnt;
         }
     }
-    if (n_cond == 0 || nH == 0) return P.pow2negL;   // empty configuration, ConditionalSamplingHMM.cpp:277-298
+    const bool empty = (n_cond == 0 || nH == 0);     // empty configuration, ConditionalSamplingHMM.cpp:277-298
     const int r = lane & (p - 1);
     const int per = kQd / p;
     auto ld = [row](int off) { return __ldg(row + off); };
-    const ChunkPartial cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
-                                          P.LA, P.LB, col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r * per, r * per + per);
+    ChunkPartial cp = {0, 0, 0, 0, 0, 0};
+    if (!empty) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
+                                   P.LA, P.LB, col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r * per, r * per + per);
     // exclusive prefixes of (pre, preB) over the lanes of the group
     double ipre = cp.pre, ipreB = cp.preB;
     for (int o = 1; o < p; o <<= 1) {
@@ -262,7 +263,7 @@ __device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int 
         acc += __shfl_xor_sync(kFull, acc, o);
         acc2 += __shfl_xor_sync(kFull, acc2, o);
     }
-    return pismc_finish(acc, acc2, tot.n);
+    return empty ? P.pow2negL : pismc_finish(acc, acc2, tot.n);
 }
 
 __device__ __forceinline__ int lanes_per_query(int nq) {
@@ -662,10 +663,10 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
             if (g == GB && b >= 0) { num += (double)c * __ldg(row + P.off_wEB + b); ncomp += (unsigned int)c; }
         }
         double pi;
-        if (g == GC) {
+        {
             ChunkPartial cp = {0, 0, 0, 0, 0, 0};
             auto ld = [row](int off) { return __ldg(row + off); };
-            if (nH > 0) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB, P.LA, P.LB,
+            if (g == GC && nH > 0) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB, P.LA, P.LB,
                                            col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
             double ipre = cp.pre, ipreB = cp.preB;
             for (int o = 1; o < p; o <<= 1) {
@@ -676,9 +677,8 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
             if (r == 0) { epre = 0.0; epreB = 0.0; }
             double acc = chunk_finish(cp, epre, epreB), acc2 = cp.acc2;
             for (int o = 1; o < p; o <<= 1) { acc += __shfl_xor_sync(kFull, acc, o); acc2 += __shfl_xor_sync(kFull, acc2, o); }
-            pi = nH > 0 ? pismc_finish(acc, acc2, tot.n) : P.pow2negL;
-        } else {
-            pi = marginal_finish(num, ncomp, nH > 0 ? n : 0u, g == GA ? P.pow2negLA : P.pow2negLB, P.wsum);
+            if (g == GC) pi = nH > 0 ? pismc_finish(acc, acc2, tot.n) : P.pow2negL;
+            else pi = marginal_finish(num, ncomp, nH > 0 ? n : 0u, g == GA ? P.pow2negLA : P.pow2negLB, P.wsum);
         }
         if (valid && r == 0) out[qi] = pi;
         __syncwarp();

@@ -40,11 +40,18 @@ def cases():
     pr5 = locus_pairs(l5)
     # driving rho chosen so that 4*lambda*V*rho == 8 exactly in epoch 0: exercises the r == n branch
     out["varV_req_n"] = (sub_problem(aln5, l5, *pr5[0], driving=(2.5e-5, 1000.0, 8.0 / (4 * 1000 * 100 * (pr5[0][2] + 1)))), 1, 60, 5)
+    # statistical case: grid around the driving values, enough reference histories for a usable ESS
+    aln, loci, pairs = make_config(1)
+    out["stat_grid"] = (sub_problem(aln, loci, *pairs[0], target_mu=[1.5e-5, 2.5e-5, 4e-5], target_rho=[5e-5, 1e-4],
+                                    target_lambda=[700.0, 1000.0, 1400.0]), 1, 3000, 4242)
     return out
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, (p, n_trace, n_run, seed) in cases().items():
+        if only and name not in only:
+            continue
         p.save(os.path.join(HERE, name + ".coalprob"))
         tmp = os.path.join(HERE, name + ".trace")
         O.run_reference(p, n_trace, seed, trace_path=tmp, trace_max=n_trace)

@@ -119,7 +119,7 @@ def test_long_loci(oracle, cuda_lib):
     _compare_histories(oracle, p, 24, seed=8, max_events=16384)
 
 
-@pytest.mark.parametrize("name", ["cfg1_pair0", "grid_pair5"])
+@pytest.mark.parametrize("name", ["cfg1_pair0", "grid_pair5", "stat_grid"])
 def test_reduction_matches_oracle_and_reference(oracle, cuda_lib, name):
     """K3 + finalize vs SamplerOutput::sumSamples semantics (sorted descending logAddition) on the same
     weights, and run_sampler end to end vs the compiled reference's output within Monte-Carlo error."""
@@ -143,11 +143,18 @@ def test_reduction_matches_oracle_and_reference(oracle, cuda_lib, name):
     res = cb.ImportanceSampler().run_sampler(p, n, seed=99)
     np.testing.assert_allclose(res.likelihood.ravel(), out.likelihood.ravel(), rtol=1e-12)
     assert res.n_histories == n and res.n_events > 0
+    n = 20000
+    res = cb.ImportanceSampler().run_sampler(p, n, seed=100)
     # vs the reference's own numbers: log mean weight within 5 standard errors (both estimates are noisy)
     n_ref = result["n_samples"]
     ref_like = np.array(result["likelihood"]) - np.log(n_ref)
     ref_se = np.sqrt(np.maximum(np.exp(np.array(result["likelihoodSq"]) - 2 * np.array(result["likelihood"])) - 1.0 / n_ref, 0))
     mine = res.likelihood.ravel() - np.log(n)
     se = np.hypot(res.standard_error().ravel(), ref_se)
-    print(name, "log mean w: gpu", mine[:3], "reference", ref_like[:3], "combined SE", se[:3])
-    assert (np.abs(mine - ref_like) < 5 * se + 0.1).all()
+    # a standard error is only meaningful where the effective sample size is not ~1 (grid points far from
+    # the driving values have heavy-tailed weights): compare where both runs have ESS >= 10
+    ref_ess = np.exp(2 * np.array(result["likelihood"]) - np.array(result["likelihoodSq"]))
+    ok = (res.ess.ravel() >= 10) & (ref_ess >= 10)
+    print(name, "grid points compared", int(ok.sum()), "of", ok.size, "log mean w: gpu", mine[ok][:3], "reference", ref_like[ok][:3], "combined SE", se[ok][:3])
+    assert ok.any() or name == "grid_pair5"     # that fixture's grid is far from the driving point (ESS ~ 1 everywhere)
+    assert (np.abs(mine - ref_like)[ok] < 5 * se[ok] + 0.05).all()
