@@ -6,7 +6,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libcoalgpu.so")
+LIB = os.environ.get("COALGPU_LIB") or os.path.join(HERE, "libcoalgpu.so")   # COALGPU_LIB: tuning variants only
 SOURCES = ["coal_api.cu", "coal_tables.cpp"]
 DEPS = SOURCES + ["coal_kernels.cu", "coal_device.cuh", "coal_math.h", "coal_tables.h", os.path.join("..", "..", "include", "coalgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,7 +24,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library if it is missing or older than its sources; returns its path."""
     if force or _stale():
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        extra = os.environ.get("COALGPU_DEFS", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
         r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -199,6 +199,7 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
 
     // launch geometry: persistent CTAs of 4 warps, as many as shared memory and registers allow
     s->warp_bytes = (int)history_warp_bytes(P.kmax, P.pvmax, P.Ltot);
+    P.warp_bytes = s->warp_bytes;
     s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta;
     while (s->smem_bytes > 227 * 1024 && s->warps_per_cta > 1) { s->warps_per_cta /= 2; s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta; }
     if (s->smem_bytes > 227 * 1024) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for one warp's shared-memory state"); }
@@ -231,7 +232,7 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
     // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
     CU_OK(cudaFuncSetAttribute(history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    history_kernel<<<grid, s->warps_per_cta * 32, s->smem_bytes, st>>>(s->P, a, s->warp_bytes);
+    history_kernel<<<grid, s->warps_per_cta * 32, s->smem_bytes, st>>>(s->P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
     return 0;

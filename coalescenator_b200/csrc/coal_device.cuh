@@ -34,7 +34,7 @@ struct GridConst {
 
 struct DevProblem {
     int T, LA, LB, Ltot, G;
-    int n_max, kmax, row_doubles, pvmax;
+    int n_max, kmax, row_doubles, pvmax, warp_bytes;
     int off_yw, off_zlow, off_g, off_zdiag, off_EA, off_EB, off_wEA, off_wEB;
     unsigned long long maskA, maskB;
     double perm_const;        // sum_t probabilitySamplePermutation (ProposalEngine.cpp:88-118,822-828)
@@ -65,7 +65,8 @@ struct SampleArgs {
 __constant__ double c_w[kQd];   // interval weights (ConditionalSamplingHMM.cpp:63-71)
 
 // ---- Philox4x32-10 ------------------------------------------------------------------------------
-__device__ __forceinline__ void philox_block(unsigned long long seed, unsigned long long hist, unsigned long long blk, unsigned int out[4]) {
+// One copy in the binary (the history kernel is instruction-cache sensitive, profiles/r1_v0_*).
+__device__ __noinline__ uint4 philox_block(unsigned long long seed, unsigned long long hist, unsigned long long blk) {
     unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
     unsigned int c0 = (unsigned int)hist, c1 = (unsigned int)(hist >> 32), c2 = (unsigned int)blk, c3 = (unsigned int)(blk >> 32);
 #pragma unroll
@@ -76,16 +77,25 @@ __device__ __forceinline__ void philox_block(unsigned long long seed, unsigned l
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
-// draw k of history hist -> (0,1), 53 bits
-__device__ __forceinline__ double philox_uniform(unsigned long long seed, unsigned long long hist, unsigned long long k) {
-    unsigned int o[4];
-    philox_block(seed, hist, k >> 1, o);
-    const unsigned int lo = (k & 1) ? o[2] : o[0], hi = (k & 1) ? o[3] : o[1];
+__device__ __forceinline__ double u53(unsigned int lo, unsigned int hi) {
     const unsigned long long bits = (((unsigned long long)hi << 32) | lo) >> 11;
     return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
 }
+// Sequential draws of one history: draw k lives in block k >> 1, half k & 1; -> (0,1), 53 bits.
+struct PhiloxStream {
+    unsigned long long seed, hist, k;
+    uint4 blk;
+    __device__ __forceinline__ void init(unsigned long long s, unsigned long long h) { seed = s; hist = h; k = 0; blk = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ double next() {
+        double u;
+        if ((k & 1) == 0) { blk = philox_block(seed, hist, k >> 1); u = u53(blk.x, blk.y); }
+        else u = u53(blk.z, blk.w);
+        k++;
+        return u;
+    }
+};
 
 // ---- warp helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -1,5 +1,9 @@
 // Kernels of the importance-sampling likelihood path. See coal_device.cuh for the design summary and
 // DESIGN.md §4 for the data layout and roofline of each kernel.
+//
+// v1 layout of the code (profiles/r1_v0_*: the first version was instruction-fetch bound, 254 KB of SASS):
+// every helper with more than one call site is __noinline__ (adjust_core, dlog, philox_block, pick), every
+// query kind has ONE call site, and per-event logarithms are folded into running products.
 #include "coal_device.cuh"
 #include "coal_math.h"
 
@@ -9,22 +13,25 @@ namespace {
 
 constexpr int GA = COALGPU_GAMMA_A, GB = COALGPU_GAMMA_B, GC = COALGPU_GAMMA_C;
 constexpr unsigned int kCntMask = 0x3fffffffu;
+constexpr int kAppended = 0x40000000;
+
+// problem + launch arguments, copied once per CTA from the kernel parameters so that the out-of-line
+// helpers can read them without carrying them in registers
+__shared__ DevProblem sP;
+__shared__ SampleArgs sA;
+extern __shared__ __align__(16) unsigned char smem_dyn[];
 
 // per-warp shared-memory state
 struct WarpMem {
     unsigned long long* words;   // [kmax]  packed haplotype of each stored type
+    double* pv;                  // [pvmax] unnormalised candidate probabilities / lineage-chooser weights
+    double* aux;                 // [kmax]  joint conditional probability per coalescence partner
     unsigned int* cg;            // [kmax]  count | gamma << 30
     unsigned int* xc;            // [kmax]  cross counts: C slot: cntA(A part) | cntB(B part) << 16;
                                  //         A slot: C lineages with this A part; B slot: likewise
-    double* pv;                  // [pvmax] unnormalised candidate probabilities of the event
-    double* aux;                 // [kmax]  joint conditional probability per coalescence partner
     unsigned int* plist;         // [kmax]  slot index of each partner
     unsigned int* hist;          // [(Ltot+2)*32] one class-histogram column per lane
-};
-
-struct HState {
-    int nslots, nA, nB, nC;
-    bool overflow;
+    double* sd;                  // [4]     scalar results of the out-of-line helpers
 };
 
 __host__ __device__ inline size_t warp_mem_bytes(int kmax, int pvmax, int Ltot) {
@@ -34,10 +41,13 @@ __host__ __device__ inline size_t warp_mem_bytes(int kmax, int pvmax, int Ltot) 
     b += (size_t)kmax * 8;                 // aux
     b += (size_t)kmax * 4 * 3;             // cg, xc, plist
     b += (size_t)(Ltot + 2) * 32 * 4;      // hist
+    b += 4 * 8;                            // sd
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ WarpMem carve(unsigned char* base, int kmax, int pvmax) {
+__device__ __forceinline__ WarpMem wm() {
+    unsigned char* base = smem_dyn + (size_t)(threadIdx.x >> 5) * sP.warp_bytes;
+    const int kmax = sP.kmax, pvmax = sP.pvmax;
     WarpMem m;
     m.words = reinterpret_cast<unsigned long long*>(base); base += (size_t)kmax * 8;
     m.pv = reinterpret_cast<double*>(base); base += (size_t)pvmax * 8;
@@ -45,22 +55,35 @@ __device__ __forceinline__ WarpMem carve(unsigned char* base, int kmax, int pvma
     m.cg = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.xc = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.plist = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
-    m.hist = reinterpret_cast<unsigned int*>(base);
+    m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)(sP.Ltot + 2) * 32 * 4;
+    m.sd = reinterpret_cast<double*>(base);
     return m;
 }
+
+struct HState {
+    int nslots, nA, nB, nC;
+    bool overflow;
+};
+
+__device__ __noinline__ double dlog(double x) { return log(x); }
 
 // ---- type store ------------------------------------------------------------------------------------
 
 // Change the multiplicity of type (g, w) by delta (TypeContainer::addType / removeType,
 // TypeContainer.cpp:409-522) keeping the cross counts of every related slot current. A type that is
-// not stored yet is appended; a slot whose count reaches 0 stays until commit(). Returns the slot.
-__device__ int adjust(const DevProblem& P, const WarpMem& m, HState& s, int g, unsigned long long w, int delta, int lane) {
+// not stored yet is appended; a slot whose count reaches 0 stays until commit().
+// Returns the slot (| kAppended when a slot was appended) or -1 when the store is full.
+__device__ __noinline__ int adjust_core(int nslots, int g, unsigned long long w, int delta) {
+    const WarpMem m = wm();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
     int found = -1;
     unsigned int newxc = 0;
-    const unsigned long long wa = w & P.maskA, wb = w & P.maskB;
-    for (int base = 0; base < s.nslots; base += 32) {
+    const unsigned long long wa = w & maskA, wb = w & maskB;
+#pragma unroll 1
+    for (int base = 0; base < nslots; base += 32) {
         const int j = base + lane;
-        const bool in = j < s.nslots;
+        const bool in = j < nslots;
         const unsigned long long wj = in ? m.words[j] : 0ull;
         const unsigned int cgj = in ? m.cg[j] : 0u;
         const int gj = (int)(cgj >> 30);
@@ -69,108 +92,108 @@ __device__ int adjust(const DevProblem& P, const WarpMem& m, HState& s, int g, u
         if (b) found = base + __ffs(b) - 1;
         if (in) {
             if (g == GA) {
-                if (gj == GC && (wj & P.maskA) == w) { m.xc[j] += (unsigned int)delta; newxc += cj; }
+                if (gj == GC && (wj & maskA) == w) { m.xc[j] += (unsigned int)delta; newxc += cj; }
             } else if (g == GB) {
-                if (gj == GC && (wj & P.maskB) == w) { m.xc[j] += (unsigned int)(delta * 65536); newxc += cj; }
+                if (gj == GC && (wj & maskB) == w) { m.xc[j] += (unsigned int)(delta * 65536); newxc += cj; }
             } else {
                 if (gj == GA && wj == wa) { m.xc[j] += (unsigned int)delta; newxc += cj; }
                 if (gj == GB && wj == wb) { m.xc[j] += (unsigned int)delta; newxc += cj << 16; }
             }
         }
     }
+    int ret;
     if (found < 0) {
         newxc = warp_sum_u(newxc);
-        if (s.nslots >= P.kmax) { s.overflow = true; return -1; }
-        found = s.nslots++;
+        if (nslots >= sP.kmax) return -1;
+        found = nslots;
         if (lane == 0) { m.words[found] = w; m.cg[found] = (unsigned int)g << 30; m.xc[found] = newxc; }
+        ret = found | kAppended;
+    } else {
+        ret = found;
     }
     __syncwarp();
     if (lane == 0) m.cg[found] += (unsigned int)delta;
     __syncwarp();
+    return ret;
+}
+
+__device__ __forceinline__ int adjust(HState& s, int g, unsigned long long w, int delta) {
+    int r = adjust_core(s.nslots, g, w, delta);
+    if (r < 0) { s.overflow = true; return -1; }
+    if (r & kAppended) { s.nslots++; r &= ~kAppended; }
     if (g == GA) s.nA += delta; else if (g == GB) s.nB += delta; else s.nC += delta;
-    return found;
+    return r;
 }
 
 // Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot
 // (the canonical order rule shared with the oracle's CANONICAL mode).
-__device__ void commit(const WarpMem& m, HState& s, int lane) {
+__device__ __forceinline__ int commit(const WarpMem& m, int nslots, int lane) {
+#pragma unroll 1
     for (;;) {
         int z = -1;
-        for (int base = ((s.nslots - 1) / 32) * 32; base >= 0 && z < 0; base -= 32) {
+#pragma unroll 1
+        for (int base = ((nslots - 1) / 32) * 32; base >= 0 && z < 0; base -= 32) {
             const int j = base + lane;
-            const bool empty = j < s.nslots && (m.cg[j] & kCntMask) == 0;
+            const bool empty = j < nslots && (m.cg[j] & kCntMask) == 0;
             const unsigned int b = __ballot_sync(kFull, empty);
             if (b) z = base + 31 - __clz(b);
         }
         if (z < 0) break;
-        const int last = s.nslots - 1;
+        const int last = nslots - 1;
         if (lane == 0 && z != last) { m.words[z] = m.words[last]; m.cg[z] = m.cg[last]; m.xc[z] = m.xc[last]; }
-        s.nslots = last;
+        nslots = last;
         __syncwarp();
-        if (s.nslots == 0) break;
+        if (nslots == 0) break;
     }
+    return nslots;
 }
 
-// Lineage chooser (TypeContainer::sampleType, TypeContainer.cpp:641-745): slot order, weights of
-// SURVEY.md Q10. Returns the slot; prob = weight / normalising constant.
-__device__ int sample_type(const WarpMem& m, const HState& s, double thA, double thB, double rho, double u, int lane, double& prob) {
-    double norm = 0.0;
-    const int rounds = (s.nslots + 31) / 32;
-    // pass 1: normalising constant (inclusive scans keep slot order)
-    double w0 = 0.0, cum0 = 0.0;
-    for (int r = 0; r < rounds; r++) {
-        const int j = r * 32 + lane;
-        double wgt = 0.0;
-        if (j < s.nslots) {
-            const unsigned int cgj = m.cg[j], xcj = m.xc[j];
-            const unsigned int c = cgj & kCntMask;
-            const int gj = (int)(cgj >> 30);
-            if (c > 0) {
-                if (gj == GC) wgt = ((((double)(c - 1) + (thA + thB)) + rho) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
-                else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + thA) * (double)c;
-                else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + thB) * (double)c;
-            }
-        }
-        const double cum = warp_incl_scan(wgt, lane) + norm;
-        if (r == 0) { w0 = wgt; cum0 = cum; }
-        norm = __shfl_sync(kFull, cum, 31);
+// Categorical draw over pv[0..n): first k with cum > u*total (strict, TypeContainer.cpp:730) or with
+// cum >= u*total (ProposalEngine.cpp:574). Partial sums run in index order (inclusive warp scans).
+// Returns k; sd[0] = pv[k], sd[1] = total.
+__device__ __noinline__ int pick(int n, double u, bool strict) {
+    const WarpMem m = wm();
+    const int lane = threadIdx.x & 31;
+    double total = 0.0;
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const double v = k < n ? m.pv[k] : 0.0;
+        total = __shfl_sync(kFull, warp_incl_scan(v, lane) + total, 31);
     }
-    const double thr = u * norm;
-    int pick = -1; double wpick = 0.0;
-    if (rounds == 1) {
-        const unsigned int b = __ballot_sync(kFull, (lane < s.nslots) && (cum0 > thr) && (w0 > 0.0));
-        if (b) { pick = __ffs(b) - 1; wpick = __shfl_sync(kFull, w0, pick); }
-    } else {
-        double carry = 0.0;
-        for (int r = 0; r < rounds && pick < 0; r++) {
-            const int j = r * 32 + lane;
-            double wgt = 0.0;
-            if (j < s.nslots) {
-                const unsigned int cgj = m.cg[j], xcj = m.xc[j];
-                const unsigned int c = cgj & kCntMask;
-                const int gj = (int)(cgj >> 30);
-                if (c > 0) {
-                    if (gj == GC) wgt = ((((double)(c - 1) + (thA + thB)) + rho) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
-                    else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + thA) * (double)c;
-                    else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + thB) * (double)c;
-                }
-            }
-            const double cum = warp_incl_scan(wgt, lane) + carry;
-            const unsigned int b = __ballot_sync(kFull, (j < s.nslots) && (cum > thr) && (wgt > 0.0));
-            if (b) { const int l = __ffs(b) - 1; pick = r * 32 + l; wpick = __shfl_sync(kFull, wgt, l); }
-            carry = __shfl_sync(kFull, cum, 31);
-        }
+    const double target = u * total;
+    int idx = -1; double pidx = 0.0, carry = 0.0;
+#pragma unroll 1
+    for (int base = 0; base < n && idx < 0; base += 32) {
+        const int k = base + lane;
+        const double v = k < n ? m.pv[k] : 0.0;
+        const double cum = warp_incl_scan(v, lane) + carry;
+        const bool hit = k < n && (strict ? (cum > target && v > 0.0) : !(cum < target));
+        const unsigned int b = __ballot_sync(kFull, hit);
+        if (b) { const int l = __ffs(b) - 1; idx = base + l; pidx = __shfl_sync(kFull, v, l); }
+        carry = __shfl_sync(kFull, cum, 31);
     }
-    if (pick < 0) {   // u*norm rounded past the last partial sum: take the last stored type
-        pick = s.nslots - 1;
-        const unsigned int cgj = m.cg[pick], xcj = m.xc[pick];
-        const unsigned int c = cgj & kCntMask; const int gj = (int)(cgj >> 30);
-        if (gj == GC) wpick = ((((double)(c - 1) + (thA + thB)) + rho) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
-        else if (gj == GA) wpick = ((double)(c - 1 + (unsigned int)s.nB + xcj) + thA) * (double)c;
-        else wpick = ((double)(c - 1 + (unsigned int)s.nA + xcj) + thB) * (double)c;
+    if (idx < 0) { idx = n - 1; pidx = m.pv[idx]; }   // u*total rounded past the last partial sum
+    __syncwarp();
+    if (lane == 0) { m.sd[0] = pidx; m.sd[1] = total; }
+    __syncwarp();
+    return idx;
+}
+
+// Lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721) into pv[]
+__device__ __forceinline__ void type_weights(const WarpMem& m, const HState& s, double thA, double thB, double rho, int lane) {
+#pragma unroll 1
+    for (int j = lane; j < s.nslots; j += 32) {
+        const unsigned int cgj = m.cg[j], xcj = m.xc[j];
+        const unsigned int c = cgj & kCntMask;
+        const int gj = (int)(cgj >> 30);
+        double wgt;
+        if (gj == GC) wgt = ((((double)(c - 1) + (thA + thB)) + rho) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
+        else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + thA) * (double)c;
+        else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + thB) * (double)c;
+        m.pv[j] = wgt;
     }
-    prob = wpick / norm;
-    return pick;
+    __syncwarp();
 }
 
 // ---- conditional sampling probabilities ----------------------------------------------------------------
@@ -178,11 +201,12 @@ __device__ int sample_type(const WarpMem& m, const HState& s, double thA, double
 // One-locus query per lane: query (qg in {A,B}, qw), optionally leaving out one copy of the query's own
 // type (the H - b_k configurations of ProposalEngine.cpp:323-329). Evaluated against two table rows at once
 // (the same distance histogram serves pi(.|H) and pi(.|H + other-locus lineage), ProposalEngine.cpp:120-132).
-__device__ __forceinline__ void marginal_query(const DevProblem& P, const WarpMem& m, int nslots, int qg, unsigned long long qw,
-                                               bool excl, const double* __restrict__ wE1, const double* __restrict__ wE2,
+__device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int qg, unsigned long long qw, bool excl,
+                                               const double* __restrict__ wE1, const double* __restrict__ wE2,
                                                double& num1, double& num2, unsigned int& ncomp) {
     num1 = 0.0; num2 = 0.0; ncomp = 0;
-    const unsigned long long mask = (qg == GA) ? P.maskA : P.maskB;
+    const unsigned long long mask = (qg == GA) ? sP.maskA : sP.maskB;
+#pragma unroll 2
     for (int j = 0; j < nslots; j++) {
         const unsigned long long wj = m.words[j];
         const unsigned int cgj = m.cg[j];
@@ -203,11 +227,14 @@ __device__ __forceinline__ void marginal_query(const DevProblem& P, const WarpMe
 // class histogram of the group's query in its own shared-memory column (TypeContainer::getDifferences,
 // TypeContainer.cpp:802-886 incl. the dA+dB collapse of SURVEY.md Q1), then takes Q/p of the intervals of
 // the forward pass. (delg, delw): one copy of that stored type is left out (delg < 0: none).
-__device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int lane, int p, unsigned long long qw,
-                         int delg, unsigned long long delw, const double* __restrict__ row, unsigned int n_cond) {
+__device__ __forceinline__ double cquery(const WarpMem& m, int nslots, int lane, int p, unsigned long long qw,
+                                         int delg, unsigned long long delw, const double* __restrict__ row, unsigned int n_cond) {
     unsigned int* col = m.hist + lane;
-    const int nsum = P.Ltot + 2;
+    const int Ltot = sP.Ltot, nsum = Ltot + 2;
+    const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
+#pragma unroll 1
     for (int sidx = 0; sidx < nsum; sidx++) col[sidx * 32] = 0xffff0000u;
+#pragma unroll 2
     for (int j = 0; j < nslots; j++) {
         const unsigned long long wj = m.words[j];
         const unsigned int cgj = m.cg[j];
@@ -216,18 +243,17 @@ __device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int 
         if (gj == delg && wj == delw) c -= 1;
         if (c > 0) {
             const unsigned long long x = wj ^ qw;
-            const int da = __popcll(x & P.maskA), db = __popcll(x & P.maskB);
+            const int da = __popcll(x & maskA), db = __popcll(x & maskB);
             int sidx; unsigned int rep;
             if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
             const unsigned int v = col[sidx * 32];
-            const unsigned int cnt = (v & 0xffffu) + c;
-            const unsigned int r = min(v >> 16, rep);
-            col[sidx * 32] = cnt | (r << 16);
+            col[sidx * 32] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
         }
     }
     // compact the classes in place (ascending dA+dB) and collect the totals
     int nH = 0;
     ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
+#pragma unroll 1
     for (int sidx = 0; sidx < nsum; sidx++) {
         const unsigned int v = col[sidx * 32];
         const unsigned int cnt = v & 0xffffu;
@@ -247,10 +273,11 @@ __device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int 
     const int per = kQd / p;
     auto ld = [row](int off) { return __ldg(row + off); };
     ChunkPartial cp = {0, 0, 0, 0, 0, 0};
-    if (!empty) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
-                                   P.LA, P.LB, col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r * per, r * per + per);
+    if (!empty) cp = chunk_forward(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB,
+                                   sP.LA, sP.LB, col, 32, nH, tot, sP.pow2negLA, sP.pow2negLB, r * per, r * per + per);
     // exclusive prefixes of (pre, preB) over the lanes of the group
     double ipre = cp.pre, ipreB = cp.preB;
+#pragma unroll 1
     for (int o = 1; o < p; o <<= 1) {
         const double t1 = __shfl_up_sync(kFull, ipre, o, p);
         const double t2 = __shfl_up_sync(kFull, ipreB, o, p);
@@ -259,11 +286,12 @@ __device__ double cquery(const DevProblem& P, const WarpMem& m, int nslots, int 
     double epre = __shfl_up_sync(kFull, ipre, 1, p), epreB = __shfl_up_sync(kFull, ipreB, 1, p);
     if (r == 0) { epre = 0.0; epreB = 0.0; }
     double acc = chunk_finish(cp, epre, epreB), acc2 = cp.acc2;
+#pragma unroll 1
     for (int o = 1; o < p; o <<= 1) {
         acc += __shfl_xor_sync(kFull, acc, o);
         acc2 += __shfl_xor_sync(kFull, acc2, o);
     }
-    return empty ? P.pow2negL : pismc_finish(acc, acc2, tot.n);
+    return empty ? sP.pow2negL : pismc_finish(acc, acc2, tot.n);
 }
 
 __device__ __forceinline__ int lanes_per_query(int nq) {
@@ -272,182 +300,155 @@ __device__ __forceinline__ int lanes_per_query(int nq) {
     return p;
 }
 
-__device__ __forceinline__ const double* row_ptr(const DevProblem& P, int set, int n_all) {
+__device__ __forceinline__ const double* row_ptr(int set, int n_all) {
     const int n = n_all < 1 ? 1 : n_all;   // n_all == 0 is never dereferenced for a result
-    return P.rows + ((size_t)set * P.n_max + (n - 1)) * P.row_doubles;
+    return sP.rows + ((size_t)set * sP.n_max + (n - 1)) * sP.row_doubles;
 }
+
+// running product with the exponent split off: a sum of logs without a log per factor
+struct LogProd {
+    double mant; int expo;
+    __device__ __forceinline__ void clear() { mant = 1.0; expo = 0; }
+    __device__ __forceinline__ void mul(double x) {
+        int e;
+        mant = frexp(mant * x, &e);
+        expo += e;
+    }
+    __device__ __forceinline__ double value() const { return dlog(mant) + (double)expo * 0.69314718055994530942; }
+};
 
 // ---- one history ------------------------------------------------------------------------------------------
 
-__device__ void run_history(const DevProblem& P, const SampleArgs& A, const WarpMem& m, unsigned long long h, int lane,
-                            unsigned long long& ev_total, unsigned long long& pi_total) {
-    const unsigned long long hist = A.first + h;
-    unsigned long long draw = 0;
+__device__ void run_history(unsigned long long h, int lane, unsigned long long& ev_total, unsigned long long& pi_total) {
+    const WarpMem m = wm();
+    const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, G = sP.G;
+    PhiloxStream rng; rng.init(sA.seed, sA.first + h);
     HState s; s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
-    const bool tracing = A.events != nullptr && h < A.n_trace;
+    const bool tracing = sA.events != nullptr && h < sA.n_trace;
     unsigned int nev = 0, npi = 0;
 
-    // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99)
-    for (int k = P.type_off[0]; k < P.type_off[1]; k++) {
-        const unsigned int cg = P.type_cg[k];
-        adjust(P, m, s, (int)(cg >> 30), P.type_w[k], (int)(cg & kCntMask), lane);
-    }
+    // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
+    int inj_lo = sP.type_off[0], inj_hi = sP.type_off[1];
+    bool injecting = true;
 
     int e = 0;                                  // epoch = index into viral / HMM time_idx
-    EpochConst ec = P.ep[0];
-    int tset = P.set_of_epoch[0];
-    double q = 0.0, consts = 0.0;
+    EpochConst ec = sP.ep[0];
+    int tset = sP.set_of_epoch[0];
+    double qsum = 0.0, consts = 0.0;            // proposal log-density = qsum + log(qprod)
+    LogProd qprod; qprod.clear();
+    LogProd evprod; evprod.clear();             // product of the event constants of the epoch
     double tsum = 0.0;
     bool post = true;
     EpochStats st; epoch_stats_clear(st);
-    // weights are accumulated per epoch into the output buffer at the end of each epoch (lanes over g)
-    double* wout = A.weights ? A.weights + h * (unsigned long long)P.G : nullptr;
-    if (wout) for (int g = lane; g < P.G; g += 32) wout[g] = 0.0;
+    double* wout = sA.weights ? sA.weights + h * (unsigned long long)G : nullptr;
+    if (wout) for (int g = lane; g < G; g += 32) wout[g] = 0.0;
 
-    auto flush_epoch = [&](int epoch) {
-        if (wout) {
-            const GridConst* gc = P.grid + (size_t)epoch * P.G;
-            for (int g = lane; g < P.G; g += 32) {
-                const GridConst c = gc[g];
-                wout[g] += epoch_log_density(st, c.theta, c.rho, c.inv2Ntau, c.log_theta, c.log_rho, c.log_2Ntau,
-                                             [](double x) { return log(x); });
-            }
-        }
-        epoch_stats_clear(st);
-    };
-
+#pragma unroll 1
     for (;;) {
-        // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
-        double p_hap;
-        const double u_type = philox_uniform(A.seed, hist, draw++);
-        const int sx = sample_type(m, s, ec.dthA, ec.dthB, ec.drho, u_type, lane, p_hap);
-        const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
-        const double Dd = (double)((unsigned int)n * (unsigned int)(n - 1)) + (double)(Ac + Cc) * ec.dthA + (double)(Bc + Cc) * ec.dthB + ec.drho * (double)Cc;
-        const double rate = Dd * ec.inv2Ntau;
-        const double u_wait = philox_uniform(A.seed, hist, draw++);
-        const double wait = -log(u_wait) / rate;
+        if (injecting) {
+            // TypeContainer::addTypeMap :525-591 + probabilityCombinatorics ProposalEngine.cpp:66-86
+            const int a0 = s.nA, b0 = s.nB, c0 = s.nC;
+            double comb = 0.0;
+#pragma unroll 1
+            for (int k = inj_lo; k < inj_hi; k++) {
+                const unsigned int cg = sP.type_cg[k];
+                const int add = (int)(cg & kCntMask);
+                const int slot = adjust(s, (int)(cg >> 30), sP.type_w[k], add);
+                if (slot < 0) break;
+                const int now = (int)(m.cg[slot] & kCntMask);
+                comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
+            }
+            if (e > 0 && !s.overflow) {
+                comb -= sP.lfact[s.nA] - sP.lfact[s.nA - a0] - sP.lfact[a0];
+                comb -= sP.lfact[s.nB] - sP.lfact[s.nB - b0] - sP.lfact[b0];
+                comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
+                consts += comb;
+            }
+            injecting = false;
+            if (s.overflow) break;
+        }
 
-        // ---- collection boundaries (ProposalEngine.cpp:694-783); a boundary redraws lineage and time ----
-        if (e < P.T - 1) {
-            if (!(tsum + wait < P.times[e + 1])) {
-                const double excess = P.times[e + 1] - tsum;
-                tsum = P.times[e + 1];
-                q += -rate * excess;
-                const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
-                const double aa = (double)((Ac + Cc) * P.LA + (Bc + Cc) * P.LB);
+        // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
+        type_weights(m, s, ec.dthA, ec.dthB, ec.drho, lane);
+        const int sx = pick(s.nslots, rng.next(), true);
+        const double p_hap = m.sd[0] / m.sd[1];
+        const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
+        const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
+        const double Dd = nn + (double)(Ac + Cc) * ec.dthA + (double)(Bc + Cc) * ec.dthB + ec.drho * (double)Cc;
+        const double rate = Dd * ec.inv2Ntau;
+        const double wait = -dlog(rng.next()) / rate;
+        const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
+
+        // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
+        const bool boundary = (e < T - 1) && !(tsum + wait < sP.times[e + 1]);
+        const bool finish = (e == T - 1) && (n <= 5);
+        if (boundary || finish) {
+            if (boundary) {
+                const double excess = sP.times[e + 1] - tsum;
+                tsum = sP.times[e + 1];
+                qsum += -rate * excess;
                 st.s_nn += nn * excess; st.s_a += aa * excess; st.s_c += (double)Cc * excess;
                 st.bnd_nn = nn; st.bnd_a = aa; st.bnd_c = (double)Cc; st.has_bnd = 1; st.n_rate += 1;
-                flush_epoch(e);
-                if (A.lineages) { if (lane == 0) A.lineages[h * (unsigned long long)P.T + e] = (double)n; }
-                // inject the next sample (TypeContainer::addTypeMap :525-591) + combinatorial terms (:66-86)
-                const int a0 = s.nA, b0 = s.nB, c0 = s.nC;
-                double comb = 0.0;
-                for (int k = P.type_off[e + 1]; k < P.type_off[e + 2]; k++) {
-                    const unsigned int cg = P.type_cg[k];
-                    const int add = (int)(cg & kCntMask);
-                    const int slot = adjust(P, m, s, (int)(cg >> 30), P.type_w[k], add, lane);
-                    if (slot < 0) break;
-                    const int now = (int)(m.cg[slot] & kCntMask);
-                    comb += P.lfact[now] - P.lfact[add] - P.lfact[now - add];
-                }
-                comb -= P.lfact[s.nA] - P.lfact[s.nA - a0] - P.lfact[a0];
-                comb -= P.lfact[s.nB] - P.lfact[s.nB - b0] - P.lfact[b0];
-                comb -= P.lfact[s.nC] - P.lfact[s.nC - c0] - P.lfact[c0];
-                consts += comb;
-                post = true;
-                e++;
-                ec = P.ep[e];
-                tset = P.set_of_epoch[e];
-                if (s.overflow) break;
-                continue;
             }
-        } else if (n <= 5) {
-            break;                               // ProposalEngine.cpp:792: stop at five lineages
+            st.slog = evprod.value();
+            if (wout) {
+                const GridConst* gc = sP.grid + (size_t)e * G;
+#pragma unroll 1
+                for (int g = lane; g < G; g += 32) {
+                    const GridConst c = gc[g];
+                    wout[g] += epoch_log_density(st, c.theta, c.rho, c.inv2Ntau, c.log_theta, c.log_rho, c.log_2Ntau,
+                                                 [](double x) { return dlog(x); });
+                }
+            }
+            epoch_stats_clear(st); evprod.clear();
+            if (sA.lineages && lane == 0) sA.lineages[h * (unsigned long long)T + e] = (double)n;
+            if (finish) break;
+            e++;
+            inj_lo = sP.type_off[e]; inj_hi = sP.type_off[e + 1];
+            injecting = true;
+            post = true;
+            ec = sP.ep[e];
+            tset = sP.set_of_epoch[e];
+            continue;
         }
         tsum += wait;
 
         // ---- one event (ProposalEngine.cpp:134-566) ----
-        q += (log(rate) - rate * wait) + log(p_hap);
         const unsigned long long xw = m.words[sx];
         const unsigned int xcg = m.cg[sx], xxc = m.xc[sx];
         const int xg = (int)(xcg >> 30);
         const unsigned int xcount = xcg & kCntMask;
-        const unsigned long long xa = xw & P.maskA, xb = xw & P.maskB;
+        const unsigned long long xa = xw & sP.maskA, xb = xw & sP.maskB;
         unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
         if (xg == GC) {
             Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16;
             unsigned int ci = 0, cj = 0;
-            for (int base = 0; base < s.nslots; base += 32) {
-                const int j = base + lane;
-                if (j < s.nslots) {
-                    const unsigned int cgj = m.cg[j];
-                    if ((int)(cgj >> 30) == GC) {
-                        const unsigned long long wj = m.words[j];
-                        if ((wj & P.maskA) == xa) ci += cgj & kCntMask;
-                        if ((wj & P.maskB) == xb) cj += cgj & kCntMask;
-                    }
+#pragma unroll 1
+            for (int j = lane; j < s.nslots; j += 32) {
+                const unsigned int cgj = m.cg[j];
+                if ((int)(cgj >> 30) == GC) {
+                    const unsigned long long wj = m.words[j];
+                    if ((wj & sP.maskA) == xa) ci += cgj & kCntMask;
+                    if ((wj & sP.maskB) == xb) cj += cgj & kCntMask;
                 }
             }
             Ci = warp_sum_u(ci); Cj = warp_sum_u(cj);
         } else if (xg == GA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
 
-        adjust(P, m, s, xg, xw, -1, lane);      // H' = H - x  (:168)
+        adjust(s, xg, xw, -1);                  // H' = H - x  (:168)
         const int ns = s.nslots;
-        const double* row_m1 = row_ptr(P, tset, n - 1);
-        const double* row_0 = row_ptr(P, tset, n);
-        const double* row_m2 = row_ptr(P, tset, n - 2);
-        int ncand = 0;
-        double pi0 = 0.0;
+        const bool isC = (xg == GC), isA = (xg == GA);
+        const int Lx = isC ? Ltot : (isA ? LA : LB), offb = (xg == GB) ? LA : 0;
+        const int pg = isA ? GB : GA;
+        const unsigned int own = isA ? Ai : Bj, ownC = isA ? Ci : Cj;
+        const double* row_m1 = row_ptr(tset, n - 1);
+        const double* row_alt = row_ptr(tset, isC ? n : n - 2);      // second row of the one-locus queries
+        const unsigned int nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
 
-        if (xg == GC) {
-            // two-locus queries: x itself and its Ltot one-site mutants, all against H' (:169, :179-187)
-            const int nq = P.Ltot + 1;
-            for (int q0 = 0; q0 < nq; q0 += 32) {
-                const int left = nq - q0;
-                const int p = left >= 32 ? 1 : lanes_per_query(left);
-                const int qi = q0 + lane / p;
-                const bool valid = qi < nq;
-                const unsigned long long qw = (valid && qi > 0) ? (xw ^ (1ull << (qi - 1))) : xw;
-                const double pi = cquery(P, m, ns, lane, p, qw, -1, 0ull, row_m1, (unsigned int)(n - 1));
-                if (valid && (lane & (p - 1)) == 0) { if (qi == 0) m.aux[0] = pi; else m.pv[qi - 1] = pi; }
-            }
-            npi += (unsigned int)nq;
-            // one-locus queries: lane 0 the A part, lane 1 the B part, each against rows n-1 and n (:198-238)
-            double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
-            {
-                const int qg = (lane == 1) ? GB : GA;
-                const unsigned long long qw = (lane == 1) ? xb : xa;
-                const int offw = (lane == 1) ? P.off_wEB : P.off_wEA;
-                if (lane < 2) marginal_query(P, m, ns, qg, qw, false, row_m1 + offw, row_0 + offw, num1, num2, ncomp);
-            }
-            npi += 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
-            const double powl = (lane == 1) ? P.pow2negLB : P.pow2negLA;
-            const double r_m1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, P.wsum);
-            const double r_0 = marginal_finish(num2, ncomp, (unsigned int)n, powl, P.wsum);
-            const double piA_m1 = __shfl_sync(kFull, r_m1, 0), piA_0 = __shfl_sync(kFull, r_0, 0);
-            const double piB_m1 = __shfl_sync(kFull, r_m1, 1), piB_0 = __shfl_sync(kFull, r_0, 1);
-            __syncwarp();
-            pi0 = m.aux[0];
-            // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
-            const double pj = 0.5 * piA_m1 * piB_0 + 0.5 * piB_m1 * piA_0;
-            ncand = P.Ltot + 4;
-            for (int k = lane; k < P.Ltot; k += 32) m.pv[k] = ec.dtheta * (double)Cij * m.pv[k] / pi0;
-            if (lane == 0) {
-                m.pv[P.Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
-                m.pv[P.Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / piA_m1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
-                m.pv[P.Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / piB_m1 : 0.0;
-                m.pv[P.Ltot + 3] = ec.drho * (double)Cij * pj / pi0;
-            }
-        } else {
-            // A-only (or, mirrored, B-only) lineage chosen (:298-449)
-            const bool isA = (xg == GA);
-            const int Lx = isA ? P.LA : P.LB, offb = isA ? 0 : P.LA;
-            const int pg = isA ? GB : GA;
-            const int off_own = isA ? P.off_wEA : P.off_wEB, off_oth = isA ? P.off_wEB : P.off_wEA;
-            const double pow_own = isA ? P.pow2negLA : P.pow2negLB, pow_oth = isA ? P.pow2negLB : P.pow2negLA;
-            const unsigned int own = isA ? Ai : Bj, ownC = isA ? Ci : Cj;
-            // partner list = stored types of the other one-locus class, slot order (:300 / :377)
-            int np = 0;
+        // partner list = stored types of the other one-locus class, slot order (:300 / :377)
+        int np = 0;
+        if (!isC) {
+#pragma unroll 1
             for (int base = 0; base < ns; base += 32) {
                 const int j = base + lane;
                 const bool is = j < ns && (int)(m.cg[j] >> 30) == pg && (m.cg[j] & kCntMask) > 0;
@@ -456,156 +457,153 @@ __device__ void run_history(const DevProblem& P, const SampleArgs& A, const Warp
                 np += __popc(b);
             }
             __syncwarp();
-            // one-locus queries, one per lane: 0 = x (rows n-1 and n-2), 1..Lx = mutants (row n-1),
-            // then one per partner b_k: pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2
-            const int nm = 1 + Lx + np;
-            double pi_x_m2 = 0.0;
-            for (int q0 = 0; q0 < nm; q0 += 32) {
-                const int qi = q0 + lane;
-                const bool valid = qi < nm;
-                const bool partner = valid && qi > Lx;
-                int qg = xg; unsigned long long qw = xw; bool excl = false; int offw = off_own; double powl = pow_own;
-                if (valid && qi >= 1 && qi <= Lx) qw = xw ^ (1ull << (offb + qi - 1));
-                if (partner) { qg = pg; qw = m.words[m.plist[qi - Lx - 1]]; excl = true; offw = off_oth; powl = pow_oth; }
-                double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
-                if (valid) marginal_query(P, m, ns, qg, qw, excl, row_m1 + offw, row_m2 + offw, num1, num2, ncomp);
-                const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, P.wsum);
-                const double v2 = marginal_finish(num2, ncomp, (unsigned int)(n - 2 < 0 ? 0 : n - 2), powl, P.wsum);
-                if (q0 == 0) { pi0 = __shfl_sync(kFull, v1, 0); pi_x_m2 = __shfl_sync(kFull, v2, 0); }
-                if (valid && qi >= 1 && qi <= Lx) m.pv[qi - 1] = ec.dtheta * (double)own * v1 / pi0;
+        }
+
+        // ---- one-locus queries, one per lane -------------------------------------------------------------
+        //  C chosen: lane 0 = A part, lane 1 = B part, rows n-1 and n (:198-238 with :120-132)
+        //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
+        //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
+        const int nm = isC ? 2 : 1 + Lx + np;
+        double pi0 = 0.0, mA1 = 0.0, mA2 = 0.0, mB1 = 0.0, mB2 = 0.0;
+#pragma unroll 1
+        for (int q0 = 0; q0 < nm; q0 += 32) {
+            const int qi = q0 + lane;
+            const bool valid = qi < nm;
+            const bool partner = !isC && valid && qi > Lx;
+            int qg; unsigned long long qw; bool excl = false;
+            if (isC) { qg = (qi == 1) ? GB : GA; qw = (qi == 1) ? xb : xa; }
+            else if (partner) { qg = pg; qw = m.words[m.plist[qi - Lx - 1]]; excl = true; }
+            else { qg = xg; qw = (valid && qi >= 1) ? (xw ^ (1ull << (offb + qi - 1))) : xw; }
+            const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
+            const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
+            double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
+            if (valid) marginal_query(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
+            const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
+            const double v2 = marginal_finish(num2, ncomp, nc_alt, powl, sP.wsum);
+            if (q0 == 0) {
+                mA1 = __shfl_sync(kFull, v1, 0); mA2 = __shfl_sync(kFull, v2, 0);
+                mB1 = __shfl_sync(kFull, v1, 1); mB2 = __shfl_sync(kFull, v2, 1);
+                if (!isC) pi0 = mA1;
+            }
+            if (!isC && valid) {
+                if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = ec.dtheta * (double)own * v1 / pi0;
                 // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
-                if (partner) m.aux[qi - Lx - 1] = 0.5 * pi_x_m2 * v1 + 0.5 * v2 * pi0;
+                if (partner) m.aux[qi - Lx - 1] = 0.5 * mA2 * v1 + 0.5 * v2 * pi0;
             }
-            npi += (unsigned int)(1 + Lx + 5 * np);
-            __syncwarp();
-            // two-locus queries: the joined haplotype (x, b_k) against H' - b_k  (:325 / :402)
-            for (int q0 = 0; q0 < np; q0 += 32) {
-                const int left = np - q0;
-                const int p = left >= 32 ? 1 : lanes_per_query(left);
-                const int qi = q0 + lane / p;
-                const bool valid = qi < np;
-                const int pslot = (int)m.plist[valid ? qi : q0];
-                const unsigned long long pw = m.words[pslot];
-                const double pi = cquery(P, m, ns, lane, p, xw | pw, pg, pw, row_m2, (unsigned int)(n - 2));
-                if (valid && (lane & (p - 1)) == 0) {
-                    const double pc = (double)(m.cg[pslot] & kCntMask);
-                    m.pv[Lx + qi] = (double)own * pc * pi / m.aux[qi];
-                }
+        }
+        __syncwarp();
+
+        // ---- two-locus queries ---------------------------------------------------------------------------
+        //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
+        //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
+        const int nq = isC ? Ltot + 1 : np;
+        const double* crow = isC ? row_m1 : row_alt;
+        const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
+#pragma unroll 1
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int left = nq - q0;
+            const int p = left >= 32 ? 1 : lanes_per_query(left);
+            const int qi = q0 + lane / p;
+            const bool valid = qi < nq;
+            unsigned long long qw, delw = 0ull; int delg = -1; int pslot = 0;
+            if (isC) qw = (valid && qi > 0) ? (xw ^ (1ull << (qi - 1))) : xw;
+            else { pslot = (int)m.plist[valid ? qi : q0]; delw = m.words[pslot]; delg = pg; qw = xw | delw; }
+            const double pi = cquery(m, ns, lane, p, qw, delg, delw, crow, cn);
+            if (valid && (lane & (p - 1)) == 0) {
+                if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
+                else m.pv[Lx + qi] = (double)own * (double)(m.cg[pslot] & kCntMask) * pi / m.aux[qi];
             }
+        }
+        __syncwarp();
+
+        int ncand;
+        if (isC) {
+            pi0 = m.sd[2];
+            // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
+            const double pj = 0.5 * mA1 * mB2 + 0.5 * mB1 * mA2;
+#pragma unroll 1
+            for (int k = lane; k < Ltot; k += 32) m.pv[k] = ec.dtheta * (double)Cij * m.pv[k] / pi0;
+            if (lane == 0) {
+                m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
+                m.pv[Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
+                m.pv[Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / mB1 : 0.0;
+                m.pv[Ltot + 3] = ec.drho * (double)Cij * pj / pi0;
+            }
+            ncand = Ltot + 4;
+            npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
+        } else {
             if (lane == 0) m.pv[Lx + np] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) / pi0 : 0.0;
             ncand = Lx + np + 1;
+            npi += (unsigned int)(1 + Lx + 5 * np);
         }
         __syncwarp();
 
         // ---- sample the move (sampleFromVector :568-583) ----
-        double total = 0.0;
-        for (int base = 0; base < ncand; base += 32) {
-            const int k = base + lane;
-            const double v = k < ncand ? m.pv[k] : 0.0;
-            total = __shfl_sync(kFull, warp_incl_scan(v, lane) + total, 31);
-        }
-        const double u_move = philox_uniform(A.seed, hist, draw++);
-        const double target = u_move * total;
-        int idx = -1; double pidx = 0.0;
-        {
-            double carry = 0.0;
-            for (int base = 0; base < ncand && idx < 0; base += 32) {
-                const int k = base + lane;
-                const double v = k < ncand ? m.pv[k] : 0.0;
-                const double cum = warp_incl_scan(v, lane) + carry;
-                const unsigned int b = __ballot_sync(kFull, k < ncand && !(cum < target));
-                if (b) { const int l = __ffs(b) - 1; idx = base + l; pidx = __shfl_sync(kFull, v, l); }
-                carry = __shfl_sync(kFull, cum, 31);
-            }
-            if (idx < 0) { idx = ncand - 1; pidx = m.pv[idx]; }
-        }
-        q += log(pidx) - log(total);
+        const int idx = pick(ncand, rng.next(), false);
+        // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
+        qsum += -rate * wait;
+        qprod.mul(rate * p_hap * m.sd[0] / m.sd[1]);
 
         // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
         double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
-        int ev_kind = 0; unsigned long long ev_aux = 0ull; int ev_site = 0xff;
-        if (xg == GC) {
-            if (idx < P.Ltot) {
-                const unsigned long long mw = xw ^ (1ull << idx);
-                const int slot = adjust(P, m, s, GC, mw, +1, lane);
-                evc = slot >= 0 ? (double)(m.cg[slot] & kCntMask) : 1.0; kind = 1;
-                ev_kind = 0; ev_aux = mw; ev_site = idx;
-            } else if (idx == P.Ltot) {
-                evc = (double)((unsigned int)Cc * (Cij - 1)); ev_kind = 1;
-            } else if (idx == P.Ltot + 1) {
-                adjust(P, m, s, GC, xw, +1, lane); adjust(P, m, s, GA, xa, -1, lane);
-                evc = (double)((unsigned int)Ac * Cij); ev_kind = 2; ev_aux = xa;
-            } else if (idx == P.Ltot + 2) {
-                adjust(P, m, s, GC, xw, +1, lane); adjust(P, m, s, GB, xb, -1, lane);
-                evc = (double)((unsigned int)Bc * Cij); ev_kind = 3; ev_aux = xb;
-            } else {
-                const int sa = adjust(P, m, s, GA, xa, +1, lane);
-                const int sb = adjust(P, m, s, GB, xb, +1, lane);
-                const double Ai2 = sa >= 0 ? (double)(m.cg[sa] & kCntMask) : 1.0, Bj2 = sb >= 0 ? (double)(m.cg[sb] & kCntMask) : 1.0;
-                evc = (double)Cc * Ai2 * Bj2 / (((double)Ac + 1.0) * ((double)Bc + 1.0)); kind = 2; ev_kind = 4;
-            }
+        int ev_kind = 1; unsigned long long ev_aux = 0ull; int ev_site = 0xff;
+        int og0 = 0, og1 = 0, od0 = 0, od1 = 0, nops = 0; unsigned long long ow0 = 0ull, ow1 = 0ull;
+        if (idx < Lx) {                                                        // mutation of site idx
+            ow0 = xw ^ (1ull << (offb + idx)); og0 = xg; od0 = +1; nops = 1;
+            kind = 1; ev_kind = 0; ev_aux = ow0; ev_site = idx;
+        } else if (isC) {
+            if (idx == Ltot) { evc = (double)((unsigned int)Cc * (Cij - 1)); }
+            else if (idx == Ltot + 1) { og0 = GC; ow0 = xw; od0 = +1; og1 = GA; ow1 = xa; od1 = -1; nops = 2;
+                                        evc = (double)((unsigned int)Ac * Cij); ev_kind = 2; ev_aux = xa; }
+            else if (idx == Ltot + 2) { og0 = GC; ow0 = xw; od0 = +1; og1 = GB; ow1 = xb; od1 = -1; nops = 2;
+                                        evc = (double)((unsigned int)Bc * Cij); ev_kind = 3; ev_aux = xb; }
+            else { og0 = GA; ow0 = xa; od0 = +1; og1 = GB; ow1 = xb; od1 = +1; nops = 2; kind = 2; ev_kind = 4; }
+        } else if (idx < Lx + np) {                                            // A^B_k coalescence
+            const unsigned long long pw = m.words[m.plist[idx - Lx]];
+            og0 = pg; ow0 = pw; od0 = -1; og1 = GC; ow1 = xw | pw; od1 = +1; nops = 2;
+            ev_kind = 5; ev_aux = pw;
         } else {
-            const bool isA = (xg == GA);
-            const int Lx = isA ? P.LA : P.LB, offb = isA ? 0 : P.LA;
-            const int np = ncand - Lx - 1;
-            if (idx < Lx) {
-                const unsigned long long mw = xw ^ (1ull << (offb + idx));
-                const int slot = adjust(P, m, s, xg, mw, +1, lane);
-                evc = slot >= 0 ? (double)(m.cg[slot] & kCntMask) : 1.0; kind = 1;
-                ev_kind = 0; ev_aux = mw; ev_site = idx;
-            } else if (idx < Lx + np) {
-                const unsigned long long pw = m.words[m.plist[idx - Lx]];
-                adjust(P, m, s, isA ? GB : GA, pw, -1, lane);
-                const int slot = adjust(P, m, s, GC, xw | pw, +1, lane);
-                const double Cnew = slot >= 0 ? (double)(m.cg[slot] & kCntMask) : 1.0;
-                evc = (double)((unsigned int)Ac * (unsigned int)Bc) * Cnew / ((double)Cc + 1.0);
-                ev_kind = 5; ev_aux = pw;
-            } else {
-                evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
-                ev_kind = 1;
-            }
+            evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
         }
-        commit(m, s, lane);
-        if (tracing && lane == 0) {
-            if (nev < A.max_events) {
-                coalgpu_event& r = A.events[(unsigned long long)h * A.max_events + nev];
-                r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
-                r.epoch = (uint8_t)e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
-            }
+        double after0 = 1.0, after1 = 1.0;
+        if (nops > 0) { const int slot = adjust(s, og0, ow0, od0); if (slot >= 0) after0 = (double)(m.cg[slot] & kCntMask); }
+        if (nops > 1) { const int slot = adjust(s, og1, ow1, od1); if (slot >= 0) after1 = (double)(m.cg[slot] & kCntMask); }
+        if (ev_kind == 0) evc = after0;
+        else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
+        else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
+        s.nslots = commit(m, s.nslots, lane);
+        if (tracing && lane == 0 && nev < sA.max_events) {
+            coalgpu_event& r = sA.events[(unsigned long long)h * sA.max_events + nev];
+            r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
+            r.epoch = (uint8_t)e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
         }
         nev++;
 
         // ---- target density bookkeeping (:457-546) ----
-        {
-            const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
-            const double aa = (double)((Ac + Cc) * P.LA + (Bc + Cc) * P.LB);
-            st.slog += log(evc);
-            st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
-            if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
-            if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; post = false; }
-            else st.n_rate++;
-        }
+        evprod.mul(evc);
+        st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
+        if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
+        if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; post = false; }
+        else st.n_rate++;
         if (s.overflow) break;
         if (nev >= (1u << 18)) { s.overflow = true; break; }   // runaway guard: histories have O(10^2-10^3) events
     }
 
     // ---- final weight (ProposalEngine.cpp:817-858) ----
-    flush_epoch(e);
-    const int nt = s.nA + s.nB + s.nC;
     const double ln2 = 0.69314718055994530942;
-    const double fin = consts + P.perm_const - q
-                     - ((double)(P.LA + P.LB) * ln2 * (double)s.nC + (double)P.LA * ln2 * (double)s.nA + (double)P.LB * ln2 * (double)s.nB);
+    const double q = qsum + qprod.value();
+    const double fin = consts + sP.perm_const - q
+                     - ((double)(LA + LB) * ln2 * (double)s.nC + (double)LA * ln2 * (double)s.nA + (double)LB * ln2 * (double)s.nB);
     if (wout) {
         __syncwarp();
         const double bad = __longlong_as_double(0x7ff8000000000000ll);
-        for (int g = lane; g < P.G; g += 32) wout[g] = s.overflow ? bad : wout[g] + fin;
+        for (int g = lane; g < G; g += 32) wout[g] = s.overflow ? bad : wout[g] + fin;
     }
     if (lane == 0) {
-        if (A.tmrca) A.tmrca[h] = tsum;
-        if (A.lineages) A.lineages[h * (unsigned long long)P.T + (P.T - 1)] = (double)nt;
-        if (A.nevents) A.nevents[h] = nev;
-        if (tracing && A.event_counts) A.event_counts[h] = nev;
-        if (s.overflow) atomicAdd(A.counters + 3, 1ull);
+        if (sA.tmrca) sA.tmrca[h] = tsum;
+        if (sA.nevents) sA.nevents[h] = nev;
+        if (tracing && sA.event_counts) sA.event_counts[h] = nev;
+        if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
     }
     ev_total += nev; pi_total += npi;
 }
@@ -613,20 +611,24 @@ __device__ void run_history(const DevProblem& P, const SampleArgs& A, const Warp
 }  // namespace
 
 // K1: persistent warps pull history indices from a global counter until the batch is drawn.
-__global__ void __launch_bounds__(128) history_kernel(DevProblem P, SampleArgs A, int warp_bytes) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpMem m = carve(smem + (size_t)warp * warp_bytes, P.kmax, P.pvmax);
+#ifndef COAL_MIN_CTAS
+#define COAL_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
+    if (threadIdx.x == 0) { sP = P; sA = A; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     unsigned long long ev_total = 0, pi_total = 0;
+#pragma unroll 1
     for (;;) {
         unsigned long long h = 0;
-        if (lane == 0) h = atomicAdd(A.counters, 1ull);
+        if (lane == 0) h = atomicAdd(sA.counters, 1ull);
         h = __shfl_sync(kFull, h, 0);
-        if (h >= A.n) break;
-        run_history(P, A, m, h, lane, ev_total, pi_total);
+        if (h >= sA.n) break;
+        run_history(h, lane, ev_total, pi_total);
         __syncwarp();
     }
-    if (lane == 0) { atomicAdd(A.counters + 1, ev_total); atomicAdd(A.counters + 2, pi_total); }
+    if (lane == 0) { atomicAdd(sA.counters + 1, ev_total); atomicAdd(sA.counters + 2, pi_total); }
 }
 
 // K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC).
@@ -636,9 +638,8 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
                                                             const long long* __restrict__ offs, const int* __restrict__ cnt,
                                                             const int* __restrict__ dA, const int* __restrict__ dB,
                                                             double* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(smem) + (size_t)warp * (P.Ltot + 2) * 32;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(smem_dyn) + (size_t)warp * (P.Ltot + 2) * 32;
     const int p = 16, r = lane & 15;
     const long long qbase = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 2;
     for (long long q0 = qbase; q0 < nq; q0 += (long long)gridDim.x * (blockDim.x >> 5) * 2) {
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
         const int g = valid ? gamma[qi] : GC;
         const unsigned int n = valid ? (unsigned int)n_all[qi] : 1u;
         const int set = valid ? P.set_of_epoch[tidx[qi]] : 0;
-        const double* row = row_ptr(P, set, (int)n);
+        const double* row = P.rows + ((size_t)set * P.n_max + (n - 1)) * P.row_doubles;
         unsigned int* col = hist + lane;
         ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
         double num = 0.0; unsigned int ncomp = 0;
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
             ChunkPartial cp = {0, 0, 0, 0, 0, 0};
             auto ld = [row](int off) { return __ldg(row + off); };
             if (g == GC && nH > 0) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB, P.LA, P.LB,
-                                           col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
+                                                      col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
             double ipre = cp.pre, ipreB = cp.preB;
             for (int o = 1; o < p; o <<= 1) {
                 const double t1 = __shfl_up_sync(kFull, ipre, o, p), t2 = __shfl_up_sync(kFull, ipreB, o, p);

@@ -21,7 +21,7 @@ import numpy as np
 from .problem import Problem
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcoalgpu.so")
+LIB_PATH = os.environ.get("COALGPU_LIB") or os.path.join(HERE, "libcoalgpu.so")   # COALGPU_LIB: tuning variants only
 
 EVENT_DTYPE = np.dtype([("chosen_word", "<u8"), ("aux_word", "<u8"), ("chosen_gamma", "u1"), ("kind", "u1"),
                         ("epoch", "u1"), ("site", "u1"), ("n_before", "<u4")])
