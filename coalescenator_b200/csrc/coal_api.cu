@@ -352,8 +352,8 @@ int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* 
     if (y) std::memcpy(y, yy, sizeof(double) * kQ);
     if (z) for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
         z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? s->tab.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
-    if (EA) std::memcpy(EA, row + lay.off_EA, sizeof(double) * kQ * (s->LA + 1));
-    if (EB) std::memcpy(EB, row + lay.off_EB, sizeof(double) * kQ * (s->LB + 1));
+    if (EA) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LA; d++) EA[i * (s->LA + 1) + d] = row[lay.off_EA + d * kQ + i];
+    if (EB) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LB; d++) EB[i * (s->LB + 1) + d] = row[lay.off_EB + d * kQ + i];
     return 0;
 }
 

@@ -30,7 +30,7 @@ struct WarpMem {
     unsigned int* xc;            // [kmax]  cross counts: C slot: cntA(A part) | cntB(B part) << 16;
                                  //         A slot: C lineages with this A part; B slot: likewise
     unsigned int* plist;         // [kmax]  slot index of each partner
-    unsigned int* hist;          // [(Ltot+2)*32] one class-histogram column per lane
+    unsigned int* hist;          // [32][hstride] class histogram / class list of each query of the batch (hstride odd)
     double* sd;                  // [4]     scalar results of the out-of-line helpers
 };
 
@@ -40,7 +40,7 @@ __host__ __device__ inline size_t warp_mem_bytes(int kmax, int pvmax, int Ltot) 
     b += (size_t)pvmax * 8;                // pv
     b += (size_t)kmax * 8;                 // aux
     b += (size_t)kmax * 4 * 3;             // cg, xc, plist
-    b += (size_t)(Ltot + 2) * 32 * 4;      // hist
+    b += (size_t)((Ltot + 2) | 1) * 32 * 4;  // hist
     b += 4 * 8;                            // sd
     return (b + 15) & ~(size_t)15;
 }
@@ -55,7 +55,7 @@ __device__ __forceinline__ WarpMem wm() {
     m.cg = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.xc = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.plist = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
-    m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)(sP.Ltot + 2) * 32 * 4;
+    m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)((sP.Ltot + 2) | 1) * 32 * 4;
     m.sd = reinterpret_cast<double*>(base);
     return m;
 }
@@ -223,58 +223,84 @@ __device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int
     }
 }
 
-// Two-locus query. Lanes are organised in groups of p (power of two): every lane of a group builds the
-// class histogram of the group's query in its own shared-memory column (TypeContainer::getDifferences,
-// TypeContainer.cpp:802-886 incl. the dA+dB collapse of SURVEY.md Q1), then takes Q/p of the intervals of
-// the forward pass. (delg, delw): one copy of that stored type is left out (delg < 0: none).
-__device__ __forceinline__ double cquery(const WarpMem& m, int nslots, int lane, int p, unsigned long long qw,
-                                         int delg, unsigned long long delw, const double* __restrict__ row, unsigned int n_cond) {
-    unsigned int* col = m.hist + lane;
-    const int Ltot = sP.Ltot, nsum = Ltot + 2;
+// Two-locus queries of one event, phase 1: class lists (TypeContainer::getDifferences for a C query,
+// TypeContainer.cpp:802-886, incl. the dA+dB collapse of SURVEY.md Q1) of up to 32 queries at once, one
+// query per lane: every lane walks the stored types (broadcast reads) and accumulates its own histogram row
+// (rows are query-major with an odd stride: conflict-free here, in the compaction and in the forward pass).
+//  C chosen:   query qb+q = x (q = 0) or x with site q-1 flipped, against H'
+//  A/B chosen: query qb+q = (x, b_k) with b_k = partner plist[qb+q], against H' - b_k
+// On return lane q < nqb holds (nH, totals) of query q and its class list sits in hist[q*hstride ...].
+// (A lanes-over-types variant with match.any + group reductions was 1.8x slower: profiles/r1_v2_*.)
+__device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb, int qb, bool isC, unsigned long long xw, int pg,
+                                              int lane, int& nH_out, ClassTotals& tot_out) {
+    const int nsum = sP.Ltot + 2, hstride = nsum | 1;
     const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
+    unsigned int* mine = m.hist + lane * hstride;
+    const bool active = lane < nqb;
+    unsigned long long qw = xw, delw = 0ull; int delg = -1;
+    if (active) {
+        const int qi = qb + lane;
+        if (isC) { if (qi > 0) qw = xw ^ (1ull << (qi - 1)); }
+        else { delw = m.words[m.plist[qi]]; delg = pg; qw = xw | delw; }
 #pragma unroll 1
-    for (int sidx = 0; sidx < nsum; sidx++) col[sidx * 32] = 0xffff0000u;
+        for (int sidx = 0; sidx < nsum; sidx++) mine[sidx] = 0xffff0000u;
 #pragma unroll 2
-    for (int j = 0; j < nslots; j++) {
-        const unsigned long long wj = m.words[j];
-        const unsigned int cgj = m.cg[j];
-        const int gj = (int)(cgj >> 30);
-        unsigned int c = cgj & kCntMask;
-        if (gj == delg && wj == delw) c -= 1;
-        if (c > 0) {
-            const unsigned long long x = wj ^ qw;
-            const int da = __popcll(x & maskA), db = __popcll(x & maskB);
-            int sidx; unsigned int rep;
-            if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
-            const unsigned int v = col[sidx * 32];
-            col[sidx * 32] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
+        for (int j = 0; j < ns; j++) {
+            const unsigned long long wj = m.words[j];
+            const unsigned int cgj = m.cg[j];
+            const int gj = (int)(cgj >> 30);
+            unsigned int c = cgj & kCntMask;
+            if (gj == delg && wj == delw) c -= 1;
+            if (c > 0) {
+                const unsigned long long y = wj ^ qw;
+                const int da = __popcll(y & maskA), db = __popcll(y & maskB);
+                int sidx; unsigned int rep;
+                if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
+                const unsigned int v = mine[sidx];
+                mine[sidx] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
+            }
         }
     }
-    // compact the classes in place (ascending dA+dB) and collect the totals
+    // compact the classes of query `lane` in place (ascending dA+dB) and collect the totals
     int nH = 0;
     ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
+    if (lane < nqb) {
 #pragma unroll 1
-    for (int sidx = 0; sidx < nsum; sidx++) {
-        const unsigned int v = col[sidx * 32];
-        const unsigned int cnt = v & 0xffffu;
-        if (cnt) {
-            const unsigned int rep = v >> 16;
-            int dA, dB;
-            if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
-            col[nH * 32] = pack_class(cnt, dA, dB);
-            nH++;
-            tot.n += cnt;
-            if (dA >= 0) tot.ncompA += cnt;
-            if (dB >= 0) tot.ncompB += cnt;
+        for (int sidx = 0; sidx < nsum; sidx++) {
+            const unsigned int v = mine[sidx];
+            const unsigned int cnt = v & 0xffffu;
+            if (cnt) {
+                const unsigned int rep = v >> 16;
+                int dA, dB;
+                if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
+                mine[nH] = pack_class(cnt, dA, dB);
+                nH++;
+                tot.n += cnt;
+                if (dA >= 0) tot.ncompA += cnt;
+                if (dB >= 0) tot.ncompB += cnt;
+            }
         }
     }
+    __syncwarp();
+    nH_out = nH; tot_out = tot;
+}
+
+// Two-locus queries, phase 2: the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) of one query
+// per group of p lanes (p a power of two), lane r of the group taking the intervals [r*16/p, (r+1)*16/p).
+__device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, ClassTotals tot, int p, int lane,
+                                               const double* __restrict__ row, unsigned int n_cond) {
     const bool empty = (n_cond == 0 || nH == 0);     // empty configuration, ConditionalSamplingHMM.cpp:277-298
     const int r = lane & (p - 1);
     const int per = kQd / p;
+    const int i0 = r * per;
     auto ld = [row](int off) { return __ldg(row + off); };
     ChunkPartial cp = {0, 0, 0, 0, 0, 0};
-    if (!empty) cp = chunk_forward(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB,
-                                   sP.LA, sP.LB, col, 32, nH, tot, sP.pow2negLA, sP.pow2negLB, r * per, r * per + per);
+    if (!empty) {
+#define COAL_FWD(PER) chunk_forward<PER>(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
+                                          cls, 1, nH, tot, sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
+        if (per == 1) cp = COAL_FWD(1); else if (per == 2) cp = COAL_FWD(2); else cp = COAL_FWD(4);
+#undef COAL_FWD
+    }
     // exclusive prefixes of (pre, preB) over the lanes of the group
     double ipre = cp.pre, ipreB = cp.preB;
 #pragma unroll 1
@@ -292,12 +318,6 @@ __device__ __forceinline__ double cquery(const WarpMem& m, int nslots, int lane,
         acc2 += __shfl_xor_sync(kFull, acc2, o);
     }
     return empty ? sP.pow2negL : pismc_finish(acc, acc2, tot.n);
-}
-
-__device__ __forceinline__ int lanes_per_query(int nq) {
-    int p = 1;
-    while (p < kQd && nq * (p * 2) <= 32) p *= 2;
-    return p;
 }
 
 __device__ __forceinline__ const double* row_ptr(int set, int n_all) {
@@ -499,20 +519,37 @@ __device__ void run_history(unsigned long long h, int lane, unsigned long long& 
         const int nq = isC ? Ltot + 1 : np;
         const double* crow = isC ? row_m1 : row_alt;
         const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
+        const int hstride = (Ltot + 2) | 1;
 #pragma unroll 1
-        for (int q0 = 0; q0 < nq; q0 += 32) {
-            const int left = nq - q0;
-            const int p = left >= 32 ? 1 : lanes_per_query(left);
-            const int qi = q0 + lane / p;
-            const bool valid = qi < nq;
-            unsigned long long qw, delw = 0ull; int delg = -1; int pslot = 0;
-            if (isC) qw = (valid && qi > 0) ? (xw ^ (1ull << (qi - 1))) : xw;
-            else { pslot = (int)m.plist[valid ? qi : q0]; delw = m.words[pslot]; delg = pg; qw = xw | delw; }
-            const double pi = cquery(m, ns, lane, p, qw, delg, delw, crow, cn);
-            if (valid && (lane & (p - 1)) == 0) {
-                if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
-                else m.pv[Lx + qi] = (double)own * (double)(m.cg[pslot] & kCntMask) * pi / m.aux[qi];
+        for (int qb = 0; qb < nq; qb += 32) {
+            const int nqb = min(32, nq - qb);
+            int my_nH; ClassTotals my_tot;
+            build_classes(m, ns, nqb, qb, isC, xw, pg, lane, my_nH, my_tot);
+            // one pass: groups of p lanes per query, p the largest power of two with nqb * p <= 32 (<= 16).
+            // (Splitting the batch into several always-full passes costs more in per-pass set-up than the idle
+            // lanes cost here: 168k vs 198k histories/s, profiles/r1_v2_notes.md.)
+            {
+                int p = 1;
+                while (p < kQd && nqb * (p * 2) <= 32) p *= 2;
+                const int ql = lane / p;
+                const bool valid = ql < nqb;
+                const int qloc = valid ? ql : 0;
+                const int nH = __shfl_sync(kFull, my_nH, qloc);
+                ClassTotals tot;
+                tot.n = __shfl_sync(kFull, my_tot.n, qloc);
+                tot.ncompA = __shfl_sync(kFull, my_tot.ncompA, qloc);
+                tot.ncompB = __shfl_sync(kFull, my_tot.ncompB, qloc);
+                const double pi = forward_pass(m.hist + qloc * hstride, nH, tot, p, lane, crow, cn);
+                if (valid && (lane & (p - 1)) == 0) {
+                    const int qi = qb + qloc;
+                    if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
+                    else {
+                        const int pslot = (int)m.plist[qi];
+                        m.pv[Lx + qi] = (double)own * (double)(m.cg[pslot] & kCntMask) * pi / m.aux[qi];
+                    }
+                }
             }
+            __syncwarp();
         }
         __syncwarp();
 
@@ -667,8 +704,8 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
         {
             ChunkPartial cp = {0, 0, 0, 0, 0, 0};
             auto ld = [row](int off) { return __ldg(row + off); };
-            if (g == GC && nH > 0) cp = chunk_forward(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB, P.LA, P.LB,
-                                                      col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
+            if (g == GC && nH > 0) cp = chunk_forward<1>(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
+                                                         col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
             double ipre = cp.pre, ipreB = cp.preB;
             for (int o = 1; o < p; o <<= 1) {
                 const double t1 = __shfl_up_sync(kFull, ipre, o, p), t2 = __shfl_up_sync(kFull, ipreB, o, p);

@@ -42,42 +42,54 @@ struct ClassTotals {
     uint32_t ncompB;
 };
 
-// Forward sweep over intervals [i0, i1) for one query. `cls` is read with stride `cstride`
-// (32 on the device: one shared-memory column per lane).
-template <class LoadF>
+// Forward sweep over intervals [i0, i1) for one query, in blocks of PER intervals (PER divides i1 - i0).
+// The loop nest is class-outer / interval-inner so that the class word is decoded once per block and the
+// PER table reads of a class are independent loads. Emission tables are stored distance-major
+// (E[d*16 + i], see coal_tables.h), i.e. the intervals of one class are contiguous.
+// `cls` is read with stride `cstride` (32 on the device: one shared-memory column per query).
+template <int PER, class LoadF>
 COAL_HD ChunkPartial chunk_forward(LoadF ld, const double* w, int off_yw, int off_zlow, int off_g, int off_zdiag,
-                                   int off_EA, int off_EB, int LA, int LB, const uint32_t* cls, int cstride, int nH,
+                                   int off_EA, int off_EB, const uint32_t* cls, int cstride, int nH,
                                    ClassTotals tot, double pow2negLA, double pow2negLB, int i0, int i1) {
     ChunkPartial p = {0, 0, 0, 0, 0, 0};
     const double invA = tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0;
     const double invB = tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0;
     const double npartA = (double)(tot.n - tot.ncompA), npartB = (double)(tot.n - tot.ncompB);
-    for (int i = i0; i < i1; i++) {
-        double aAll = 0, bAll = 0, x = 0, aAo = 0, bBo = 0;
-        const int ea_base = off_EA + i * (LA + 1), eb_base = off_EB + i * (LB + 1);
+    for (int ib = i0; ib < i1; ib += PER) {
+        double aAll[PER], bAll[PER], x[PER], aAo[PER], bBo[PER];
+#pragma unroll
+        for (int ii = 0; ii < PER; ii++) { aAll[ii] = 0; bAll[ii] = 0; x[ii] = 0; aAo[ii] = 0; bBo[ii] = 0; }
         for (int k = 0; k < nH; k++) {
             const uint32_t v = cls[k * cstride];
             const double c = (double)(v & 0xffffu);
             const int dA = (int)((v >> 16) & 0xffu) - 1, dB = (int)(v >> 24) - 1;
-            const double ea = dA >= 0 ? ld(ea_base + dA) : 0.0;
-            const double eb = dB >= 0 ? ld(eb_base + dB) : 0.0;
-            const double ca = c * ea, cb = c * eb;
-            aAll += ca; bAll += cb; x += ca * eb;
-            aAo += dB < 0 ? ca : 0.0;
-            bBo += dA < 0 ? cb : 0.0;
+            const int ea_base = off_EA + (dA < 0 ? 0 : dA) * 16 + ib, eb_base = off_EB + (dB < 0 ? 0 : dB) * 16 + ib;
+            const double ca0 = dA >= 0 ? c : 0.0, cb0 = dB >= 0 ? c : 0.0;
+#pragma unroll
+            for (int ii = 0; ii < PER; ii++) {
+                const double eb = ld(eb_base + ii);
+                const double ca = ca0 * ld(ea_base + ii), cb = cb0 * eb;
+                aAll[ii] += ca; bAll[ii] += cb; x[ii] += ca * (dB >= 0 ? eb : 0.0);
+                if (dB < 0) aAo[ii] += ca;
+                if (dA < 0) bBo[ii] += cb;
+            }
         }
-        const double PA = tot.ncompA ? aAll * invA : pow2negLA;
-        const double PB = tot.ncompB ? bAll * invB : pow2negLB;
-        const double Ai = aAll + npartA * PA, Bi = bAll + npartB * PB;
-        const double Xi = x + PB * aAo + PA * bBo;
-        const double wi = w[i];
-        const double bi = wi * Ai;
-        p.acc += Bi * (wi * p.pre + ld(off_zdiag + i) * bi) + bi * p.preB;
-        p.acc2 += ld(off_yw + i) * Xi;
-        p.sBw += Bi * wi;
-        p.sb += bi;
-        p.pre += bi * ld(off_g + i);
-        p.preB += Bi * ld(off_zlow + i);
+#pragma unroll
+        for (int ii = 0; ii < PER; ii++) {
+            const int i = ib + ii;
+            const double PA = tot.ncompA ? aAll[ii] * invA : pow2negLA;
+            const double PB = tot.ncompB ? bAll[ii] * invB : pow2negLB;
+            const double Ai = aAll[ii] + npartA * PA, Bi = bAll[ii] + npartB * PB;
+            const double Xi = x[ii] + PB * aAo[ii] + PA * bBo[ii];
+            const double wi = w[i];
+            const double bi = wi * Ai;
+            p.acc += Bi * (wi * p.pre + ld(off_zdiag + i) * bi) + bi * p.preB;
+            p.acc2 += ld(off_yw + i) * Xi;
+            p.sBw += Bi * wi;
+            p.sb += bi;
+            p.pre += bi * ld(off_g + i);
+            p.preB += Bi * ld(off_zlow + i);
+        }
     }
     return p;
 }

@@ -15,7 +15,7 @@ constexpr int kQ = 16;   // quadrature intervals (main.cpp:103 hard-codes 16)
 struct TableLayout {
     int LA = 0, LB = 0;
     int off_yw = 0, off_zlow = kQ, off_g = 2 * kQ, off_zdiag = 3 * kQ;
-    int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;
+    int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;   // EA: [(LA+1)][kQ], EB: [(LB+1)][kQ] (distance-major)
     int row_doubles = 0;   // multiple of 2 (16-byte rows for bulk copies)
     void init(int la, int lb) {
         LA = la; LB = lb;

@@ -32,8 +32,8 @@ int hs_tables(void* hp, int n_all, int time_idx, double* w, double* y, double* z
     std::memcpy(y, t.y.data() + ((size_t)set * t.n_max + (n_all - 1)) * kQ, sizeof(double) * kQ);
     for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
         z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? t.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
-    std::memcpy(EA, row + lay.off_EA, sizeof(double) * kQ * (lay.LA + 1));
-    std::memcpy(EB, row + lay.off_EB, sizeof(double) * kQ * (lay.LB + 1));
+    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LA; d++) EA[i * (lay.LA + 1) + d] = row[lay.off_EA + d * kQ + i];
+    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LB; d++) EB[i * (lay.LB + 1) + d] = row[lay.off_EB + d * kQ + i];
     return t.n_sets;
 }
 
@@ -63,8 +63,11 @@ double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int3
     const int per = kQ / p;
     double pre = 0, preB = 0, acc = 0, acc2 = 0;
     for (int r = 0; r < p; r++) {
-        ChunkPartial cp = chunk_forward(ld, t.w.data(), lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB,
-                                        lay.LA, lay.LB, cls.data(), 1, nH, tot, p2A, p2B, r * per, r * per + per);
+        ChunkPartial cp;
+#define HS_CALL(PER) chunk_forward<PER>(ld, t.w.data(), lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB, \
+                                        cls.data(), 1, nH, tot, p2A, p2B, r * per, r * per + per)
+        if (per == 1) cp = HS_CALL(1); else if (per == 2) cp = HS_CALL(2); else cp = HS_CALL(4);
+#undef HS_CALL
         acc += chunk_finish(cp, pre, preB); acc2 += cp.acc2;
         pre += cp.pre; preB += cp.preB;
     }
