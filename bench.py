@@ -231,15 +231,31 @@ def main():
 
     pk, pk_kind = peaks()
     T = probs[0].T
-    bytes_per_hist = (1 + 1 + T) * 8 + 4          # G=1 weight + tmrca + lineages[T] + event count, written once
+    # HBM roofline (the contract's bound): algorithmic bytes of one launch = what a history must leave in HBM,
+    # (G + 1 + T) doubles + its event count; problem and tables are shared by all histories.
+    bytes_per_hist = (1 + 1 + T) * 8 + 4
     achieved = per_pair * bytes_per_hist / (k_avg_ms * 1e-3) / 1e9
-    flop_per_pismc = 16 * (2 * 16 + 4) * 4.0      # reference's own loop nest at the mean class count
+    # What actually binds is the fp64 pipe / instruction issue. Algorithmic FLOPs per launch (SURVEY.md §8d,
+    # "minimum after hoisting"): P_C (2 Q^2 + 8 nH Q) + P_AB 4 nH Q with the counters of this very run.
+    Q = 16
+    p_c = sum(c["n_two_locus"] for c in cnt)
+    n_cls = sum(c["n_classes"] for c in cnt)
+    nh = n_cls / max(p_c, 1)
+    p_ab = pi_total - p_c
+    flop_total = p_c * 2 * Q * Q + 8 * Q * n_cls + p_ab * 4 * nh * Q
+    flop_per_launch = flop_total / (n_drawn / per_pair)
+    from coalescenator_b200.sampler import fp64_peak_tflops
+    fp64_peak = fp64_peak_tflops(local)
+    fp64_achieved = flop_per_launch / (k_avg_ms * 1e-3) / 1e12
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
             "traffic": None, "peak_kind": pk_kind, "kernel": "history_kernel", "kernel_ms": k_avg_ms,
             "note": "path is fp64-ALU / issue bound, not HBM bound (SURVEY.md §8d): see alu",
-            "alu": {"pismc_per_s": pi_total / n_drawn * per_pair / (k_avg_ms * 1e-3),
+            "alu": {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+                    "peak_kind": "measured in this run (coalgpu_fp64_peak, dependent FMA chains)",
+                    "flop_model": "P_C*(2Q^2+8*nH*Q) + P_AB*4*nH*Q (SURVEY.md 8d)",
                     "events_per_history": ev_total / n_drawn, "pismc_per_history": pi_total / n_drawn,
-                    "algorithmic_fp64_tflops": pi_total / n_drawn * per_pair * flop_per_pismc / (k_avg_ms * 1e-3) / 1e12}}
+                    "two_locus_per_history": p_c / n_drawn, "classes_per_two_locus": nh,
+                    "pismc_per_s": pi_total / n_drawn * per_pair / (k_avg_ms * 1e-3)}}
     line = {"metric": "importance-sampled histories/sec", "value": value, "unit": "histories/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

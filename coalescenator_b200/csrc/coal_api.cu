@@ -193,9 +193,9 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf;
     P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
     CU_OK(cudaMemcpyToSymbol(c_w, s->tab.w.data(), sizeof(double) * kQ));
-    CU_OK(cudaMalloc((void**)&s->d_counters, 4 * sizeof(unsigned long long)));
+    CU_OK(cudaMalloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));
     s->allocs.push_back(s->d_counters);
-    CU_OK(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU_OK(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
 
     // launch geometry: persistent CTAs of 4 warps, as many as shared memory and registers allow
     s->warp_bytes = (int)history_warp_bytes(P.kmax, P.pvmax, P.Ltot);
@@ -241,11 +241,47 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
 int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow) {
     if (!s) return fail(COALGPU_EINVAL, "null sampler");
     CU_OK(cudaSetDevice(s->device));
-    unsigned long long h[4];
+    unsigned long long h[8];
     CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
     if (n_events) *n_events = h[1];
     if (n_pismc) *n_pismc = h[2];
     if (n_overflow) *n_overflow = h[3];
+    return 0;
+}
+
+int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n_classes) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
+    CU_OK(cudaSetDevice(s->device));
+    unsigned long long h[8];
+    CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    if (n_two_locus) *n_two_locus = h[4];
+    if (n_classes) *n_classes = h[5];
+    return 0;
+}
+
+int coalgpu_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(COALGPU_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double* d = nullptr;
+    CU_OK(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU_OK(cudaEventCreate(&e0)); CU_OK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU_OK(cudaEventRecord(e0, 0));
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        g_launches++;
+        CU_OK(cudaEventRecord(e1, 0));
+        CU_OK(cudaEventSynchronize(e1));
+        float ms = 0; CU_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
     return 0;
 }
 

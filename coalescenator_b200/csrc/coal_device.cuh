@@ -59,7 +59,7 @@ struct SampleArgs {
     coalgpu_event* events;    // [n_trace][max_events]
     unsigned int* event_counts;
     unsigned int n_trace, max_events;
-    unsigned long long* counters;   // [0] next history, [1] events, [2] pismc, [3] overflow
+    unsigned long long* counters;   // [0] next history, [1] events, [2] pismc, [3] overflow, [4] two-locus queries, [5] their classes
 };
 
 __constant__ double c_w[kQd];   // interval weights (ConditionalSamplingHMM.cpp:63-71)

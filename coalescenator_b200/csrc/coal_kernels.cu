@@ -339,13 +339,14 @@ struct LogProd {
 
 // ---- one history ------------------------------------------------------------------------------------------
 
-__device__ void run_history(unsigned long long h, int lane, unsigned long long& ev_total, unsigned long long& pi_total) {
+__device__ void run_history(unsigned long long h, int lane, unsigned long long& ev_total, unsigned long long& pi_total,
+                            unsigned long long& cq_total, unsigned int& nh_lane) {
     const WarpMem m = wm();
     const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, G = sP.G;
     PhiloxStream rng; rng.init(sA.seed, sA.first + h);
     HState s; s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
     const bool tracing = sA.events != nullptr && h < sA.n_trace;
-    unsigned int nev = 0, npi = 0;
+    unsigned int nev = 0, npi = 0, ncq = 0;
 
     // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
     int inj_lo = sP.type_off[0], inj_hi = sP.type_off[1];
@@ -525,6 +526,7 @@ __device__ void run_history(unsigned long long h, int lane, unsigned long long& 
             const int nqb = min(32, nq - qb);
             int my_nH; ClassTotals my_tot;
             build_classes(m, ns, nqb, qb, isC, xw, pg, lane, my_nH, my_tot);
+            nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
             // one pass: groups of p lanes per query, p the largest power of two with nqb * p <= 32 (<= 16).
             // (Splitting the batch into several always-full passes costs more in per-pass set-up than the idle
             // lanes cost here: 168k vs 198k histories/s, profiles/r1_v2_notes.md.)
@@ -642,7 +644,7 @@ __device__ void run_history(unsigned long long h, int lane, unsigned long long& 
         if (tracing && sA.event_counts) sA.event_counts[h] = nev;
         if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
     }
-    ev_total += nev; pi_total += npi;
+    ev_total += nev; pi_total += npi; cq_total += ncq;
 }
 
 }  // namespace
@@ -655,17 +657,22 @@ __global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevPr
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    unsigned long long ev_total = 0, pi_total = 0;
+    unsigned long long ev_total = 0, pi_total = 0, cq_total = 0;
+    unsigned int nh_lane = 0;
 #pragma unroll 1
     for (;;) {
         unsigned long long h = 0;
         if (lane == 0) h = atomicAdd(sA.counters, 1ull);
         h = __shfl_sync(kFull, h, 0);
         if (h >= sA.n) break;
-        run_history(h, lane, ev_total, pi_total);
+        run_history(h, lane, ev_total, pi_total, cq_total, nh_lane);
         __syncwarp();
     }
-    if (lane == 0) { atomicAdd(sA.counters + 1, ev_total); atomicAdd(sA.counters + 2, pi_total); }
+    const unsigned long long nh_total = (unsigned long long)warp_sum_u(nh_lane);   // < 2^32 per warp and launch
+    if (lane == 0) {
+        atomicAdd(sA.counters + 1, ev_total); atomicAdd(sA.counters + 2, pi_total);
+        atomicAdd(sA.counters + 4, cq_total); atomicAdd(sA.counters + 5, nh_total);
+    }
 }
 
 // K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC).
@@ -771,6 +778,21 @@ __global__ void lse_combine_kernel(int nblocks, int total, const double* __restr
     double sm = 0.0;
     if (mx > -INFINITY) for (int b = 0; b < nblocks; b++) sm += p[2 * b + 1] * exp(p[2 * b] - mx);
     partials[2 * i] = mx; partials[2 * i + 1] = sm;
+}
+
+// FP64 FMA throughput probe (the roofline denominator of an fp64-ALU-bound path; MEASURED_PEAKS.json has none):
+// 8 independent dependent-FMA chains per thread.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
 size_t history_warp_bytes(int kmax, int pvmax, int Ltot) { return warp_mem_bytes(kmax, pvmax, Ltot); }

@@ -54,7 +54,7 @@ _lib = None
 
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
-           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version"]
+           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak"]
 
 
 def load_library():
@@ -78,6 +78,8 @@ def load_library():
         L.coalgpu_finalize.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.coalgpu_tables.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
         L.coalgpu_pismc_classes.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
+        L.coalgpu_work_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.coalgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -236,7 +238,9 @@ class DeviceSampler:
     def counters(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(self.L.coalgpu_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value)
+        d, e = C.c_uint64(), C.c_uint64()
+        _check(self.L.coalgpu_work_counters(self._h, C.byref(d), C.byref(e)))
+        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value, n_two_locus=d.value, n_classes=e.value)
 
     def events(self, buf) -> List[np.ndarray]:
         """Traced event records per history (the integer history encoding)."""
@@ -265,6 +269,13 @@ class DeviceSampler:
         vp = lambda x: x.ctypes.data_as(C.c_void_p)
         _check(self.L.coalgpu_pismc_classes(self._h, len(g), vp(g), vp(n), vp(t), vp(o), vp(c), vp(a), vp(b), vp(out)))
         return out
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of the device (TFLOP/s)."""
+    v = C.c_double()
+    _check(load_library().coalgpu_fp64_peak(int(device), C.byref(v)))
+    return float(v.value)
 
 
 def launch_count() -> int:

@@ -119,6 +119,14 @@ int coalgpu_finalize(int32_t G, int32_t T, const double* h_partials, coalgpu_res
  * number of histories that overflowed the type-store capacity (must be 0). */
 int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow);
 
+/* Two-locus pi_SMC evaluations drawn so far and the number of haplotype classes they summed over
+ * (the quantities the algorithmic FLOP model of DESIGN.md §5 is written in). */
+int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n_classes);
+
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (dependent-FMA chains, best of 3): the roofline
+ * denominator of this fp64-ALU-bound path (MEASURED_PEAKS.json only carries HBM and bf16 peaks). */
+int coalgpu_fp64_peak(int device, double* tflops);
+
 /* ---- inner seams used by the parity tests ------------------------------------------------------*/
 /* Host copy of the table row for (n_all, time_idx): y[Q], z[Q*Q] (expanded from the structured
  * form the kernels use), EA[Q*(LA+1)], EB[Q*(LB+1)], w[Q]. Any output may be NULL. */

@@ -11,7 +11,7 @@ from conftest import ROOT, has_gpu, load_golden
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "coalgpu.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(coalgpu_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(coalgpu_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_exports_match_header(cuda_lib):
