@@ -213,8 +213,10 @@ def main():
     e2e_n = per_pair
     t0 = time.perf_counter()
     h2d = d2h = 0
+    e2e_dev = 0.0
     for p in probs:
         r = cb.ImportanceSampler().run_sampler(p, e2e_n, seed=4242 + rank, device=local)
+        e2e_dev += r.seconds_device
         d2h += (3 + p.T) * p.G * 2 * 8
         h2d += sum(len(tp) for tp in p.types) * 16 + (p.T * 8 + p.G * p.T * 6) * 8
     torch.cuda.synchronize()
@@ -264,7 +266,7 @@ def main():
                        "parallelism": "dp%d over histories" % world},
             "clocks": clk.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "histories/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "histories": e2e_n * npairs * world},
+                    "histories": e2e_n * npairs * world, "wall_s_rank0": e2e_dt, "device_s_rank0": e2e_dev},
             "roofline": roof}
 
     if not args.no_cpu_baseline:

@@ -85,9 +85,11 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     }
     if (device < 0 || device >= ndev) return fail(COALGPU_ENODEV, "device index out of range");
     CU_OK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
+    // cudaGetDeviceProperties costs tens of milliseconds per call; two attributes are all that is needed
+    int cc_major = 0, sm_count = 0;
+    CU_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
 
     coalgpu_sampler* s = new coalgpu_sampler;
     s->device = device; s->T = p->T; s->LA = p->LA; s->LB = p->LB;
@@ -207,7 +209,7 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     int occ = 0;
     CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, history_kernel, s->warps_per_cta * 32, s->smem_bytes));
     if (occ < 1) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, "history kernel does not fit on an SM"); }
-    s->grid = prop.multiProcessorCount * occ;
+    s->grid = sm_count * occ;
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
     return 0;
@@ -262,9 +264,9 @@ int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n
 int coalgpu_fp64_peak(int device, double* tflops) {
     if (!tflops) return fail(COALGPU_EINVAL, "null argument");
     CU_OK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU_OK(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    int sm_count = 0;
+    CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sm_count * 8, threads = 256, iters = 4096;
     double* d = nullptr;
     CU_OK(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
     cudaEvent_t e0, e1;

@@ -158,3 +158,22 @@ def test_reduction_matches_oracle_and_reference(oracle, cuda_lib, name):
     print(name, "grid points compared", int(ok.sum()), "of", ok.size, "log mean w: gpu", mine[ok][:3], "reference", ref_like[ok][:3], "combined SE", se[ok][:3])
     assert ok.any() or name == "grid_pair5"     # that fixture's grid is far from the driving point (ESS ~ 1 everywhere)
     assert (np.abs(mine - ref_like)[ok] < 5 * se[ok] + 0.05).all()
+
+
+def test_cfg3_full_grid_32x32(oracle, cuda_lib):
+    """BASELINE config 3: all 1024 (mu, lambda) grid points scored from the same histories."""
+    from coalescenator_b200.problem import make_config, sub_problem, grid_cfg3
+    aln, loci, pairs = make_config(2)
+    mu, rho, lam = grid_cfg3()
+    p = sub_problem(aln, loci, *pairs[5], target_mu=mu, target_rho=rho, target_lambda=lam)
+    assert p.G == 1024
+    _compare_histories(oracle, p, 12, seed=31)
+
+
+def test_cfg4_shape_200_sequences_10_time_points(oracle, cuda_lib):
+    """BASELINE config 4 shape (10 time points x 20 sequences): large type store, long histories."""
+    from coalescenator_b200.problem import make_config, sub_problem
+    aln, loci, pairs = make_config(4)
+    p = sub_problem(aln, loci, *pairs[3])
+    assert p.T == 10 and p.n_lineages() == 200
+    _compare_histories(oracle, p, 6, seed=41, max_events=1 << 16)
