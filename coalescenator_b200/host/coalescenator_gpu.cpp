@@ -1,0 +1,242 @@
+// coalescenator-gpu — C++ host driver with the reference's command line and output files
+// (/root/reference/src/main.cpp:48-354), calling the B200 path through the C ABI of include/coalgpu.h
+// where the reference calls ImportanceSampler::runSampler (main.cpp:281-283).
+//
+// Same options as the reference (main.cpp:54-88); additions: --device N, --dump-problems DIR (write one
+// .coalprob file per eligible locus pair and stop: needs no GPU), --ess (append an ESS column).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/coalgpu.h"
+#include "fasta_input.h"
+
+using namespace coalhost;
+
+namespace {
+
+struct Options {
+    unsigned num_threads = 1, seed = 0, loci_size = 1, mc_samples = 500000, min_dist = 1, max_dist = 400;
+    std::string prefix = "coalescenator", fasta_list, time_list, viral_list, coordinate_list;
+    std::string mutation_list = "1e-6,5e-6,1e-5,2.5e-5,5e-5,7.5e-5,1e-4";
+    std::string scale_list = "250,500,750,1000,2000,4000";
+    std::string rho_list = "1e-10,1e-9,1e-8,1e-7,1e-6,5e-6,1e-5,5e-5,1e-4,5e-4,1e-3";
+    double generation_time = 0, mutation_driving = 2.5e-5, scale_driving = 1000, rho_driving = 5e-5;
+    bool have_coords = false, have_generation_time = false, ess = false;
+    int device = 0;
+    std::string dump_dir;
+};
+
+std::string now() {   // Utils.hpp:211-265: dd/mm/yyyy hh:mm:ss
+    time_t t = time(nullptr); struct tm lt; localtime_r(&t, &lt);
+    char buf[32]; strftime(buf, sizeof buf, "%d/%m/%Y %H:%M:%S", &lt);
+    return buf;
+}
+
+void usage() {
+    std::cout << "\n#### Coalescenator (B200) ####\n"
+              << "  -h [ --help ]  -p [ --num-threads ] N (ignored)  -s [ --seed ] N  --output-file-prefix S  --device N\n"
+              << "  -f [ --fasta-list ] a.fa,b.fa  -t [ --time-list ] t1,t2  -v [ --viral-list ] v1,v2  -g [ --generation-time ] X\n"
+              << "  --coordinate-list [l-r],... | bp1,bp2   --loci-size N (1)\n"
+              << "  -i [ --mc-samples ] N (500000)  --mutation-list L  --mutation-driving X (2.5e-5)  --scale-list L  --scale-driving X (1000)\n"
+              << "  --rho-list L  --rho-driving X (5e-5)  --min-comp-dist N (1)  --max-comp-dist N (400)\n"
+              << "  --dump-problems DIR  --ess\n";
+}
+
+Options parse(int argc, char** argv) {
+    Options o; o.seed = (unsigned)time(nullptr);
+    std::map<std::string, std::string> alias = {{"-p", "--num-threads"}, {"-s", "--seed"}, {"-f", "--fasta-list"}, {"-t", "--time-list"},
+                                                {"-v", "--viral-list"}, {"-g", "--generation-time"}, {"-i", "--mc-samples"}, {"-h", "--help"}};
+    for (int i = 1; i < argc; i++) {
+        std::string k = argv[i], v;
+        const size_t eq = k.find('=');
+        if (k.rfind("--", 0) == 0 && eq != std::string::npos) { v = k.substr(eq + 1); k = k.substr(0, eq); }
+        if (alias.count(k)) k = alias[k];
+        if (k == "--help") { usage(); exit(1); }
+        if (k == "--ess") { o.ess = true; continue; }
+        if (v.empty() && eq == std::string::npos) { if (i + 1 >= argc) throw std::runtime_error("the required argument for option '" + k + "' is missing"); v = argv[++i]; }
+        if (k == "--num-threads") o.num_threads = (unsigned)std::stoul(v);
+        else if (k == "--seed") o.seed = (unsigned)std::stoul(v);
+        else if (k == "--output-file-prefix") o.prefix = v;
+        else if (k == "--fasta-list") o.fasta_list = v;
+        else if (k == "--time-list") o.time_list = v;
+        else if (k == "--viral-list") o.viral_list = v;
+        else if (k == "--generation-time") { o.generation_time = std::stod(v); o.have_generation_time = true; }
+        else if (k == "--coordinate-list") { o.coordinate_list = v; o.have_coords = true; }
+        else if (k == "--loci-size") o.loci_size = (unsigned)std::stoul(v);
+        else if (k == "--mc-samples") o.mc_samples = (unsigned)std::stoul(v);
+        else if (k == "--mutation-list") o.mutation_list = v;
+        else if (k == "--mutation-driving") o.mutation_driving = std::stod(v);
+        else if (k == "--scale-list") o.scale_list = v;
+        else if (k == "--scale-driving") o.scale_driving = std::stod(v);
+        else if (k == "--rho-list") o.rho_list = v;
+        else if (k == "--rho-driving") o.rho_driving = std::stod(v);
+        else if (k == "--min-comp-dist") o.min_dist = (unsigned)std::stoul(v);
+        else if (k == "--max-comp-dist") o.max_dist = (unsigned)std::stoul(v);
+        else if (k == "--device") o.device = std::stoi(v);
+        else if (k == "--dump-problems") o.dump_dir = v;
+        else throw std::runtime_error("unrecognised option '" + k + "'");
+    }
+    if (argc == 1) { usage(); exit(1); }
+    for (auto& req : {std::make_pair("--fasta-list", &o.fasta_list), std::make_pair("--time-list", &o.time_list), std::make_pair("--viral-list", &o.viral_list)})
+        if (req.second->empty()) throw std::runtime_error(std::string("the option '") + req.first + "' is required but missing");
+    if (!o.have_generation_time) throw std::runtime_error("the option '--generation-time' is required but missing");
+    return o;
+}
+
+std::vector<double> number_list(const std::string& s) {
+    std::vector<double> v;
+    for (const std::string& t : split(s, ",")) v.push_back(std::atof(t.c_str()));
+    return v;
+}
+
+double log_addition(double a, double b) {   // Utils.hpp:88-107
+    return a < b ? b + std::log(1 + std::exp(a - b)) : a + std::log(1 + std::exp(b - a));
+}
+
+std::string bits_of(const PairProblem& p, int g, uint64_t w) {
+    const unsigned off = g == 1 ? p.LA : 0, len = g == 0 ? p.LA : (g == 1 ? p.LB : p.LA + p.LB);
+    std::string s;
+    for (unsigned i = 0; i < len; i++) s.push_back(((w >> (off + i)) & 1) ? '1' : '0');
+    return s;
+}
+
+void dump_problem(const std::string& path, const PairProblem& p, double tau, double dmu, double dlambda, double drho,
+                  const std::vector<double>& mu, const std::vector<double>& rho, const std::vector<double>& lambda) {
+    std::ofstream f(path.c_str());
+    f << std::setprecision(17);
+    f << "coalprob 1\nT " << p.times.size() << " LA " << p.LA << " LB " << p.LB << "\ntimes";
+    for (double x : p.times) f << " " << x;
+    f << "\nviral";
+    for (double x : p.viral) f << " " << x;
+    f << "\ntau " << tau << "\ndriving " << dmu << " " << dlambda << " " << drho << "\n";
+    f << "mu " << mu.size(); for (double x : mu) f << " " << x;
+    f << "\nrho " << rho.size(); for (double x : rho) f << " " << x;
+    f << "\nlambda " << lambda.size(); for (double x : lambda) f << " " << x;
+    f << "\n";
+    for (size_t t = 0; t < p.times.size(); t++) {
+        f << "types " << t << " " << (p.type_offsets[t + 1] - p.type_offsets[t]) << "\n";
+        for (int k = p.type_offsets[t]; k < p.type_offsets[t + 1]; k++)
+            f << "ABC"[p.type_gamma[k]] << " " << bits_of(p, p.type_gamma[k], p.type_words[k]) << " " << p.type_counts[k] << "\n";
+    }
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        Options o = parse(argc, argv);
+        std::cout << "\n[" << now() << "] Seed used for pseudo-random generator: " << o.seed << "\n" << std::endl;
+
+        Alignment aln(o.fasta_list, o.time_list, o.viral_list);                     // main.cpp:107
+        if (o.have_coords) aln.parse_coordinates(o.coordinate_list); else aln.tile_loci(o.loci_size);   // :109-117
+        const size_t s1 = aln.filter_ambiguous(), s2 = aln.filter_indels(), s3 = aln.filter_non_biallelic();   // :119-121
+        for (const std::string& m : aln.messages) std::cout << "[" << now() << "] " << m << std::endl;
+        std::cout << "[" << now() << "] " << s1 << " sites remaining after filtering ambiguous sites, " << s2 << " after filtering indels, "
+                  << s3 << " after filtering non-bi-allelic positions." << std::endl;
+
+        const std::vector<Locus>& loci = aln.loci();
+        const std::vector<Locus>& orig = aln.original_loci();
+        if (loci.empty()) { std::cout << "\n[" << now() << "] All loci was removed by the filtering process - exiting!" << std::endl; return 0; }   // :126-130
+        std::cout << "\n[" << now() << "] Number of loci: " << loci.size() << std::endl;
+        std::cout << "[" << now() << "] List of loci lengths: \n\n\t" << loci[0].second - loci[0].first + 1;
+        for (size_t i = 1; i < loci.size(); i++) std::cout << ", " << loci[i].second - loci[i].first + 1;
+        std::cout << std::endl;
+        if (!(o.mutation_driving > 0) || !(o.scale_driving > 0) || !(o.rho_driving > 0) || !(o.generation_time > 0))
+            throw std::runtime_error("driving values and generation time must be positive");   // :147-150
+
+        const std::vector<double> mu_list = number_list(o.mutation_list), lambda_list = number_list(o.scale_list), rho_list = number_list(o.rho_list);
+        if (loci.size() == 1) { std::cout << "\n[" << now() << "] Only a single loci left no remcobination estimation possible - exiting!" << std::endl; return 0; }   // :202-207
+
+        struct Pair { size_t i, j; unsigned dist; };
+        std::vector<Pair> pairs;                                                       // :211-225, :242-252
+        for (size_t i = 0; i < loci.size(); i++) for (size_t j = i + 1; j < loci.size(); j++) {
+            const unsigned dist = orig[j].first - orig[i].second - 1;
+            if (dist < o.min_dist || dist > o.max_dist) continue;
+            pairs.push_back({i, j, dist});
+        }
+        std::cout << "\n[" << now() << "] For each of the " << pairs.size() << " loci combination(s) generate " << o.mc_samples << " importance samples. "
+                  << (unsigned long long)o.mc_samples * pairs.size() << " samples in total.\n" << std::endl;
+
+        const size_t nmu = mu_list.size(), nrho = rho_list.size(), nlam = lambda_list.size(), G = nmu * nrho * nlam;
+        std::vector<double> composite(G, 0.0), mean_tmrca(G, 0.0);                    // :229-230 (mean_tmrca starts at 0 in the log domain)
+
+        std::ofstream pairwise;
+        if (o.dump_dir.empty()) {
+            pairwise.open((o.prefix + "_pairwise_loglikelihood.txt").c_str());
+            if (!pairwise.is_open()) throw std::runtime_error("cannot open the pairwise output file");
+            pairwise << "locus1\tlocus2\tmu\trho\tlambda\tloglikelihood\ttmrca\tlineages_remaining\tloglikelihoodSq" << (o.ess ? "\tess" : "") << "\n";   // :240
+        }
+
+        size_t remaining = pairs.size();
+        for (const Pair& pr : pairs) {
+            PairProblem sp = aln.sub_sample(loci[pr.i], loci[pr.j]);                  // :254
+            std::vector<double> rho_scaled = rho_list;
+            for (double& r : rho_scaled) r *= pr.dist + 1;                            // :260-271
+            const double drho = o.rho_driving * (pr.dist + 1);
+            remaining--;
+            std::ostringstream l1, l2;
+            l1 << "(" << orig[pr.i].first << ", " << orig[pr.i].second << ")";
+            l2 << "(" << orig[pr.j].first << ", " << orig[pr.j].second << ")";
+            std::cout << "[" << now() << "] Working on locus " << l1.str() << " and " << l2.str() << " having " << sp.nA << ", " << sp.nB << " and " << sp.nC
+                      << " sequences with ancentry A, B and C respectively taken at " << sp.times.size() << " different time points. " << remaining
+                      << " remaining pairwise combinations." << std::endl;
+            if (!o.dump_dir.empty()) {
+                std::ostringstream path;
+                path << o.dump_dir << "/pair_" << orig[pr.i].first << "-" << orig[pr.i].second << "_" << orig[pr.j].first << "-" << orig[pr.j].second << ".coalprob";
+                dump_problem(path.str(), sp, o.generation_time, o.mutation_driving, o.scale_driving, drho, mu_list, rho_scaled, lambda_list);
+                continue;
+            }
+
+            coalgpu_problem p = {};
+            const int T = (int)sp.times.size();
+            p.T = T; p.LA = (int)sp.LA; p.LB = (int)sp.LB;
+            p.times = sp.times.data(); p.viral = sp.viral.data(); p.tau = o.generation_time;
+            p.driving_mu = o.mutation_driving; p.driving_lambda = o.scale_driving; p.driving_rho = drho;
+            p.n_mu = (int)nmu; p.n_rho = (int)nrho; p.n_lambda = (int)nlam;
+            p.mu = mu_list.data(); p.rho = rho_scaled.data(); p.lambda = lambda_list.data();
+            p.type_offsets = sp.type_offsets.data(); p.type_gamma = sp.type_gamma.data();
+            p.type_words = sp.type_words.data(); p.type_counts = sp.type_counts.data();
+            std::vector<double> like(G), likesq(G), tm(G), lin(G * T), ess(G);
+            coalgpu_result r = {like.data(), likesq.data(), tm.data(), lin.data(), ess.data(), 0, 0, 0, 0.0};
+            const int rc = coalgpu_run_sampler(&p, o.mc_samples, 16, o.seed, o.device, &r);   // replaces :281-283
+            if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+
+            size_t g = 0;
+            for (size_t i = 0; i < nmu; i++) for (size_t j = 0; j < nrho; j++) for (size_t k = 0; k < nlam; k++, g++) {   // :285-310
+                composite[g] += like[g];
+                mean_tmrca[g] = log_addition(mean_tmrca[g], tm[g]);
+                pairwise << l1.str() << "\t" << l2.str() << "\t" << mu_list[i] << "\t" << rho_list[j] << "\t" << lambda_list[k] << "\t" << like[g] << "\t" << std::exp(tm[g]) << "\t";
+                for (int l = 0; l < T; l++) pairwise << (l ? "," : "") << std::exp(lin[(size_t)l * G + g]);
+                pairwise << "\t" << likesq[g];
+                if (o.ess) pairwise << "\t" << ess[g];
+                pairwise << "\n";
+            }
+        }
+        if (!o.dump_dir.empty()) { std::cout << "[" << now() << "] Wrote " << pairs.size() << " problem file(s) to " << o.dump_dir << std::endl; return 0; }
+        pairwise.close();
+
+        std::ofstream comp((o.prefix + "_composite_loglikelihood.txt").c_str());     // :317-340
+        if (!comp.is_open()) throw std::runtime_error("cannot open the composite output file");
+        const double norm = std::log((double)(loci.size() * (loci.size() - 1) / 2));  // :325 (all locus pairs, filtered or not)
+        comp << "mu\trho\tlambda\tlikelihood\ttmrca\n";
+        size_t g = 0;
+        for (size_t i = 0; i < nmu; i++) for (size_t j = 0; j < nrho; j++) for (size_t k = 0; k < nlam; k++, g++)
+            comp << mu_list[i] << "\t" << rho_list[j] << "\t" << lambda_list[k] << "\t" << composite[g] << "\t" << std::exp(mean_tmrca[g] - norm) << "\n";
+        comp.close();
+    } catch (std::exception& e) {
+        std::cerr << "ERROR: " << e.what() << std::endl;                              // :343-346
+        return 1;
+    }
+    std::cout << "[" << now() << "] Coalescenated succesfully." << std::endl;
+    return 0;
+}

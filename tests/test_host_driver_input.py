@@ -1,0 +1,173 @@
+"""The C++ host driver's own input path (coalescenator_b200/host/fasta_input.cpp: FASTA parsing, allele coding,
+missing / indel / ambiguous handling, site filters with coordinate remapping, locus tiling, pair selection and
+sub-sample extraction) against the UNMODIFIED reference input path (Sample.cpp, driven by
+oracle/ref_input_driver.cpp). Golden output committed in tests/golden/input_*.txt; regenerated and compared live
+wherever oracle/_ref is built."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, GOLDEN
+
+HOST = os.path.join(ROOT, "coalescenator_b200", "coalescenator-gpu")
+REF_INPUT = os.path.join(ROOT, "oracle", "_ref", "coalref_input")
+
+
+def write_fasta_set(directory, seed=7, n_times=3, n_seq=7, length=240):
+    """Synthetic serially sampled alignments with everything the reference's parser distinguishes: bi-, tri- and
+    mono-allelic sites, 'N', internal '-' (indels), left/right '-' runs (missing data), duplicate sequences."""
+    rng = np.random.default_rng(seed)
+    anc = rng.choice(list("ACGT"), size=length)
+    seg = np.sort(rng.choice(length, size=60, replace=False))
+    alt = {int(s): rng.choice([c for c in "ACGT" if c != anc[s]]) for s in seg}
+    tri = {int(s): rng.choice([c for c in "ACGT" if c != anc[s] and c != alt[int(s)]]) for s in seg[::9]}
+    founders = (rng.random((4, len(seg))) < 0.35)
+    paths = []
+    for t in range(n_times):
+        lines = []
+        for r in range(n_seq):
+            f = founders[rng.integers(0, 4)] ^ (rng.random(len(seg)) < 0.04)
+            s = anc.copy()
+            for k, site in enumerate(seg):
+                if f[k]:
+                    s[site] = alt[int(site)]
+            for site, c in tri.items():
+                if rng.random() < 0.15:
+                    s[site] = c
+            if rng.random() < 0.3:
+                s[rng.integers(0, length)] = "N"
+            if rng.random() < 0.3:
+                a = rng.integers(20, length - 20); s[a:a + rng.integers(1, 3)] = "-"
+            if rng.random() < 0.35:
+                s[:rng.integers(1, 60)] = "-"
+            if rng.random() < 0.35:
+                s[length - rng.integers(1, 60):] = "-"
+            lines.append(">seq%d_%d" % (t, r)); lines.append("".join(s))
+            if r == 2:
+                lines.append(">dup%d" % t); lines.append("".join(s))
+        path = os.path.join(directory, "t%d.fa" % t)
+        with open(path, "w") as fh:
+            fh.write("\n".join(lines) + "\n\n")
+        paths.append(path)
+    # files listed out of time order on purpose: the reference sorts them by time
+    order = [2, 0, 1][:n_times]
+    times = [0.0, 40.0, 95.5][:n_times]
+    viral = [120.0, 80.0, 200.0][:n_times]
+    return ",".join(paths[i] for i in order), ",".join(str(times[i]) for i in order), ",".join(str(viral[i]) for i in order)
+
+
+def build_host():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "coalescenator_b200", "host")], check=True, capture_output=True)
+
+
+def parse_ref_dump(text):
+    """coalref_input output -> {(a1,a2,b1,b2): dict}"""
+    out, cur, tp = {}, None, None
+    for line in text.splitlines():
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "pair":
+            cur = dict(dist=int(t[6]), LA=int(t[8]), LB=int(t[10]), times=[], viral=[], types=[], counts=tuple(int(x) for x in t[14:17]))
+            out[tuple(int(x) for x in t[1:5])] = cur
+        elif t[0] == "time" and cur is not None:
+            cur["times"].append(float(t[1])); cur["viral"].append(float(t[3])); tp = []; cur["types"].append(tp)
+        elif t[0] in "ABC" and len(t) == 3 and cur is not None:
+            tp.append((t[0], t[1], int(t[2])))
+    return out
+
+
+def parse_host_dump(directory):
+    from coalescenator_b200.problem import Problem, GAMMA_NAMES
+    out = {}
+    for f in sorted(os.listdir(directory)):
+        if not f.endswith(".coalprob"):
+            continue
+        a, b = f[len("pair_"):-len(".coalprob")].split("_")
+        key = tuple(int(x) for x in a.split("-")) + tuple(int(x) for x in b.split("-"))
+        p = Problem.load(os.path.join(directory, f))
+        types = [sorted((GAMMA_NAMES[g], p.bits(g, w), c) for (g, w, c) in tp) for tp in p.types]
+        out[key] = dict(LA=p.LA, LB=p.LB, times=p.times, viral=p.viral, types=types, drho=p.driving_rho, rho=p.target_rho)
+    return out
+
+
+@pytest.mark.parametrize("loci,tag", [("30", "tile30"), ("[5-60],[70-130],[150-239]", "coords"), ("50,120,200", "breaks")])
+def test_input_path_matches_reference(tmp_path, loci, tag):
+    if not os.path.exists(os.path.join(ROOT, "coalescenator_b200", "libcoalgpu.so")):
+        from coalescenator_b200 import build as B
+        B.build_cuda()
+    build_host()
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    golden = os.path.join(GOLDEN, "input_%s.txt" % tag)
+    if os.path.exists(REF_INPUT):
+        ref_text = subprocess.run([REF_INPUT, fl, tl, vl, loci, "1", "400"], check=True, capture_output=True, text=True).stdout
+        if os.environ.get("COAL_UPDATE_GOLDEN"):
+            with open(golden, "w") as fh:
+                fh.write(ref_text)
+        assert ref_text == open(golden).read(), "reference output changed; regenerate with COAL_UPDATE_GOLDEN=1"
+    else:
+        ref_text = open(golden).read()
+    ref = parse_ref_dump(ref_text)
+    dump = tmp_path / "dump"
+    dump.mkdir()
+    args = [HOST, "-f", fl, "-t", tl, "-v", vl, "-g", "1.5", "--dump-problems", str(dump), "--rho-driving", "5e-5", "--rho-list", "1e-6,1e-4"]
+    args += ["--coordinate-list", loci] if ("," in loci or "[" in loci) else ["--loci-size", loci]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    mine = parse_host_dump(str(dump))
+    assert len(ref) >= 1
+    assert sorted(mine) == sorted(ref), (sorted(mine), sorted(ref))
+    for key, rp in ref.items():
+        mp = mine[key]
+        assert (mp["LA"], mp["LB"]) == (rp["LA"], rp["LB"]), key
+        assert mp["times"] == rp["times"] and mp["viral"] == rp["viral"], key
+        assert mp["types"] == [sorted(tp) for tp in rp["types"]], key
+        # rho scaling by distance + 1 (main.cpp:260-271)
+        assert mp["drho"] == pytest.approx(5e-5 * (rp["dist"] + 1), rel=1e-15)
+        assert mp["rho"] == pytest.approx([1e-6 * (rp["dist"] + 1), 1e-4 * (rp["dist"] + 1)], rel=1e-15)
+
+
+@pytest.mark.gpu
+def test_host_driver_end_to_end_outputs(tmp_path):
+    """The C++ driver (reference CLI + output files, main.cpp:232-340) on a GPU: same numbers as the Python
+    mirror for the same problem and seed, files in the reference's format."""
+    import math
+    import coalescenator_b200 as cb
+    from coalescenator_b200 import build as B
+    from coalescenator_b200.problem import Problem
+    B.build_cuda()
+    build_host()
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    common = ["-f", fl, "-t", tl, "-v", vl, "-g", "1.5", "--loci-size", "30", "--mutation-list", "1e-5,2.5e-5", "--scale-list", "1000",
+              "--rho-list", "5e-5,1e-4", "-s", "77", "-i", "1500", "--max-comp-dist", "60"]
+    dump = tmp_path / "dump"; dump.mkdir()
+    assert subprocess.run([HOST] + common + ["--dump-problems", str(dump)], capture_output=True).returncode == 0
+    prefix = str(tmp_path / "run")
+    r = subprocess.run([HOST] + common + ["--output-file-prefix", prefix], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "Coalescenated succesfully." in r.stdout
+    rows = [l.rstrip("\n").split("\t") for l in open(prefix + "_pairwise_loglikelihood.txt")]
+    assert rows[0] == ["locus1", "locus2", "mu", "rho", "lambda", "loglikelihood", "tmrca", "lineages_remaining", "loglikelihoodSq"]
+    problems = sorted(f for f in os.listdir(dump) if f.endswith(".coalprob"))
+    assert len(rows) - 1 == len(problems) * 4
+    # first pair: identical to the Python mirror (same C entry point, same seed) up to the 6 printed digits
+    first = [x for x in rows[1:] if (x[0], x[1]) == (rows[1][0], rows[1][1])]
+    a, b = rows[1][0].strip("()").split(", "), rows[1][1].strip("()").split(", ")
+    p = Problem.load(os.path.join(dump, "pair_%s-%s_%s-%s.coalprob" % (a[0], a[1], b[0], b[1])))
+    out = cb.ImportanceSampler().run_sampler(p, 1500, seed=77)
+    g = 0
+    for i in range(2):
+        for j in range(2):
+            row = first[g]; g += 1
+            assert float(row[5]) == pytest.approx(out.likelihood[i, j, 0], rel=2e-6)
+            assert float(row[6]) == pytest.approx(math.exp(out.tmrca[i, j, 0]), rel=2e-6)
+            lin = [float(x) for x in row[7].split(",")]
+            assert lin == pytest.approx([math.exp(out.lineages_remaining[l, i, j, 0]) for l in range(p.T)], rel=2e-6)
+            assert float(row[8]) == pytest.approx(out.likelihoodSq[i, j, 0], rel=2e-6)
+    comp = [l.split("\t") for l in open(prefix + "_composite_loglikelihood.txt")]
+    assert [c.strip() for c in comp[0]] == ["mu", "rho", "lambda", "likelihood", "tmrca"]
+    # composite = sum over pairs of the pairwise log-likelihoods (main.cpp:285)
+    tot = sum(float(x[5]) for x in rows[1:] if (x[2], x[3], x[4]) == (rows[1][2], rows[1][3], rows[1][4]))
+    assert float(comp[1][3]) == pytest.approx(tot, rel=1e-4)
