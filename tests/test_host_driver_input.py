@@ -161,11 +161,11 @@ def test_host_driver_end_to_end_outputs(tmp_path):
     for i in range(2):
         for j in range(2):
             row = first[g]; g += 1
-            assert float(row[5]) == pytest.approx(out.likelihood[i, j, 0], rel=2e-6)
-            assert float(row[6]) == pytest.approx(math.exp(out.tmrca[i, j, 0]), rel=2e-6)
+            assert float(row[5]) == pytest.approx(out.likelihood[i, j, 0], rel=1e-5)
+            assert float(row[6]) == pytest.approx(math.exp(out.tmrca[i, j, 0]), rel=1e-5)
             lin = [float(x) for x in row[7].split(",")]
-            assert lin == pytest.approx([math.exp(out.lineages_remaining[l, i, j, 0]) for l in range(p.T)], rel=2e-6)
-            assert float(row[8]) == pytest.approx(out.likelihoodSq[i, j, 0], rel=2e-6)
+            assert lin == pytest.approx([math.exp(out.lineages_remaining[l, i, j, 0]) for l in range(p.T)], rel=1e-5)
+            assert float(row[8]) == pytest.approx(out.likelihoodSq[i, j, 0], rel=1e-5)
     comp = [l.split("\t") for l in open(prefix + "_composite_loglikelihood.txt")]
     assert [c.strip() for c in comp[0]] == ["mu", "rho", "lambda", "likelihood", "tmrca"]
     # composite = sum over pairs of the pairwise log-likelihoods (main.cpp:285)
