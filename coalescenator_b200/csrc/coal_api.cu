@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,7 +50,7 @@ struct coalgpu_sampler {
     unsigned long long* d_counters = nullptr;
     double* d_block_partials = nullptr;
     size_t block_partials_cap = 0;
-    int warp_bytes = 0, warps_per_cta = 4, grid = 0;
+    int warp_bytes = 0, warps_per_cta = 4, grid = 0, group = 32;   // group = lanes per history (16 or 32)
     size_t smem_bytes = 0;
     unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
     // K2 scratch smem
@@ -199,15 +200,22 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     s->allocs.push_back(s->d_counters);
     CU_OK(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
 
-    // launch geometry: persistent CTAs of 4 warps, as many as shared memory and registers allow
-    s->warp_bytes = (int)history_warp_bytes(P.kmax, P.pvmax, P.Ltot);
+    // launch geometry: persistent CTAs of 128 threads = 128/W groups of W lanes, one history per group.
+    // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
+    s->group = (P.Ltot + 1 <= 16) ? 16 : 32;
+    if (const char* g = std::getenv("COALGPU_GROUP")) { const int v = std::atoi(g); if (v == 8 || v == 16 || v == 32) s->group = v; }
+    for (;;) {
+        s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
+        s->smem_bytes = (size_t)s->warp_bytes * (128 / s->group);
+        if (s->smem_bytes <= 227 * 1024 || s->group == 32) break;
+        s->group *= 2;
+    }
     P.warp_bytes = s->warp_bytes;
-    s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta;
-    while (s->smem_bytes > 227 * 1024 && s->warps_per_cta > 1) { s->warps_per_cta /= 2; s->smem_bytes = (size_t)s->warp_bytes * s->warps_per_cta; }
-    if (s->smem_bytes > 227 * 1024) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for one warp's shared-memory state"); }
-    CU_OK(cudaFuncSetAttribute(history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    if (s->smem_bytes > 227 * 1024) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
+    const void* kfn = s->group == 8 ? (const void*)history_kernel<8> : s->group == 16 ? (const void*)history_kernel<16> : (const void*)history_kernel<32>;
+    CU_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     int occ = 0;
-    CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, history_kernel, s->warps_per_cta * 32, s->smem_bytes));
+    CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 128, s->smem_bytes));
     if (occ < 1) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, "history kernel does not fit on an SM"); }
     s->grid = sm_count * occ;
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
@@ -228,13 +236,21 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
     a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
     a.counters = s->d_counters;
-    const unsigned long long warps_needed = n;
+    const int groups_per_cta = 128 / s->group;
     int grid = s->grid;
-    const unsigned long long ctas_needed = (warps_needed + s->warps_per_cta - 1) / s->warps_per_cta;
+    const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
     // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
-    CU_OK(cudaFuncSetAttribute(history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    history_kernel<<<grid, s->warps_per_cta * 32, s->smem_bytes, st>>>(s->P, a);
+    if (s->group == 8) {
+        CU_OK(cudaFuncSetAttribute(history_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        history_kernel<8><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
+    } else if (s->group == 16) {
+        CU_OK(cudaFuncSetAttribute(history_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        history_kernel<16><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
+    } else {
+        CU_OK(cudaFuncSetAttribute(history_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        history_kernel<32><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
+    }
     g_launches++;
     CU_OK(cudaGetLastError());
     return 0;

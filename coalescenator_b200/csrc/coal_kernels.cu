@@ -34,19 +34,48 @@ struct WarpMem {
     double* sd;                  // [4]     scalar results of the out-of-line helpers
 };
 
-__host__ __device__ inline size_t warp_mem_bytes(int kmax, int pvmax, int Ltot) {
+__host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W) {
     size_t b = 0;
     b += (size_t)kmax * 8;                 // words
     b += (size_t)pvmax * 8;                // pv
     b += (size_t)kmax * 8;                 // aux
     b += (size_t)kmax * 4 * 3;             // cg, xc, plist
-    b += (size_t)((Ltot + 2) | 1) * 32 * 4;  // hist
+    b += (size_t)((Ltot + 2) | 1) * W * 4; // hist: one row per query of a batch (a batch = W queries)
     b += 4 * 8;                            // sd
     return (b + 15) & ~(size_t)15;
 }
 
+// A GROUP of W lanes (W = 16 or 32) draws one history; a warp carries 32/W independent groups. Every
+// collective below names only the lanes of its own group (mask), so the groups of a warp never wait for each
+// other; where their control flow coincides the hardware issues one instruction for all of them.
+template <int W>
+struct Grp {
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int sub() { return threadIdx.x & (W - 1); }
+    static __device__ __forceinline__ int base() { return (threadIdx.x & 31) & ~(W - 1); }
+    static __device__ __forceinline__ unsigned int mask() { return W == 32 ? 0xffffffffu : (((1u << W) - 1u) << base()); }
+    static __device__ __forceinline__ unsigned int ballot(bool p) { return __ballot_sync(mask(), p) >> base(); }
+    template <class T> static __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(mask(), v, src, W); }
+    static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+    static __device__ __forceinline__ unsigned int sum_u(unsigned int v) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask(), v, o, W);
+        return v;
+    }
+    static __device__ __forceinline__ double incl_scan(double v) {
+        const int s = sub();
+#pragma unroll
+        for (int o = 1; o < W; o <<= 1) {
+            const double t = __shfl_up_sync(mask(), v, o, W);
+            if (s >= o) v += t;
+        }
+        return v;
+    }
+};
+
+template <int W>
 __device__ __forceinline__ WarpMem wm() {
-    unsigned char* base = smem_dyn + (size_t)(threadIdx.x >> 5) * sP.warp_bytes;
+    unsigned char* base = smem_dyn + (size_t)(threadIdx.x / W) * sP.warp_bytes;
     const int kmax = sP.kmax, pvmax = sP.pvmax;
     WarpMem m;
     m.words = reinterpret_cast<unsigned long long*>(base); base += (size_t)kmax * 8;
@@ -55,7 +84,7 @@ __device__ __forceinline__ WarpMem wm() {
     m.cg = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.xc = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.plist = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
-    m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)((sP.Ltot + 2) | 1) * 32 * 4;
+    m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)((sP.Ltot + 2) | 1) * W * 4;
     m.sd = reinterpret_cast<double*>(base);
     return m;
 }
@@ -73,22 +102,24 @@ __device__ __noinline__ double dlog(double x) { return log(x); }
 // TypeContainer.cpp:409-522) keeping the cross counts of every related slot current. A type that is
 // not stored yet is appended; a slot whose count reaches 0 stays until commit().
 // Returns the slot (| kAppended when a slot was appended) or -1 when the store is full.
+template <int W>
 __device__ __noinline__ int adjust_core(int nslots, int g, unsigned long long w, int delta) {
-    const WarpMem m = wm();
-    const int lane = threadIdx.x & 31;
+    typedef Grp<W> G;
+    const WarpMem m = wm<W>();
+    const int sub = G::sub();
     const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
     int found = -1;
     unsigned int newxc = 0;
     const unsigned long long wa = w & maskA, wb = w & maskB;
 #pragma unroll 1
-    for (int base = 0; base < nslots; base += 32) {
-        const int j = base + lane;
+    for (int base = 0; base < nslots; base += W) {
+        const int j = base + sub;
         const bool in = j < nslots;
         const unsigned long long wj = in ? m.words[j] : 0ull;
         const unsigned int cgj = in ? m.cg[j] : 0u;
         const int gj = (int)(cgj >> 30);
         const unsigned int cj = cgj & kCntMask;
-        const unsigned int b = __ballot_sync(kFull, in && gj == g && wj == w);
+        const unsigned int b = G::ballot(in && gj == g && wj == w);
         if (b) found = base + __ffs(b) - 1;
         if (in) {
             if (g == GA) {
@@ -103,22 +134,23 @@ __device__ __noinline__ int adjust_core(int nslots, int g, unsigned long long w,
     }
     int ret;
     if (found < 0) {
-        newxc = warp_sum_u(newxc);
+        newxc = G::sum_u(newxc);
         if (nslots >= sP.kmax) return -1;
         found = nslots;
-        if (lane == 0) { m.words[found] = w; m.cg[found] = (unsigned int)g << 30; m.xc[found] = newxc; }
+        if (sub == 0) { m.words[found] = w; m.cg[found] = (unsigned int)g << 30; m.xc[found] = newxc; }
         ret = found | kAppended;
     } else {
         ret = found;
     }
-    __syncwarp();
-    if (lane == 0) m.cg[found] += (unsigned int)delta;
-    __syncwarp();
+    G::sync();
+    if (sub == 0) m.cg[found] += (unsigned int)delta;
+    G::sync();
     return ret;
 }
 
+template <int W>
 __device__ __forceinline__ int adjust(HState& s, int g, unsigned long long w, int delta) {
-    int r = adjust_core(s.nslots, g, w, delta);
+    int r = adjust_core<W>(s.nslots, g, w, delta);
     if (r < 0) { s.overflow = true; return -1; }
     if (r & kAppended) { s.nslots++; r &= ~kAppended; }
     if (g == GA) s.nA += delta; else if (g == GB) s.nB += delta; else s.nC += delta;
@@ -127,63 +159,69 @@ __device__ __forceinline__ int adjust(HState& s, int g, unsigned long long w, in
 
 // Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot
 // (the canonical order rule shared with the oracle's CANONICAL mode).
-__device__ __forceinline__ int commit(const WarpMem& m, int nslots, int lane) {
+template <int W>
+__device__ __forceinline__ int commit(const WarpMem& m, int nslots) {
+    typedef Grp<W> G;
+    const int sub = G::sub();
 #pragma unroll 1
     for (;;) {
         int z = -1;
 #pragma unroll 1
-        for (int base = ((nslots - 1) / 32) * 32; base >= 0 && z < 0; base -= 32) {
-            const int j = base + lane;
+        for (int base = ((nslots - 1) / W) * W; base >= 0 && z < 0; base -= W) {
+            const int j = base + sub;
             const bool empty = j < nslots && (m.cg[j] & kCntMask) == 0;
-            const unsigned int b = __ballot_sync(kFull, empty);
+            const unsigned int b = G::ballot(empty);
             if (b) z = base + 31 - __clz(b);
         }
         if (z < 0) break;
         const int last = nslots - 1;
-        if (lane == 0 && z != last) { m.words[z] = m.words[last]; m.cg[z] = m.cg[last]; m.xc[z] = m.xc[last]; }
+        if (sub == 0 && z != last) { m.words[z] = m.words[last]; m.cg[z] = m.cg[last]; m.xc[z] = m.xc[last]; }
         nslots = last;
-        __syncwarp();
+        G::sync();
         if (nslots == 0) break;
     }
     return nslots;
 }
 
 // Categorical draw over pv[0..n): first k with cum > u*total (strict, TypeContainer.cpp:730) or with
-// cum >= u*total (ProposalEngine.cpp:574). Partial sums run in index order (inclusive warp scans).
+// cum >= u*total (ProposalEngine.cpp:574). Partial sums run in index order (inclusive group scans).
 // Returns k; sd[0] = pv[k], sd[1] = total.
+template <int W>
 __device__ __noinline__ int pick(int n, double u, bool strict) {
-    const WarpMem m = wm();
-    const int lane = threadIdx.x & 31;
+    typedef Grp<W> G;
+    const WarpMem m = wm<W>();
+    const int sub = G::sub();
     double total = 0.0;
 #pragma unroll 1
-    for (int base = 0; base < n; base += 32) {
-        const int k = base + lane;
+    for (int base = 0; base < n; base += W) {
+        const int k = base + sub;
         const double v = k < n ? m.pv[k] : 0.0;
-        total = __shfl_sync(kFull, warp_incl_scan(v, lane) + total, 31);
+        total = G::shfl(G::incl_scan(v) + total, W - 1);
     }
     const double target = u * total;
     int idx = -1; double pidx = 0.0, carry = 0.0;
 #pragma unroll 1
-    for (int base = 0; base < n && idx < 0; base += 32) {
-        const int k = base + lane;
+    for (int base = 0; base < n && idx < 0; base += W) {
+        const int k = base + sub;
         const double v = k < n ? m.pv[k] : 0.0;
-        const double cum = warp_incl_scan(v, lane) + carry;
+        const double cum = G::incl_scan(v) + carry;
         const bool hit = k < n && (strict ? (cum > target && v > 0.0) : !(cum < target));
-        const unsigned int b = __ballot_sync(kFull, hit);
-        if (b) { const int l = __ffs(b) - 1; idx = base + l; pidx = __shfl_sync(kFull, v, l); }
-        carry = __shfl_sync(kFull, cum, 31);
+        const unsigned int b = G::ballot(hit);
+        if (b) { const int l = __ffs(b) - 1; idx = base + l; pidx = G::shfl(v, l); }
+        carry = G::shfl(cum, W - 1);
     }
     if (idx < 0) { idx = n - 1; pidx = m.pv[idx]; }   // u*total rounded past the last partial sum
-    __syncwarp();
-    if (lane == 0) { m.sd[0] = pidx; m.sd[1] = total; }
-    __syncwarp();
+    G::sync();
+    if (sub == 0) { m.sd[0] = pidx; m.sd[1] = total; }
+    G::sync();
     return idx;
 }
 
 // Lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721) into pv[]
-__device__ __forceinline__ void type_weights(const WarpMem& m, const HState& s, double thA, double thB, double rho, int lane) {
+template <int W>
+__device__ __forceinline__ void type_weights(const WarpMem& m, const HState& s, double thA, double thB, double rho) {
 #pragma unroll 1
-    for (int j = lane; j < s.nslots; j += 32) {
+    for (int j = Grp<W>::sub(); j < s.nslots; j += W) {
         const unsigned int cgj = m.cg[j], xcj = m.xc[j];
         const unsigned int c = cgj & kCntMask;
         const int gj = (int)(cgj >> 30);
@@ -193,7 +231,7 @@ __device__ __forceinline__ void type_weights(const WarpMem& m, const HState& s, 
         else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + thB) * (double)c;
         m.pv[j] = wgt;
     }
-    __syncwarp();
+    Grp<W>::sync();
 }
 
 // ---- conditional sampling probabilities ----------------------------------------------------------------
@@ -224,22 +262,26 @@ __device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int
 }
 
 // Two-locus queries of one event, phase 1: class lists (TypeContainer::getDifferences for a C query,
-// TypeContainer.cpp:802-886, incl. the dA+dB collapse of SURVEY.md Q1) of up to 32 queries at once, one
+// TypeContainer.cpp:802-886, incl. the dA+dB collapse of SURVEY.md Q1) of up to W queries at once, one
 // query per lane: every lane walks the stored types (broadcast reads) and accumulates its own histogram row
 // (rows are query-major with an odd stride: conflict-free here, in the compaction and in the forward pass).
 //  C chosen:   query qb+q = x (q = 0) or x with site q-1 flipped, against H'
 //  A/B chosen: query qb+q = (x, b_k) with b_k = partner plist[qb+q], against H' - b_k
 // On return lane q < nqb holds (nH, totals) of query q and its class list sits in hist[q*hstride ...].
 // (A lanes-over-types variant with match.any + group reductions was 1.8x slower: profiles/r1_v2_*.)
+template <int W>
 __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb, int qb, bool isC, unsigned long long xw, int pg,
-                                              int lane, int& nH_out, ClassTotals& tot_out) {
+                                              int& nH_out, ClassTotals& tot_out) {
+    const int sub = Grp<W>::sub();
     const int nsum = sP.Ltot + 2, hstride = nsum | 1;
     const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
-    unsigned int* mine = m.hist + lane * hstride;
-    const bool active = lane < nqb;
+    unsigned int* mine = m.hist + sub * hstride;
+    const bool active = sub < nqb;
     unsigned long long qw = xw, delw = 0ull; int delg = -1;
+    int nH = 0;
+    ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
     if (active) {
-        const int qi = qb + lane;
+        const int qi = qb + sub;
         if (isC) { if (qi > 0) qw = xw ^ (1ull << (qi - 1)); }
         else { delw = m.words[m.plist[qi]]; delg = pg; qw = xw | delw; }
 #pragma unroll 1
@@ -260,11 +302,7 @@ __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb,
                 mine[sidx] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
             }
         }
-    }
-    // compact the classes of query `lane` in place (ascending dA+dB) and collect the totals
-    int nH = 0;
-    ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
-    if (lane < nqb) {
+        // compact the classes in place (ascending dA+dB) and collect the totals
 #pragma unroll 1
         for (int sidx = 0; sidx < nsum; sidx++) {
             const unsigned int v = mine[sidx];
@@ -281,16 +319,18 @@ __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb,
             }
         }
     }
-    __syncwarp();
+    Grp<W>::sync();
     nH_out = nH; tot_out = tot;
 }
 
 // Two-locus queries, phase 2: the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) of one query
-// per group of p lanes (p a power of two), lane r of the group taking the intervals [r*16/p, (r+1)*16/p).
-__device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, ClassTotals tot, int p, int lane,
+// per sub-group of p lanes (p a power of two), lane r of it taking the intervals [r*16/p, (r+1)*16/p).
+template <int W>
+__device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, ClassTotals tot, int p,
                                                const double* __restrict__ row, unsigned int n_cond) {
+    const unsigned int gm = Grp<W>::mask();
     const bool empty = (n_cond == 0 || nH == 0);     // empty configuration, ConditionalSamplingHMM.cpp:277-298
-    const int r = lane & (p - 1);
+    const int r = Grp<W>::sub() & (p - 1);
     const int per = kQd / p;
     const int i0 = r * per;
     auto ld = [row](int off) { return __ldg(row + off); };
@@ -301,21 +341,21 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
         if (per == 1) cp = COAL_FWD(1); else if (per == 2) cp = COAL_FWD(2); else cp = COAL_FWD(4);
 #undef COAL_FWD
     }
-    // exclusive prefixes of (pre, preB) over the lanes of the group
+    // exclusive prefixes of (pre, preB) over the lanes of the sub-group
     double ipre = cp.pre, ipreB = cp.preB;
 #pragma unroll 1
     for (int o = 1; o < p; o <<= 1) {
-        const double t1 = __shfl_up_sync(kFull, ipre, o, p);
-        const double t2 = __shfl_up_sync(kFull, ipreB, o, p);
+        const double t1 = __shfl_up_sync(gm, ipre, o, p);
+        const double t2 = __shfl_up_sync(gm, ipreB, o, p);
         if (r >= o) { ipre += t1; ipreB += t2; }
     }
-    double epre = __shfl_up_sync(kFull, ipre, 1, p), epreB = __shfl_up_sync(kFull, ipreB, 1, p);
+    double epre = __shfl_up_sync(gm, ipre, 1, p), epreB = __shfl_up_sync(gm, ipreB, 1, p);
     if (r == 0) { epre = 0.0; epreB = 0.0; }
     double acc = chunk_finish(cp, epre, epreB), acc2 = cp.acc2;
 #pragma unroll 1
     for (int o = 1; o < p; o <<= 1) {
-        acc += __shfl_xor_sync(kFull, acc, o);
-        acc2 += __shfl_xor_sync(kFull, acc2, o);
+        acc += __shfl_xor_sync(gm, acc, o, p);
+        acc2 += __shfl_xor_sync(gm, acc2, o, p);
     }
     return empty ? sP.pow2negL : pismc_finish(acc, acc2, tot.n);
 }
@@ -337,35 +377,57 @@ struct LogProd {
     __device__ __forceinline__ double value() const { return dlog(mant) + (double)expo * 0.69314718055994530942; }
 };
 
-// ---- one history ------------------------------------------------------------------------------------------
+// ---- the history loop --------------------------------------------------------------------------------------
+// One flat loop per group: fetch a history index, draw the history event by event, write its outputs, fetch
+// the next. Keeping everything in ONE loop body lets the groups that share a warp reconverge at every
+// iteration (structured control flow) instead of drifting into different call frames.
+template <int W>
+__device__ __forceinline__ void run_group() {
+    typedef Grp<W> G;
+    const WarpMem m = wm<W>();
+    const int sub = G::sub();
+    const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
+    unsigned long long ev_total = 0, pi_total = 0, cq_total = 0;
+    unsigned int nh_lane = 0;
 
-__device__ void run_history(unsigned long long h, int lane, unsigned long long& ev_total, unsigned long long& pi_total,
-                            unsigned long long& cq_total, unsigned int& nh_lane) {
-    const WarpMem m = wm();
-    const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, G = sP.G;
-    PhiloxStream rng; rng.init(sA.seed, sA.first + h);
+    // per-history state
+    bool have = false;
+    unsigned long long h = 0;
+    PhiloxStream rng; rng.init(0, 0);
     HState s; s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
-    const bool tracing = sA.events != nullptr && h < sA.n_trace;
+    bool tracing = false, injecting = false, post = true;
     unsigned int nev = 0, npi = 0, ncq = 0;
-
-    // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
-    int inj_lo = sP.type_off[0], inj_hi = sP.type_off[1];
-    bool injecting = true;
-
-    int e = 0;                                  // epoch = index into viral / HMM time_idx
+    int inj_lo = 0, inj_hi = 0, e = 0, tset = 0;
     EpochConst ec = sP.ep[0];
-    int tset = sP.set_of_epoch[0];
-    double qsum = 0.0, consts = 0.0;            // proposal log-density = qsum + log(qprod)
+    double qsum = 0.0, consts = 0.0, tsum = 0.0;
     LogProd qprod; qprod.clear();
-    LogProd evprod; evprod.clear();             // product of the event constants of the epoch
-    double tsum = 0.0;
-    bool post = true;
+    LogProd evprod; evprod.clear();
     EpochStats st; epoch_stats_clear(st);
-    double* wout = sA.weights ? sA.weights + h * (unsigned long long)G : nullptr;
-    if (wout) for (int g = lane; g < G; g += 32) wout[g] = 0.0;
+    double* wout = nullptr;
 
 #pragma unroll 1
     for (;;) {
+        if (!have) {
+            unsigned long long h0 = 0;
+            if (sub == 0) h0 = atomicAdd(sA.counters, 1ull);
+            h = G::shfl(h0, 0);
+            if (h >= sA.n) break;
+            have = true;
+            rng.init(sA.seed, sA.first + h);
+            s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
+            tracing = sA.events != nullptr && h < sA.n_trace;
+            nev = 0; npi = 0; ncq = 0;
+            // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
+            inj_lo = sP.type_off[0]; inj_hi = sP.type_off[1];
+            injecting = true; post = true;
+            e = 0; ec = sP.ep[0]; tset = sP.set_of_epoch[0];
+            qsum = 0.0; consts = 0.0; tsum = 0.0;
+            qprod.clear(); evprod.clear(); epoch_stats_clear(st);
+            wout = sA.weights ? sA.weights + h * (unsigned long long)NG : nullptr;
+            if (wout) for (int g = sub; g < NG; g += W) wout[g] = 0.0;
+        }
+        bool end_now = false;
+
         if (injecting) {
             // TypeContainer::addTypeMap :525-591 + probabilityCombinatorics ProposalEngine.cpp:66-86
             const int a0 = s.nA, b0 = s.nB, c0 = s.nC;
@@ -374,7 +436,7 @@ __device__ void run_history(unsigned long long h, int lane, unsigned long long& 
             for (int k = inj_lo; k < inj_hi; k++) {
                 const unsigned int cg = sP.type_cg[k];
                 const int add = (int)(cg & kCntMask);
-                const int slot = adjust(s, (int)(cg >> 30), sP.type_w[k], add);
+                const int slot = adjust<W>(s, (int)(cg >> 30), sP.type_w[k], add);
                 if (slot < 0) break;
                 const int now = (int)(m.cg[slot] & kCntMask);
                 comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
@@ -386,294 +448,293 @@ __device__ void run_history(unsigned long long h, int lane, unsigned long long& 
                 consts += comb;
             }
             injecting = false;
-            if (s.overflow) break;
+            end_now = s.overflow;
         }
 
-        // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
-        type_weights(m, s, ec.dthA, ec.dthB, ec.drho, lane);
-        const int sx = pick(s.nslots, rng.next(), true);
-        const double p_hap = m.sd[0] / m.sd[1];
-        const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
-        const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
-        const double Dd = nn + (double)(Ac + Cc) * ec.dthA + (double)(Bc + Cc) * ec.dthB + ec.drho * (double)Cc;
-        const double rate = Dd * ec.inv2Ntau;
-        const double wait = -dlog(rng.next()) / rate;
-        const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
+        if (!end_now) {
+            // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
+            type_weights<W>(m, s, ec.dthA, ec.dthB, ec.drho);
+            const int sx = pick<W>(s.nslots, rng.next(), true);
+            const double p_hap = m.sd[0] / m.sd[1];
+            const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
+            const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
+            const double Dd = nn + (double)(Ac + Cc) * ec.dthA + (double)(Bc + Cc) * ec.dthB + ec.drho * (double)Cc;
+            const double rate = Dd * ec.inv2Ntau;
+            const double wait = -dlog(rng.next()) / rate;
+            const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
 
-        // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
-        const bool boundary = (e < T - 1) && !(tsum + wait < sP.times[e + 1]);
-        const bool finish = (e == T - 1) && (n <= 5);
-        if (boundary || finish) {
-            if (boundary) {
-                const double excess = sP.times[e + 1] - tsum;
-                tsum = sP.times[e + 1];
-                qsum += -rate * excess;
-                st.s_nn += nn * excess; st.s_a += aa * excess; st.s_c += (double)Cc * excess;
-                st.bnd_nn = nn; st.bnd_a = aa; st.bnd_c = (double)Cc; st.has_bnd = 1; st.n_rate += 1;
-            }
-            st.slog = evprod.value();
-            if (wout) {
-                const GridConst* gc = sP.grid + (size_t)e * G;
-#pragma unroll 1
-                for (int g = lane; g < G; g += 32) {
-                    const GridConst c = gc[g];
-                    wout[g] += epoch_log_density(st, c.theta, c.rho, c.inv2Ntau, c.log_theta, c.log_rho, c.log_2Ntau,
-                                                 [](double x) { return dlog(x); });
+            // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
+            const bool boundary = (e < T - 1) && !(tsum + wait < sP.times[e + 1]);
+            const bool finish = (e == T - 1) && (n <= 5);
+            if (boundary || finish) {
+                if (boundary) {
+                    const double excess = sP.times[e + 1] - tsum;
+                    tsum = sP.times[e + 1];
+                    qsum += -rate * excess;
+                    st.s_nn += nn * excess; st.s_a += aa * excess; st.s_c += (double)Cc * excess;
+                    st.bnd_nn = nn; st.bnd_a = aa; st.bnd_c = (double)Cc; st.has_bnd = 1; st.n_rate += 1;
                 }
-            }
-            epoch_stats_clear(st); evprod.clear();
-            if (sA.lineages && lane == 0) sA.lineages[h * (unsigned long long)T + e] = (double)n;
-            if (finish) break;
-            e++;
-            inj_lo = sP.type_off[e]; inj_hi = sP.type_off[e + 1];
-            injecting = true;
-            post = true;
-            ec = sP.ep[e];
-            tset = sP.set_of_epoch[e];
-            continue;
-        }
-        tsum += wait;
-
-        // ---- one event (ProposalEngine.cpp:134-566) ----
-        const unsigned long long xw = m.words[sx];
-        const unsigned int xcg = m.cg[sx], xxc = m.xc[sx];
-        const int xg = (int)(xcg >> 30);
-        const unsigned int xcount = xcg & kCntMask;
-        const unsigned long long xa = xw & sP.maskA, xb = xw & sP.maskB;
-        unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
-        if (xg == GC) {
-            Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16;
-            unsigned int ci = 0, cj = 0;
+                st.slog = evprod.value();
+                if (wout) {
+                    const GridConst* gc = sP.grid + (size_t)e * NG;
 #pragma unroll 1
-            for (int j = lane; j < s.nslots; j += 32) {
-                const unsigned int cgj = m.cg[j];
-                if ((int)(cgj >> 30) == GC) {
-                    const unsigned long long wj = m.words[j];
-                    if ((wj & sP.maskA) == xa) ci += cgj & kCntMask;
-                    if ((wj & sP.maskB) == xb) cj += cgj & kCntMask;
-                }
-            }
-            Ci = warp_sum_u(ci); Cj = warp_sum_u(cj);
-        } else if (xg == GA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
-
-        adjust(s, xg, xw, -1);                  // H' = H - x  (:168)
-        const int ns = s.nslots;
-        const bool isC = (xg == GC), isA = (xg == GA);
-        const int Lx = isC ? Ltot : (isA ? LA : LB), offb = (xg == GB) ? LA : 0;
-        const int pg = isA ? GB : GA;
-        const unsigned int own = isA ? Ai : Bj, ownC = isA ? Ci : Cj;
-        const double* row_m1 = row_ptr(tset, n - 1);
-        const double* row_alt = row_ptr(tset, isC ? n : n - 2);      // second row of the one-locus queries
-        const unsigned int nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
-
-        // partner list = stored types of the other one-locus class, slot order (:300 / :377)
-        int np = 0;
-        if (!isC) {
-#pragma unroll 1
-            for (int base = 0; base < ns; base += 32) {
-                const int j = base + lane;
-                const bool is = j < ns && (int)(m.cg[j] >> 30) == pg && (m.cg[j] & kCntMask) > 0;
-                const unsigned int b = __ballot_sync(kFull, is);
-                if (is) m.plist[np + __popc(b & ((1u << lane) - 1))] = (unsigned int)j;
-                np += __popc(b);
-            }
-            __syncwarp();
-        }
-
-        // ---- one-locus queries, one per lane -------------------------------------------------------------
-        //  C chosen: lane 0 = A part, lane 1 = B part, rows n-1 and n (:198-238 with :120-132)
-        //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
-        //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
-        const int nm = isC ? 2 : 1 + Lx + np;
-        double pi0 = 0.0, mA1 = 0.0, mA2 = 0.0, mB1 = 0.0, mB2 = 0.0;
-#pragma unroll 1
-        for (int q0 = 0; q0 < nm; q0 += 32) {
-            const int qi = q0 + lane;
-            const bool valid = qi < nm;
-            const bool partner = !isC && valid && qi > Lx;
-            int qg; unsigned long long qw; bool excl = false;
-            if (isC) { qg = (qi == 1) ? GB : GA; qw = (qi == 1) ? xb : xa; }
-            else if (partner) { qg = pg; qw = m.words[m.plist[qi - Lx - 1]]; excl = true; }
-            else { qg = xg; qw = (valid && qi >= 1) ? (xw ^ (1ull << (offb + qi - 1))) : xw; }
-            const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
-            const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
-            double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
-            if (valid) marginal_query(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
-            const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
-            const double v2 = marginal_finish(num2, ncomp, nc_alt, powl, sP.wsum);
-            if (q0 == 0) {
-                mA1 = __shfl_sync(kFull, v1, 0); mA2 = __shfl_sync(kFull, v2, 0);
-                mB1 = __shfl_sync(kFull, v1, 1); mB2 = __shfl_sync(kFull, v2, 1);
-                if (!isC) pi0 = mA1;
-            }
-            if (!isC && valid) {
-                if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = ec.dtheta * (double)own * v1 / pi0;
-                // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
-                if (partner) m.aux[qi - Lx - 1] = 0.5 * mA2 * v1 + 0.5 * v2 * pi0;
-            }
-        }
-        __syncwarp();
-
-        // ---- two-locus queries ---------------------------------------------------------------------------
-        //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
-        //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
-        const int nq = isC ? Ltot + 1 : np;
-        const double* crow = isC ? row_m1 : row_alt;
-        const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
-        const int hstride = (Ltot + 2) | 1;
-#pragma unroll 1
-        for (int qb = 0; qb < nq; qb += 32) {
-            const int nqb = min(32, nq - qb);
-            int my_nH; ClassTotals my_tot;
-            build_classes(m, ns, nqb, qb, isC, xw, pg, lane, my_nH, my_tot);
-            nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
-            // one pass: groups of p lanes per query, p the largest power of two with nqb * p <= 32 (<= 16).
-            // (Splitting the batch into several always-full passes costs more in per-pass set-up than the idle
-            // lanes cost here: 168k vs 198k histories/s, profiles/r1_v2_notes.md.)
-            {
-                int p = 1;
-                while (p < kQd && nqb * (p * 2) <= 32) p *= 2;
-                const int ql = lane / p;
-                const bool valid = ql < nqb;
-                const int qloc = valid ? ql : 0;
-                const int nH = __shfl_sync(kFull, my_nH, qloc);
-                ClassTotals tot;
-                tot.n = __shfl_sync(kFull, my_tot.n, qloc);
-                tot.ncompA = __shfl_sync(kFull, my_tot.ncompA, qloc);
-                tot.ncompB = __shfl_sync(kFull, my_tot.ncompB, qloc);
-                const double pi = forward_pass(m.hist + qloc * hstride, nH, tot, p, lane, crow, cn);
-                if (valid && (lane & (p - 1)) == 0) {
-                    const int qi = qb + qloc;
-                    if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
-                    else {
-                        const int pslot = (int)m.plist[qi];
-                        m.pv[Lx + qi] = (double)own * (double)(m.cg[pslot] & kCntMask) * pi / m.aux[qi];
+                    for (int g = sub; g < NG; g += W) {
+                        const GridConst c = gc[g];
+                        wout[g] += epoch_log_density(st, c.theta, c.rho, c.inv2Ntau, c.log_theta, c.log_rho, c.log_2Ntau,
+                                                     [](double x) { return dlog(x); });
                     }
                 }
-            }
-            __syncwarp();
-        }
-        __syncwarp();
+                epoch_stats_clear(st); evprod.clear();
+                if (sA.lineages && sub == 0) sA.lineages[h * (unsigned long long)T + e] = (double)n;
+                if (finish) {
+                    end_now = true;
+                } else {
+                    e++;
+                    inj_lo = sP.type_off[e]; inj_hi = sP.type_off[e + 1];
+                    injecting = true;
+                    post = true;
+                    ec = sP.ep[e];
+                    tset = sP.set_of_epoch[e];
+                }
+            } else {
+                tsum += wait;
 
-        int ncand;
-        if (isC) {
-            pi0 = m.sd[2];
-            // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
-            const double pj = 0.5 * mA1 * mB2 + 0.5 * mB1 * mA2;
+                // ---- one event (ProposalEngine.cpp:134-566) ----
+                const unsigned long long xw = m.words[sx];
+                const unsigned int xcg = m.cg[sx], xxc = m.xc[sx];
+                const int xg = (int)(xcg >> 30);
+                const unsigned int xcount = xcg & kCntMask;
+                const unsigned long long xa = xw & sP.maskA, xb = xw & sP.maskB;
+                unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
+                if (xg == GC) {
+                    Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16;
+                    unsigned int ci = 0, cj = 0;
 #pragma unroll 1
-            for (int k = lane; k < Ltot; k += 32) m.pv[k] = ec.dtheta * (double)Cij * m.pv[k] / pi0;
-            if (lane == 0) {
-                m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
-                m.pv[Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
-                m.pv[Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / mB1 : 0.0;
-                m.pv[Ltot + 3] = ec.drho * (double)Cij * pj / pi0;
-            }
-            ncand = Ltot + 4;
-            npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
-        } else {
-            if (lane == 0) m.pv[Lx + np] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) / pi0 : 0.0;
-            ncand = Lx + np + 1;
-            npi += (unsigned int)(1 + Lx + 5 * np);
-        }
-        __syncwarp();
+                    for (int j = sub; j < s.nslots; j += W) {
+                        const unsigned int cgj = m.cg[j];
+                        if ((int)(cgj >> 30) == GC) {
+                            const unsigned long long wj = m.words[j];
+                            if ((wj & sP.maskA) == xa) ci += cgj & kCntMask;
+                            if ((wj & sP.maskB) == xb) cj += cgj & kCntMask;
+                        }
+                    }
+                    Ci = G::sum_u(ci); Cj = G::sum_u(cj);
+                } else if (xg == GA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
 
-        // ---- sample the move (sampleFromVector :568-583) ----
-        const int idx = pick(ncand, rng.next(), false);
-        // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
-        qsum += -rate * wait;
-        qprod.mul(rate * p_hap * m.sd[0] / m.sd[1]);
+                adjust<W>(s, xg, xw, -1);               // H' = H - x  (:168)
+                const int ns = s.nslots;
+                const bool isC = (xg == GC), isA = (xg == GA);
+                const int Lx = isC ? Ltot : (isA ? LA : LB), offb = (xg == GB) ? LA : 0;
+                const int pg = isA ? GB : GA;
+                const unsigned int own = isA ? Ai : Bj, ownC = isA ? Ci : Cj;
+                const double* row_m1 = row_ptr(tset, n - 1);
+                const double* row_alt = row_ptr(tset, isC ? n : n - 2);      // second row of the one-locus queries
+                const unsigned int nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
 
-        // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
-        double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
-        int ev_kind = 1; unsigned long long ev_aux = 0ull; int ev_site = 0xff;
-        int og0 = 0, og1 = 0, od0 = 0, od1 = 0, nops = 0; unsigned long long ow0 = 0ull, ow1 = 0ull;
-        if (idx < Lx) {                                                        // mutation of site idx
-            ow0 = xw ^ (1ull << (offb + idx)); og0 = xg; od0 = +1; nops = 1;
-            kind = 1; ev_kind = 0; ev_aux = ow0; ev_site = idx;
-        } else if (isC) {
-            if (idx == Ltot) { evc = (double)((unsigned int)Cc * (Cij - 1)); }
-            else if (idx == Ltot + 1) { og0 = GC; ow0 = xw; od0 = +1; og1 = GA; ow1 = xa; od1 = -1; nops = 2;
-                                        evc = (double)((unsigned int)Ac * Cij); ev_kind = 2; ev_aux = xa; }
-            else if (idx == Ltot + 2) { og0 = GC; ow0 = xw; od0 = +1; og1 = GB; ow1 = xb; od1 = -1; nops = 2;
-                                        evc = (double)((unsigned int)Bc * Cij); ev_kind = 3; ev_aux = xb; }
-            else { og0 = GA; ow0 = xa; od0 = +1; og1 = GB; ow1 = xb; od1 = +1; nops = 2; kind = 2; ev_kind = 4; }
-        } else if (idx < Lx + np) {                                            // A^B_k coalescence
-            const unsigned long long pw = m.words[m.plist[idx - Lx]];
-            og0 = pg; ow0 = pw; od0 = -1; og1 = GC; ow1 = xw | pw; od1 = +1; nops = 2;
-            ev_kind = 5; ev_aux = pw;
-        } else {
-            evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
-        }
-        double after0 = 1.0, after1 = 1.0;
-        if (nops > 0) { const int slot = adjust(s, og0, ow0, od0); if (slot >= 0) after0 = (double)(m.cg[slot] & kCntMask); }
-        if (nops > 1) { const int slot = adjust(s, og1, ow1, od1); if (slot >= 0) after1 = (double)(m.cg[slot] & kCntMask); }
-        if (ev_kind == 0) evc = after0;
-        else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
-        else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
-        s.nslots = commit(m, s.nslots, lane);
-        if (tracing && lane == 0 && nev < sA.max_events) {
-            coalgpu_event& r = sA.events[(unsigned long long)h * sA.max_events + nev];
-            r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
-            r.epoch = (uint8_t)e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
-        }
-        nev++;
-
-        // ---- target density bookkeeping (:457-546) ----
-        evprod.mul(evc);
-        st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
-        if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
-        if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; post = false; }
-        else st.n_rate++;
-        if (s.overflow) break;
-        if (nev >= (1u << 18)) { s.overflow = true; break; }   // runaway guard: histories have O(10^2-10^3) events
-    }
-
-    // ---- final weight (ProposalEngine.cpp:817-858) ----
-    const double ln2 = 0.69314718055994530942;
-    const double q = qsum + qprod.value();
-    const double fin = consts + sP.perm_const - q
-                     - ((double)(LA + LB) * ln2 * (double)s.nC + (double)LA * ln2 * (double)s.nA + (double)LB * ln2 * (double)s.nB);
-    if (wout) {
-        __syncwarp();
-        const double bad = __longlong_as_double(0x7ff8000000000000ll);
-        for (int g = lane; g < G; g += 32) wout[g] = s.overflow ? bad : wout[g] + fin;
-    }
-    if (lane == 0) {
-        if (sA.tmrca) sA.tmrca[h] = tsum;
-        if (sA.nevents) sA.nevents[h] = nev;
-        if (tracing && sA.event_counts) sA.event_counts[h] = nev;
-        if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
-    }
-    ev_total += nev; pi_total += npi; cq_total += ncq;
-}
-
-}  // namespace
-
-// K1: persistent warps pull history indices from a global counter until the batch is drawn.
-#ifndef COAL_MIN_CTAS
-#define COAL_MIN_CTAS 3
-#endif
-__global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
-    if (threadIdx.x == 0) { sP = P; sA = A; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    unsigned long long ev_total = 0, pi_total = 0, cq_total = 0;
-    unsigned int nh_lane = 0;
+                // partner list = stored types of the other one-locus class, slot order (:300 / :377)
+                int np = 0;
+                if (!isC) {
 #pragma unroll 1
-    for (;;) {
-        unsigned long long h = 0;
-        if (lane == 0) h = atomicAdd(sA.counters, 1ull);
-        h = __shfl_sync(kFull, h, 0);
-        if (h >= sA.n) break;
-        run_history(h, lane, ev_total, pi_total, cq_total, nh_lane);
-        __syncwarp();
+                    for (int base = 0; base < ns; base += W) {
+                        const int j = base + sub;
+                        const bool is = j < ns && (int)(m.cg[j] >> 30) == pg && (m.cg[j] & kCntMask) > 0;
+                        const unsigned int b = G::ballot(is);
+                        if (is) m.plist[np + __popc(b & ((1u << sub) - 1))] = (unsigned int)j;
+                        np += __popc(b);
+                    }
+                    G::sync();
+                }
+
+                // ---- one-locus queries, one per lane ---------------------------------------------------------
+                //  C chosen: lane 0 = A part, lane 1 = B part, rows n-1 and n (:198-238 with :120-132)
+                //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
+                //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
+                const int nm = isC ? 2 : 1 + Lx + np;
+                double pi0 = 0.0, mA1 = 0.0, mA2 = 0.0, mB1 = 0.0, mB2 = 0.0;
+#pragma unroll 1
+                for (int q0 = 0; q0 < nm; q0 += W) {
+                    const int qi = q0 + sub;
+                    const bool valid = qi < nm;
+                    const bool partner = !isC && valid && qi > Lx;
+                    int qg; unsigned long long qw; bool excl = false;
+                    if (isC) { qg = (qi == 1) ? GB : GA; qw = (qi == 1) ? xb : xa; }
+                    else if (partner) { qg = pg; qw = m.words[m.plist[qi - Lx - 1]]; excl = true; }
+                    else { qg = xg; qw = (valid && qi >= 1) ? (xw ^ (1ull << (offb + qi - 1))) : xw; }
+                    const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
+                    const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
+                    double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
+                    if (valid) marginal_query(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
+                    const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
+                    const double v2 = marginal_finish(num2, ncomp, nc_alt, powl, sP.wsum);
+                    if (q0 == 0) {
+                        mA1 = G::shfl(v1, 0); mA2 = G::shfl(v2, 0);
+                        mB1 = G::shfl(v1, 1); mB2 = G::shfl(v2, 1);
+                        if (!isC) pi0 = mA1;
+                    }
+                    if (!isC && valid) {
+                        if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = ec.dtheta * (double)own * v1 / pi0;
+                        // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
+                        if (partner) m.aux[qi - Lx - 1] = 0.5 * mA2 * v1 + 0.5 * v2 * pi0;
+                    }
+                }
+                G::sync();
+
+                // ---- two-locus queries -----------------------------------------------------------------------
+                //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
+                //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
+                const int nq = isC ? Ltot + 1 : np;
+                const double* crow = isC ? row_m1 : row_alt;
+                const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
+                const int hstride = (Ltot + 2) | 1;
+#pragma unroll 1
+                for (int qb = 0; qb < nq; qb += W) {
+                    const int nqb = min(W, nq - qb);
+                    int my_nH; ClassTotals my_tot;
+                    build_classes<W>(m, ns, nqb, qb, isC, xw, pg, my_nH, my_tot);
+                    nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
+                    // one pass: sub-groups of p lanes per query, p the largest power of two with nqb * p <= W (<= 16).
+                    // (Splitting the batch into several always-full passes costs more in per-pass set-up than the
+                    // idle lanes cost here, profiles/r1_kernel_iterations.md.)
+                    int p = 1;
+                    while (p < kQd && nqb * (p * 2) <= W) p *= 2;
+                    const int ql = sub / p;
+                    const bool valid = ql < nqb;
+                    const int qloc = valid ? ql : 0;
+                    const int nH = G::shfl(my_nH, qloc);
+                    ClassTotals tot;
+                    tot.n = G::shfl(my_tot.n, qloc);
+                    tot.ncompA = G::shfl(my_tot.ncompA, qloc);
+                    tot.ncompB = G::shfl(my_tot.ncompB, qloc);
+                    const double pi = forward_pass<W>(m.hist + qloc * hstride, nH, tot, p, crow, cn);
+                    if (valid && (sub & (p - 1)) == 0) {
+                        const int qi = qb + qloc;
+                        if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
+                        else {
+                            const int pslot = (int)m.plist[qi];
+                            m.pv[Lx + qi] = (double)own * (double)(m.cg[pslot] & kCntMask) * pi / m.aux[qi];
+                        }
+                    }
+                    G::sync();
+                }
+                G::sync();
+
+                int ncand;
+                if (isC) {
+                    pi0 = m.sd[2];
+                    // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
+                    const double pj = 0.5 * mA1 * mB2 + 0.5 * mB1 * mA2;
+#pragma unroll 1
+                    for (int k = sub; k < Ltot; k += W) m.pv[k] = ec.dtheta * (double)Cij * m.pv[k] / pi0;
+                    if (sub == 0) {
+                        m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
+                        m.pv[Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
+                        m.pv[Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / mB1 : 0.0;
+                        m.pv[Ltot + 3] = ec.drho * (double)Cij * pj / pi0;
+                    }
+                    ncand = Ltot + 4;
+                    npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
+                } else {
+                    if (sub == 0) m.pv[Lx + np] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) / pi0 : 0.0;
+                    ncand = Lx + np + 1;
+                    npi += (unsigned int)(1 + Lx + 5 * np);
+                }
+                G::sync();
+
+                // ---- sample the move (sampleFromVector :568-583) ----
+                const int idx = pick<W>(ncand, rng.next(), false);
+                // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
+                qsum += -rate * wait;
+                qprod.mul(rate * p_hap * m.sd[0] / m.sd[1]);
+
+                // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
+                double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
+                int ev_kind = 1; unsigned long long ev_aux = 0ull; int ev_site = 0xff;
+                int og0 = 0, og1 = 0, od0 = 0, od1 = 0, nops = 0; unsigned long long ow0 = 0ull, ow1 = 0ull;
+                if (idx < Lx) {                                                        // mutation of site idx
+                    ow0 = xw ^ (1ull << (offb + idx)); og0 = xg; od0 = +1; nops = 1;
+                    kind = 1; ev_kind = 0; ev_aux = ow0; ev_site = idx;
+                } else if (isC) {
+                    if (idx == Ltot) { evc = (double)((unsigned int)Cc * (Cij - 1)); }
+                    else if (idx == Ltot + 1) { og0 = GC; ow0 = xw; od0 = +1; og1 = GA; ow1 = xa; od1 = -1; nops = 2;
+                                                evc = (double)((unsigned int)Ac * Cij); ev_kind = 2; ev_aux = xa; }
+                    else if (idx == Ltot + 2) { og0 = GC; ow0 = xw; od0 = +1; og1 = GB; ow1 = xb; od1 = -1; nops = 2;
+                                                evc = (double)((unsigned int)Bc * Cij); ev_kind = 3; ev_aux = xb; }
+                    else { og0 = GA; ow0 = xa; od0 = +1; og1 = GB; ow1 = xb; od1 = +1; nops = 2; kind = 2; ev_kind = 4; }
+                } else if (idx < Lx + np) {                                            // A^B_k coalescence
+                    const unsigned long long pw = m.words[m.plist[idx - Lx]];
+                    og0 = pg; ow0 = pw; od0 = -1; og1 = GC; ow1 = xw | pw; od1 = +1; nops = 2;
+                    ev_kind = 5; ev_aux = pw;
+                } else {
+                    evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
+                }
+                double after0 = 1.0, after1 = 1.0;
+                if (nops > 0) { const int slot = adjust<W>(s, og0, ow0, od0); if (slot >= 0) after0 = (double)(m.cg[slot] & kCntMask); }
+                if (nops > 1) { const int slot = adjust<W>(s, og1, ow1, od1); if (slot >= 0) after1 = (double)(m.cg[slot] & kCntMask); }
+                if (ev_kind == 0) evc = after0;
+                else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
+                else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
+                s.nslots = commit<W>(m, s.nslots);
+                if (tracing && sub == 0 && nev < sA.max_events) {
+                    coalgpu_event& r = sA.events[(unsigned long long)h * sA.max_events + nev];
+                    r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
+                    r.epoch = (uint8_t)e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
+                }
+                nev++;
+
+                // ---- target density bookkeeping (:457-546) ----
+                evprod.mul(evc);
+                st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
+                if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
+                if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; post = false; }
+                else st.n_rate++;
+                if (nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
+                end_now = s.overflow;
+            }
+        }
+
+        if (end_now) {
+            // ---- final weight (ProposalEngine.cpp:817-858) ----
+            const double ln2 = 0.69314718055994530942;
+            const double q = qsum + qprod.value();
+            const double fin = consts + sP.perm_const - q
+                             - ((double)(LA + LB) * ln2 * (double)s.nC + (double)LA * ln2 * (double)s.nA + (double)LB * ln2 * (double)s.nB);
+            if (wout) {
+                G::sync();
+                const double bad = __longlong_as_double(0x7ff8000000000000ll);
+                for (int g = sub; g < NG; g += W) wout[g] = s.overflow ? bad : wout[g] + fin;
+            }
+            if (sub == 0) {
+                if (sA.tmrca) sA.tmrca[h] = tsum;
+                if (sA.nevents) sA.nevents[h] = nev;
+                if (tracing && sA.event_counts) sA.event_counts[h] = nev;
+                if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
+            }
+            ev_total += nev; pi_total += npi; cq_total += ncq;
+            have = false;
+        }
     }
-    const unsigned long long nh_total = (unsigned long long)warp_sum_u(nh_lane);   // < 2^32 per warp and launch
-    if (lane == 0) {
+    const unsigned long long nh_total = (unsigned long long)G::sum_u(nh_lane);   // < 2^32 per group and launch
+    if (sub == 0) {
         atomicAdd(sA.counters + 1, ev_total); atomicAdd(sA.counters + 2, pi_total);
         atomicAdd(sA.counters + 4, cq_total); atomicAdd(sA.counters + 5, nh_total);
     }
 }
+
+}  // namespace
+
+// K1: persistent groups of W lanes pull history indices from a global counter until the batch is drawn.
+#ifndef COAL_MIN_CTAS
+#define COAL_MIN_CTAS 3
+#endif
+template <int W>
+__global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
+    if (threadIdx.x == 0) { sP = P; sA = A; }
+    __syncthreads();
+    run_group<W>();
+}
+template __global__ void history_kernel<8>(const DevProblem, const SampleArgs);
+template __global__ void history_kernel<16>(const DevProblem, const SampleArgs);
+template __global__ void history_kernel<32>(const DevProblem, const SampleArgs);
 
 // K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC).
 // One group of 16 lanes per query; classes are staged into the group's shared-memory column.
@@ -795,6 +856,6 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-size_t history_warp_bytes(int kmax, int pvmax, int Ltot) { return warp_mem_bytes(kmax, pvmax, Ltot); }
+size_t history_group_bytes(int kmax, int pvmax, int Ltot, int W) { return group_mem_bytes(kmax, pvmax, Ltot, W); }
 
 }  // namespace coalgpu
