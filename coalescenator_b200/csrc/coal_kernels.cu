@@ -32,6 +32,26 @@ struct WarpMem {
     unsigned int* plist;         // [kmax]  slot index of each partner
     unsigned int* hist;          // [32][hstride] class histogram / class list of each query of the batch (hstride odd)
     double* sd;                  // [4]     scalar results of the out-of-line helpers
+    struct HistScalars* hs;      //         per-history scalars that are touched once per event (kept out of registers)
+};
+
+// running product with the exponent split off: a sum of logs without a log per factor
+struct LogProd {
+    double mant; int expo;
+    __host__ __device__ __forceinline__ void clear() { mant = 1.0; expo = 0; }
+    __device__ __forceinline__ void mul(double x) {
+        int e;
+        mant = frexp(mant * x, &e);
+        expo += e;
+    }
+};
+
+// Scalars of the history a group is drawing. Written by lane 0 of the group once per event / boundary and
+// read by all lanes after a group sync; living in shared memory they cost no registers in the hot loops.
+struct HistScalars {
+    EpochStats st;            // target-density statistics of the current epoch
+    LogProd qprod, evprod;    // proposal density (product part), event constants of the epoch
+    double qsum, consts, tsum;
 };
 
 __host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W) {
@@ -42,6 +62,7 @@ __host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot,
     b += (size_t)kmax * 4 * 3;             // cg, xc, plist
     b += (size_t)((Ltot + 2) | 1) * W * 4; // hist: one row per query of a batch (a batch = W queries)
     b += 4 * 8;                            // sd
+    b += (sizeof(HistScalars) + 15) & ~(size_t)15;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -85,7 +106,8 @@ __device__ __forceinline__ WarpMem wm() {
     m.xc = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.plist = reinterpret_cast<unsigned int*>(base); base += (size_t)kmax * 4;
     m.hist = reinterpret_cast<unsigned int*>(base); base += (size_t)((sP.Ltot + 2) | 1) * W * 4;
-    m.sd = reinterpret_cast<double*>(base);
+    m.sd = reinterpret_cast<double*>(base); base += 4 * 8;
+    m.hs = reinterpret_cast<HistScalars*>(base);
     return m;
 }
 
@@ -365,17 +387,7 @@ __device__ __forceinline__ const double* row_ptr(int set, int n_all) {
     return sP.rows + ((size_t)set * sP.n_max + (n - 1)) * sP.row_doubles;
 }
 
-// running product with the exponent split off: a sum of logs without a log per factor
-struct LogProd {
-    double mant; int expo;
-    __device__ __forceinline__ void clear() { mant = 1.0; expo = 0; }
-    __device__ __forceinline__ void mul(double x) {
-        int e;
-        mant = frexp(mant * x, &e);
-        expo += e;
-    }
-    __device__ __forceinline__ double value() const { return dlog(mant) + (double)expo * 0.69314718055994530942; }
-};
+__device__ __forceinline__ double logprod_value(const LogProd& p) { return dlog(p.mant) + (double)p.expo * 0.69314718055994530942; }
 
 // ---- the history loop --------------------------------------------------------------------------------------
 // One flat loop per group: fetch a history index, draw the history event by event, write its outputs, fetch
@@ -398,11 +410,7 @@ __device__ __forceinline__ void run_group() {
     bool tracing = false, injecting = false, post = true;
     unsigned int nev = 0, npi = 0, ncq = 0;
     int inj_lo = 0, inj_hi = 0, e = 0, tset = 0;
-    EpochConst ec = sP.ep[0];
-    double qsum = 0.0, consts = 0.0, tsum = 0.0;
-    LogProd qprod; qprod.clear();
-    LogProd evprod; evprod.clear();
-    EpochStats st; epoch_stats_clear(st);
+    HistScalars* const hs = m.hs;
     double* wout = nullptr;
 
 #pragma unroll 1
@@ -420,9 +428,12 @@ __device__ __forceinline__ void run_group() {
             // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
             inj_lo = sP.type_off[0]; inj_hi = sP.type_off[1];
             injecting = true; post = true;
-            e = 0; ec = sP.ep[0]; tset = sP.set_of_epoch[0];
-            qsum = 0.0; consts = 0.0; tsum = 0.0;
-            qprod.clear(); evprod.clear(); epoch_stats_clear(st);
+            e = 0; tset = sP.set_of_epoch[0];
+            if (sub == 0) {
+                hs->qsum = 0.0; hs->consts = 0.0; hs->tsum = 0.0;
+                hs->qprod.clear(); hs->evprod.clear(); epoch_stats_clear(hs->st);
+            }
+            G::sync();
             wout = sA.weights ? sA.weights + h * (unsigned long long)NG : nullptr;
             if (wout) for (int g = sub; g < NG; g += W) wout[g] = 0.0;
         }
@@ -445,7 +456,7 @@ __device__ __forceinline__ void run_group() {
                 comb -= sP.lfact[s.nA] - sP.lfact[s.nA - a0] - sP.lfact[a0];
                 comb -= sP.lfact[s.nB] - sP.lfact[s.nB - b0] - sP.lfact[b0];
                 comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
-                consts += comb;
+                if (sub == 0) hs->consts += comb;
             }
             injecting = false;
             end_now = s.overflow;
@@ -453,13 +464,16 @@ __device__ __forceinline__ void run_group() {
 
         if (!end_now) {
             // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
-            type_weights<W>(m, s, ec.dthA, ec.dthB, ec.drho);
+            const EpochConst* __restrict__ ecp = sP.ep + e;
+            const double dthA = __ldg(&ecp->dthA), dthB = __ldg(&ecp->dthB), drho_e = __ldg(&ecp->drho);
+            type_weights<W>(m, s, dthA, dthB, drho_e);
             const int sx = pick<W>(s.nslots, rng.next(), true);
             const double p_hap = m.sd[0] / m.sd[1];
             const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
             const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
-            const double Dd = nn + (double)(Ac + Cc) * ec.dthA + (double)(Bc + Cc) * ec.dthB + ec.drho * (double)Cc;
-            const double rate = Dd * ec.inv2Ntau;
+            const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
+            const double rate = Dd * __ldg(&ecp->inv2Ntau);
+            const double tsum = hs->tsum;
             const double wait = -dlog(rng.next()) / rate;
             const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
 
@@ -467,15 +481,20 @@ __device__ __forceinline__ void run_group() {
             const bool boundary = (e < T - 1) && !(tsum + wait < sP.times[e + 1]);
             const bool finish = (e == T - 1) && (n <= 5);
             if (boundary || finish) {
-                if (boundary) {
-                    const double excess = sP.times[e + 1] - tsum;
-                    tsum = sP.times[e + 1];
-                    qsum += -rate * excess;
-                    st.s_nn += nn * excess; st.s_a += aa * excess; st.s_c += (double)Cc * excess;
-                    st.bnd_nn = nn; st.bnd_a = aa; st.bnd_c = (double)Cc; st.has_bnd = 1; st.n_rate += 1;
+                if (sub == 0) {
+                    EpochStats& st = hs->st;
+                    if (boundary) {
+                        const double excess = sP.times[e + 1] - tsum;
+                        hs->tsum = sP.times[e + 1];
+                        hs->qsum += -rate * excess;
+                        st.s_nn += nn * excess; st.s_a += aa * excess; st.s_c += (double)Cc * excess;
+                        st.bnd_nn = nn; st.bnd_a = aa; st.bnd_c = (double)Cc; st.has_bnd = 1; st.n_rate += 1;
+                    }
+                    st.slog = logprod_value(hs->evprod);
                 }
-                st.slog = evprod.value();
+                G::sync();
                 if (wout) {
+                    const EpochStats st = hs->st;
                     const GridConst* gc = sP.grid + (size_t)e * NG;
 #pragma unroll 1
                     for (int g = sub; g < NG; g += W) {
@@ -484,7 +503,8 @@ __device__ __forceinline__ void run_group() {
                                                      [](double x) { return dlog(x); });
                     }
                 }
-                epoch_stats_clear(st); evprod.clear();
+                G::sync();
+                if (sub == 0) { epoch_stats_clear(hs->st); hs->evprod.clear(); }
                 if (sA.lineages && sub == 0) sA.lineages[h * (unsigned long long)T + e] = (double)n;
                 if (finish) {
                     end_now = true;
@@ -493,12 +513,9 @@ __device__ __forceinline__ void run_group() {
                     inj_lo = sP.type_off[e]; inj_hi = sP.type_off[e + 1];
                     injecting = true;
                     post = true;
-                    ec = sP.ep[e];
                     tset = sP.set_of_epoch[e];
                 }
             } else {
-                tsum += wait;
-
                 // ---- one event (ProposalEngine.cpp:134-566) ----
                 const unsigned long long xw = m.words[sx];
                 const unsigned int xcg = m.cg[sx], xxc = m.xc[sx];
@@ -522,6 +539,7 @@ __device__ __forceinline__ void run_group() {
                 } else if (xg == GA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
 
                 adjust<W>(s, xg, xw, -1);               // H' = H - x  (:168)
+                const double dtheta_e = __ldg(&ecp->dtheta);
                 const int ns = s.nslots;
                 const bool isC = (xg == GC), isA = (xg == GA);
                 const int Lx = isC ? Ltot : (isA ? LA : LB), offb = (xg == GB) ? LA : 0;
@@ -572,7 +590,7 @@ __device__ __forceinline__ void run_group() {
                         if (!isC) pi0 = mA1;
                     }
                     if (!isC && valid) {
-                        if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = ec.dtheta * (double)own * v1 / pi0;
+                        if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = dtheta_e * (double)own * v1 / pi0;
                         // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
                         if (partner) m.aux[qi - Lx - 1] = 0.5 * mA2 * v1 + 0.5 * v2 * pi0;
                     }
@@ -624,12 +642,12 @@ __device__ __forceinline__ void run_group() {
                     // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
                     const double pj = 0.5 * mA1 * mB2 + 0.5 * mB1 * mA2;
 #pragma unroll 1
-                    for (int k = sub; k < Ltot; k += W) m.pv[k] = ec.dtheta * (double)Cij * m.pv[k] / pi0;
+                    for (int k = sub; k < Ltot; k += W) m.pv[k] = dtheta_e * (double)Cij * m.pv[k] / pi0;
                     if (sub == 0) {
                         m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
                         m.pv[Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
                         m.pv[Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / mB1 : 0.0;
-                        m.pv[Ltot + 3] = ec.drho * (double)Cij * pj / pi0;
+                        m.pv[Ltot + 3] = drho_e * (double)Cij * pj / pi0;
                     }
                     ncand = Ltot + 4;
                     npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
@@ -643,8 +661,7 @@ __device__ __forceinline__ void run_group() {
                 // ---- sample the move (sampleFromVector :568-583) ----
                 const int idx = pick<W>(ncand, rng.next(), false);
                 // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
-                qsum += -rate * wait;
-                qprod.mul(rate * p_hap * m.sd[0] / m.sd[1]);
+                const double qfac = rate * p_hap * m.sd[0] / m.sd[1];
 
                 // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
                 double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
@@ -682,11 +699,19 @@ __device__ __forceinline__ void run_group() {
                 nev++;
 
                 // ---- target density bookkeeping (:457-546) ----
-                evprod.mul(evc);
-                st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
-                if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
-                if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; post = false; }
-                else st.n_rate++;
+                if (sub == 0) {
+                    EpochStats& st = hs->st;
+                    hs->tsum = tsum + wait;
+                    hs->qsum += -rate * wait;
+                    hs->qprod.mul(qfac);
+                    hs->evprod.mul(evc);
+                    st.s_nn += nn * wait; st.s_a += aa * wait; st.s_c += (double)Cc * wait;
+                    if (kind == 1) st.n_mut++; else if (kind == 2) st.n_rec++;
+                    if (post) { st.has_post = 1; st.post_nn = nn; st.post_a = aa; st.post_c = (double)Cc; }
+                    else st.n_rate++;
+                }
+                post = false;
+                G::sync();
                 if (nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
                 end_now = s.overflow;
             }
@@ -695,8 +720,9 @@ __device__ __forceinline__ void run_group() {
         if (end_now) {
             // ---- final weight (ProposalEngine.cpp:817-858) ----
             const double ln2 = 0.69314718055994530942;
-            const double q = qsum + qprod.value();
-            const double fin = consts + sP.perm_const - q
+            G::sync();
+            const double q = hs->qsum + logprod_value(hs->qprod);
+            const double fin = hs->consts + sP.perm_const - q
                              - ((double)(LA + LB) * ln2 * (double)s.nC + (double)LA * ln2 * (double)s.nA + (double)LB * ln2 * (double)s.nB);
             if (wout) {
                 G::sync();
@@ -704,7 +730,7 @@ __device__ __forceinline__ void run_group() {
                 for (int g = sub; g < NG; g += W) wout[g] = s.overflow ? bad : wout[g] + fin;
             }
             if (sub == 0) {
-                if (sA.tmrca) sA.tmrca[h] = tsum;
+                if (sA.tmrca) sA.tmrca[h] = hs->tsum;
                 if (sA.nevents) sA.nevents[h] = nev;
                 if (tracing && sA.event_counts) sA.event_counts[h] = nev;
                 if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
