@@ -202,21 +202,27 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
 
     // launch geometry: persistent CTAs of 128 threads = 128/W groups of W lanes, one history per group.
     // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
-    s->group = (P.Ltot + 1 <= 16) ? 16 : 32;
+    // The width that keeps more histories in flight per SM wins (shared memory per group grows with the
+    // lineage bound: 200 sequences need ~15 KB per group and W = 16 would leave one CTA per SM).
+    auto geometry = [&](int W, size_t& smem, int& occ) -> int {
+        const size_t gb = history_group_bytes(P.kmax, P.pvmax, P.Ltot, W);
+        smem = gb * (128 / W); occ = 0;
+        if (smem > 227 * 1024) return -1;
+        const void* fn = W == 8 ? (const void*)history_kernel<8> : W == 16 ? (const void*)history_kernel<16> : (const void*)history_kernel<32>;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem) != cudaSuccess) return -1;
+        return occ * (128 / W);
+    };
+    size_t smem16 = 0, smem32 = 0; int occ16 = 0, occ32 = 0;
+    const int g16 = (P.Ltot + 1 <= 16) ? geometry(16, smem16, occ16) : -1;
+    const int g32 = geometry(32, smem32, occ32);
+    s->group = (g16 > g32) ? 16 : 32;
     if (const char* g = std::getenv("COALGPU_GROUP")) { const int v = std::atoi(g); if (v == 8 || v == 16 || v == 32) s->group = v; }
-    for (;;) {
-        s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
-        s->smem_bytes = (size_t)s->warp_bytes * (128 / s->group);
-        if (s->smem_bytes <= 227 * 1024 || s->group == 32) break;
-        s->group *= 2;
-    }
+    size_t smem = 0; int occ = 0;
+    if (geometry(s->group, smem, occ) < 1) { cudaGetLastError(); coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
+    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
+    s->smem_bytes = smem;
     P.warp_bytes = s->warp_bytes;
-    if (s->smem_bytes > 227 * 1024) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
-    const void* kfn = s->group == 8 ? (const void*)history_kernel<8> : s->group == 16 ? (const void*)history_kernel<16> : (const void*)history_kernel<32>;
-    CU_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    int occ = 0;
-    CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, 128, s->smem_bytes));
-    if (occ < 1) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, "history kernel does not fit on an SM"); }
     s->grid = sm_count * occ;
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
@@ -392,6 +398,82 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     cleanup();
     if (rc) return fail(rc, m);
     if (nov) return fail(COALGPU_EOVERFLOW, "a history outgrew the type-store capacity");
+    return 0;
+}
+
+// Locus-pair batching: the reference runs its pairs one after another (main.cpp:242-311);
+// a pair with a few thousand importance samples cannot fill 148 SMs, so the pairs of a wave are launched
+// on separate streams and run concurrently. Results are identical to n_problems calls of coalgpu_run_sampler.
+int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples, uint32_t Q,
+                              uint64_t seed, int device, coalgpu_result* results) {
+    if (n_problems < 0 || (n_problems > 0 && (!problems || !results))) return fail(COALGPU_EINVAL, "null argument");
+    if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
+    const int kWave = 32, kStreams = 16;
+    struct Job { coalgpu_sampler* s = nullptr; double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr; std::vector<double> hp; };
+    cudaStream_t streams[kStreams] = {};
+    int n_streams = 0;
+    int rc = 0; std::string err;
+    for (int w0 = 0; w0 < n_problems && !rc; w0 += kWave) {
+        const int nw = std::min(kWave, n_problems - w0);
+        // a pair whose weight matrix is large already fills the device: run it through the chunked path
+        std::vector<Job> jobs(nw);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        auto cleanup = [&]() {
+            for (Job& j : jobs) {
+                if (j.d_w) cudaFree(j.d_w); if (j.d_t) cudaFree(j.d_t); if (j.d_l) cudaFree(j.d_l); if (j.d_p) cudaFree(j.d_p);
+                if (j.s) coalgpu_destroy(j.s);
+            }
+            if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
+        };
+#define WB_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess && !rc) { rc = COALGPU_ECUDA; err = std::string(#expr) + ": " + cudaGetErrorString(_e); } } while (0)
+        for (int k = 0; k < nw && !rc; k++) {
+            const coalgpu_problem* p = problems + w0 + k;
+            const size_t G = (size_t)p->n_mu * p->n_rho * p->n_lambda;
+            if (n_samples * (G + p->T + 1) * 8 > (256ull << 20)) {        // big pair: sequential, chunked
+                rc = coalgpu_run_sampler(p, n_samples, Q, seed, device, results + w0 + k);
+                if (rc) err = g_err;
+                continue;
+            }
+            Job& j = jobs[k];
+            rc = coalgpu_create(p, Q, device, &j.s);
+            if (rc) { err = g_err; break; }
+            if (n_streams == 0) { for (int i = 0; i < kStreams; i++) WB_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)); n_streams = kStreams; }
+            const int T = j.s->T; const size_t nstat = 3 + T;
+            j.hp.resize(nstat * G * 2);
+            WB_OK(cudaMalloc((void**)&j.d_w, n_samples * G * sizeof(double)));
+            WB_OK(cudaMalloc((void**)&j.d_t, n_samples * sizeof(double)));
+            WB_OK(cudaMalloc((void**)&j.d_l, n_samples * T * sizeof(double)));
+            WB_OK(cudaMalloc((void**)&j.d_p, j.hp.size() * sizeof(double)));
+        }
+        if (!rc) { WB_OK(cudaEventCreate(&e0)); WB_OK(cudaEventCreate(&e1)); WB_OK(cudaDeviceSynchronize()); WB_OK(cudaEventRecord(e0, streams[0])); }
+        for (int k = 0; k < nw && !rc; k++) {
+            Job& j = jobs[k];
+            if (!j.s) continue;
+            cudaStream_t st = streams[k % kStreams];
+            rc = coalgpu_sample(j.s, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0);
+            if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
+            if (rc) { err = g_err; break; }
+            WB_OK(cudaMemcpyAsync(j.hp.data(), j.d_p, j.hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        WB_OK(cudaDeviceSynchronize());
+        float ms = 0;
+        if (!rc && e0) { WB_OK(cudaEventRecord(e1, streams[0])); WB_OK(cudaEventSynchronize(e1)); WB_OK(cudaEventElapsedTime(&ms, e0, e1)); }
+#undef WB_OK
+        for (int k = 0; k < nw && !rc; k++) {
+            Job& j = jobs[k];
+            if (!j.s) continue;
+            coalgpu_result* r = results + w0 + k;
+            uint64_t nev = 0, npi = 0, nov = 0;
+            rc = coalgpu_counters(j.s, &nev, &npi, &nov);
+            if (!rc) rc = coalgpu_finalize(j.s->G, j.s->T, j.hp.data(), r);
+            if (rc) { err = g_err; break; }
+            r->n_histories = n_samples; r->n_events = nev; r->n_pismc = npi; r->seconds_device = ms * 1e-3 / nw;
+            if (nov) { rc = COALGPU_EOVERFLOW; err = "a history outgrew the type-store capacity"; }
+        }
+        cleanup();
+    }
+    for (int i = 0; i < n_streams; i++) cudaStreamDestroy(streams[i]);
+    if (rc) return fail(rc, err);
     return 0;
 }
 

@@ -52,7 +52,7 @@ class _CResult(C.Structure):
 
 _lib = None
 
-EXPORTS = ["coalgpu_run_sampler", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
+EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
            "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak"]
 
@@ -75,6 +75,7 @@ def load_library():
         L.coalgpu_destroy.restype = None
         L.coalgpu_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.coalgpu_run_sampler.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
+        L.coalgpu_run_sampler_batch.argtypes = [C.c_int32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         L.coalgpu_finalize.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.coalgpu_tables.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
         L.coalgpu_pismc_classes.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
@@ -169,6 +170,18 @@ class ImportanceSampler:
         return _to_output(sample, arrs, res)
 
     runSampler = run_sampler
+
+    def run_sampler_batch(self, samples, num_iterations: int, quadrature_points: int = 16, seed: int = 0, device: int = 0):
+        """runSampler for every locus pair of an analysis (the loop of main.cpp:242-311) in one call: the
+        pairs run concurrently on the GPU. Returns one SamplerOutput per problem, identical to run_sampler's."""
+        L = load_library()
+        n = len(samples)
+        packed = [_PackedProblem(p) for p in samples]
+        probs = (_CProblem * n)(*[pk.struct for pk in packed])
+        arrs = [_result_arrays(p) for p in samples]
+        ress = (_CResult * n)(*[_CResult(_dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), 0, 0, 0, 0.0) for a in arrs])
+        _check(L.coalgpu_run_sampler_batch(n, probs, int(num_iterations), int(quadrature_points), int(seed), int(device), ress))
+        return [_to_output(p, a, r) for p, a, r in zip(samples, arrs, ress)]
 
 
 class DeviceSampler:

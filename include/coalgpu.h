@@ -91,6 +91,11 @@ typedef struct coalgpu_sampler coalgpu_sampler;
 int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t quadrature_points,
                         uint64_t seed, int device, coalgpu_result* result);
 
+/* The same for several locus pairs at once (the double loop of main.cpp:242-311): pairs are launched on
+ * separate CUDA streams so that small batches still fill the device. results[k] belongs to problems[k]. */
+int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples,
+                              uint32_t quadrature_points, uint64_t seed, int device, coalgpu_result* results);
+
 /* ---- staged API --------------------------------------------------------------------------------*/
 /* Build the HMM tables on the host (ConditionalSamplingHMM.cpp:36-226, same operation order),
  * upload problem + tables to `device`. */

@@ -177,3 +177,22 @@ def test_cfg4_shape_200_sequences_10_time_points(oracle, cuda_lib):
     p = sub_problem(aln, loci, *pairs[3])
     assert p.T == 10 and p.n_lineages() == 200
     _compare_histories(oracle, p, 6, seed=41, max_events=1 << 16)
+
+
+def test_batched_pairs_equal_single_calls(cuda_lib):
+    """coalgpu_run_sampler_batch (pairs launched concurrently on streams) returns exactly what
+    one coalgpu_run_sampler call per pair returns."""
+    import coalescenator_b200 as cb
+    from coalescenator_b200.problem import make_config, sub_problem
+    aln, loci, pairs = make_config(1)
+    probs = [sub_problem(aln, loci, *pr, target_mu=[1e-5, 2.5e-5], target_lambda=[500.0, 1000.0]) for pr in pairs[:9]]
+    smp = cb.ImportanceSampler()
+    batch = smp.run_sampler_batch(probs, 700, seed=5)
+    assert len(batch) == len(probs)
+    for p, b in zip(probs, batch):
+        one = smp.run_sampler(p, 700, seed=5)
+        np.testing.assert_array_equal(b.likelihood, one.likelihood)
+        np.testing.assert_array_equal(b.likelihoodSq, one.likelihoodSq)
+        np.testing.assert_array_equal(b.tmrca, one.tmrca)
+        np.testing.assert_array_equal(b.lineages_remaining, one.lineages_remaining)
+        assert b.n_events == one.n_events and b.n_histories == 700
