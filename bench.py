@@ -249,8 +249,16 @@ def main():
     from coalescenator_b200.sampler import fp64_peak_tflops
     fp64_peak = fp64_peak_tflops(local)
     fp64_achieved = flop_per_launch / (k_avg_ms * 1e-3) / 1e12
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled to this launch size
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["histories_in_launch"] * per_pair
+        traffic_note = "ncu capture of a %d-history launch (%s), scaled to %d histories" % (tj["histories_in_launch"], tj["capture"], per_pair)
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": None, "peak_kind": pk_kind, "kernel": "history_kernel", "kernel_ms": k_avg_ms,
+            "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes": per_pair * bytes_per_hist, "peak_kind": pk_kind, "kernel": "history_kernel", "kernel_ms": k_avg_ms,
             "note": "path is fp64-ALU / issue bound, not HBM bound (SURVEY.md §8d): see alu",
             "alu": {"bound": "fp64", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
                     "peak_kind": "measured in this run (coalgpu_fp64_peak, dependent FMA chains)",
