@@ -14,6 +14,10 @@ namespace {
 constexpr int GA = COALGPU_GAMMA_A, GB = COALGPU_GAMMA_B, GC = COALGPU_GAMMA_C;
 constexpr unsigned int kCntMask = 0x3fffffffu;
 constexpr int kAppended = 0x40000000;
+#ifndef COAL_SLOT_UNROLL
+#define COAL_SLOT_UNROLL 1
+#endif
+constexpr int kSlotUnroll = COAL_SLOT_UNROLL;   // unroll factor of the loops over stored types
 
 // problem + launch arguments, copied once per CTA from the kernel parameters so that the out-of-line
 // helpers can read them without carrying them in registers
@@ -266,7 +270,7 @@ __device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int
                                                double& num1, double& num2, unsigned int& ncomp) {
     num1 = 0.0; num2 = 0.0; ncomp = 0;
     const unsigned long long mask = (qg == GA) ? sP.maskA : sP.maskB;
-#pragma unroll 2
+#pragma unroll kSlotUnroll
     for (int j = 0; j < nslots; j++) {
         const unsigned long long wj = m.words[j];
         const unsigned int cgj = m.cg[j];
@@ -308,7 +312,7 @@ __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb,
         else { delw = m.words[m.plist[qi]]; delg = pg; qw = xw | delw; }
 #pragma unroll 1
         for (int sidx = 0; sidx < nsum; sidx++) mine[sidx] = 0xffff0000u;
-#pragma unroll 2
+#pragma unroll kSlotUnroll
         for (int j = 0; j < ns; j++) {
             const unsigned long long wj = m.words[j];
             const unsigned int cgj = m.cg[j];
@@ -360,7 +364,7 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
     if (!empty) {
 #define COAL_FWD(PER) chunk_forward<PER>(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
                                           cls, 1, nH, tot, sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
-        if (per == 1) cp = COAL_FWD(1); else if (per == 2) cp = COAL_FWD(2); else cp = COAL_FWD(4);
+        cp = COAL_FWD(4);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
 #undef COAL_FWD
     }
     // exclusive prefixes of (pre, preB) over the lanes of the sub-group
@@ -610,11 +614,11 @@ __device__ __forceinline__ void run_group() {
                     int my_nH; ClassTotals my_tot;
                     build_classes<W>(m, ns, nqb, qb, isC, xw, pg, my_nH, my_tot);
                     nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
-                    // one pass: sub-groups of p lanes per query, p the largest power of two with nqb * p <= W (<= 16).
+                    // one pass: sub-groups of p lanes per query, p the largest power of two with nqb * p <= W (<= 4).
                     // (Splitting the batch into several always-full passes costs more in per-pass set-up than the
                     // idle lanes cost here, profiles/r1_kernel_iterations.md.)
                     int p = 1;
-                    while (p < kQd && nqb * (p * 2) <= W) p *= 2;
+                    while (p < 4 && nqb * (p * 2) <= W) p *= 2;
                     const int ql = sub / p;
                     const bool valid = ql < nqb;
                     const int qloc = valid ? ql : 0;
