@@ -208,7 +208,7 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
         const size_t gb = history_group_bytes(P.kmax, P.pvmax, P.Ltot, W);
         smem = gb * (128 / W); occ = 0;
         if (smem > 227 * 1024) return -1;
-        const void* fn = W == 8 ? (const void*)history_kernel<8> : W == 16 ? (const void*)history_kernel<16> : (const void*)history_kernel<32>;
+        const void* fn = (const void*)history_kernel_select(W, P.Ltot <= 32);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem) != cudaSuccess) return -1;
         return occ * (128 / W);
@@ -247,16 +247,9 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
     // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
-    if (s->group == 8) {
-        CU_OK(cudaFuncSetAttribute(history_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        history_kernel<8><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
-    } else if (s->group == 16) {
-        CU_OK(cudaFuncSetAttribute(history_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        history_kernel<16><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
-    } else {
-        CU_OK(cudaFuncSetAttribute(history_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        history_kernel<32><<<grid, 128, s->smem_bytes, st>>>(s->P, a);
-    }
+    history_kernel_fn kfn = history_kernel_select(s->group, s->P.Ltot <= 32);
+    CU_OK(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    kfn<<<grid, 128, s->smem_bytes, st>>>(s->P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
     return 0;

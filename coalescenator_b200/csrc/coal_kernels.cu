@@ -122,6 +122,22 @@ struct HState {
 
 __device__ __noinline__ double dlog(double x) { return log(x); }
 
+// Haplotype words in the hot loops over stored types: when LA + LB <= 32 only the low half of the 64-bit
+// word is populated and the xor / mask / popcount chain runs on 32-bit registers (half the ALU and XU work).
+template <bool N32> struct WordOps;
+template <> struct WordOps<true> {
+    typedef unsigned int T;
+    static __device__ __forceinline__ T load(const unsigned long long* words, int j) { return reinterpret_cast<const unsigned int*>(words)[2 * j]; }
+    static __device__ __forceinline__ T narrow(unsigned long long w) { return (unsigned int)w; }
+    static __device__ __forceinline__ int popc(T x) { return __popc(x); }
+};
+template <> struct WordOps<false> {
+    typedef unsigned long long T;
+    static __device__ __forceinline__ T load(const unsigned long long* words, int j) { return words[j]; }
+    static __device__ __forceinline__ T narrow(unsigned long long w) { return w; }
+    static __device__ __forceinline__ int popc(T x) { return __popcll(x); }
+};
+
 // ---- type store ------------------------------------------------------------------------------------
 
 // Change the multiplicity of type (g, w) by delta (TypeContainer::addType / removeType,
@@ -265,20 +281,22 @@ __device__ __forceinline__ void type_weights(const WarpMem& m, const HState& s, 
 // One-locus query per lane: query (qg in {A,B}, qw), optionally leaving out one copy of the query's own
 // type (the H - b_k configurations of ProposalEngine.cpp:323-329). Evaluated against two table rows at once
 // (the same distance histogram serves pi(.|H) and pi(.|H + other-locus lineage), ProposalEngine.cpp:120-132).
-__device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int qg, unsigned long long qw, bool excl,
+template <bool N32>
+__device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int qg, unsigned long long qw64, bool excl,
                                                const double* __restrict__ wE1, const double* __restrict__ wE2,
                                                double& num1, double& num2, unsigned int& ncomp) {
+    typedef WordOps<N32> WO;
     num1 = 0.0; num2 = 0.0; ncomp = 0;
-    const unsigned long long mask = (qg == GA) ? sP.maskA : sP.maskB;
+    const typename WO::T mask = WO::narrow((qg == GA) ? sP.maskA : sP.maskB), qw = WO::narrow(qw64);
 #pragma unroll kSlotUnroll
     for (int j = 0; j < nslots; j++) {
-        const unsigned long long wj = m.words[j];
+        const typename WO::T wj = WO::load(m.words, j);
         const unsigned int cgj = m.cg[j];
         const int gj = (int)(cgj >> 30);
         unsigned int c = cgj & kCntMask;
         if (gj == qg || gj == GC) {
             if (excl && gj == qg && wj == qw) c -= 1;
-            const int d = __popcll((wj ^ qw) & mask);
+            const int d = WO::popc((wj ^ qw) & mask);
             const double cf = (double)c;
             num1 += cf * __ldg(wE1 + d);
             num2 += cf * __ldg(wE2 + d);
@@ -295,33 +313,35 @@ __device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int
 //  A/B chosen: query qb+q = (x, b_k) with b_k = partner plist[qb+q], against H' - b_k
 // On return lane q < nqb holds (nH, totals) of query q and its class list sits in hist[q*hstride ...].
 // (A lanes-over-types variant with match.any + group reductions was 1.8x slower: profiles/r1_v2_*.)
-template <int W>
+template <int W, bool N32>
 __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb, int qb, bool isC, unsigned long long xw, int pg,
                                               int& nH_out, ClassTotals& tot_out) {
     const int sub = Grp<W>::sub();
     const int nsum = sP.Ltot + 2, hstride = nsum | 1;
-    const unsigned long long maskA = sP.maskA, maskB = sP.maskB;
+    typedef WordOps<N32> WO;
+    const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
     unsigned int* mine = m.hist + sub * hstride;
     const bool active = sub < nqb;
-    unsigned long long qw = xw, delw = 0ull; int delg = -1;
+    unsigned long long qw64 = xw, delw64 = 0ull; int delg = -1;
     int nH = 0;
     ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
     if (active) {
         const int qi = qb + sub;
-        if (isC) { if (qi > 0) qw = xw ^ (1ull << (qi - 1)); }
-        else { delw = m.words[m.plist[qi]]; delg = pg; qw = xw | delw; }
+        if (isC) { if (qi > 0) qw64 = xw ^ (1ull << (qi - 1)); }
+        else { delw64 = m.words[m.plist[qi]]; delg = pg; qw64 = xw | delw64; }
+        const typename WO::T qw = WO::narrow(qw64), delw = WO::narrow(delw64);
 #pragma unroll 1
         for (int sidx = 0; sidx < nsum; sidx++) mine[sidx] = 0xffff0000u;
 #pragma unroll kSlotUnroll
         for (int j = 0; j < ns; j++) {
-            const unsigned long long wj = m.words[j];
+            const typename WO::T wj = WO::load(m.words, j);
             const unsigned int cgj = m.cg[j];
             const int gj = (int)(cgj >> 30);
             unsigned int c = cgj & kCntMask;
             if (gj == delg && wj == delw) c -= 1;
             if (c > 0) {
-                const unsigned long long y = wj ^ qw;
-                const int da = __popcll(y & maskA), db = __popcll(y & maskB);
+                const typename WO::T y = wj ^ qw;
+                const int da = WO::popc(y & maskA), db = WO::popc(y & maskB);
                 int sidx; unsigned int rep;
                 if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
                 const unsigned int v = mine[sidx];
@@ -397,7 +417,7 @@ __device__ __forceinline__ double logprod_value(const LogProd& p) { return dlog(
 // One flat loop per group: fetch a history index, draw the history event by event, write its outputs, fetch
 // the next. Keeping everything in ONE loop body lets the groups that share a warp reconverge at every
 // iteration (structured control flow) instead of drifting into different call frames.
-template <int W>
+template <int W, bool N32>
 __device__ __forceinline__ void run_group() {
     typedef Grp<W> G;
     const WarpMem m = wm<W>();
@@ -585,7 +605,7 @@ __device__ __forceinline__ void run_group() {
                     const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
                     const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
                     double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
-                    if (valid) marginal_query(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
+                    if (valid) marginal_query<N32>(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
                     const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
                     const double v2 = marginal_finish(num2, ncomp, nc_alt, powl, sP.wsum);
                     if (q0 == 0) {
@@ -612,7 +632,7 @@ __device__ __forceinline__ void run_group() {
                 for (int qb = 0; qb < nq; qb += W) {
                     const int nqb = min(W, nq - qb);
                     int my_nH; ClassTotals my_tot;
-                    build_classes<W>(m, ns, nqb, qb, isC, xw, pg, my_nH, my_tot);
+                    build_classes<W, N32>(m, ns, nqb, qb, isC, xw, pg, my_nH, my_tot);
                     nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
                     // one pass: sub-groups of p lanes per query, p the largest power of two with nqb * p <= W (<= 4).
                     // (Splitting the batch into several always-full passes costs more in per-pass set-up than the
@@ -756,15 +776,19 @@ __device__ __forceinline__ void run_group() {
 #ifndef COAL_MIN_CTAS
 #define COAL_MIN_CTAS 3
 #endif
-template <int W>
+template <int W, bool N32>
 __global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
-    run_group<W>();
+    run_group<W, N32>();
 }
-template __global__ void history_kernel<8>(const DevProblem, const SampleArgs);
-template __global__ void history_kernel<16>(const DevProblem, const SampleArgs);
-template __global__ void history_kernel<32>(const DevProblem, const SampleArgs);
+
+// host-side selection of the instantiation: W lanes per history, narrow words when LA + LB <= 32
+typedef void (*history_kernel_fn)(const DevProblem, const SampleArgs);
+history_kernel_fn history_kernel_select(int W, bool narrow) {
+    if (narrow) return W == 8 ? history_kernel<8, true> : W == 16 ? history_kernel<16, true> : history_kernel<32, true>;
+    return W == 8 ? history_kernel<8, false> : W == 16 ? history_kernel<16, false> : history_kernel<32, false>;
+}
 
 // K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC).
 // One group of 16 lanes per query; classes are staged into the group's shared-memory column.
