@@ -64,12 +64,17 @@ struct SampleArgs {
 
 __constant__ double c_w[kQd];   // interval weights (ConditionalSamplingHMM.cpp:63-71)
 
+#ifndef COAL_PHILOX_UNROLL
+#define COAL_PHILOX_UNROLL 2
+#endif
+constexpr int kPhiloxUnroll = COAL_PHILOX_UNROLL;
+
 // ---- Philox4x32-10 ------------------------------------------------------------------------------
 // One copy in the binary (the history kernel is instruction-cache sensitive, profiles/r1_v0_*).
 __device__ __noinline__ uint4 philox_block(unsigned long long seed, unsigned long long hist, unsigned long long blk) {
     unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
     unsigned int c0 = (unsigned int)hist, c1 = (unsigned int)(hist >> 32), c2 = (unsigned int)blk, c3 = (unsigned int)(blk >> 32);
-#pragma unroll
+#pragma unroll kPhiloxUnroll
     for (int r = 0; r < 10; r++) {
         const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
