@@ -168,6 +168,8 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     }
     std::vector<double> lfact(n_max + 2);
     for (int i = 0; i < n_max + 2; i++) lfact[i] = std::lgamma((double)i + 1.0);
+    std::vector<double> rcp(n_max + 2, 0.0);
+    for (int i = 1; i < n_max + 2; i++) rcp[i] = 1.0 / (double)i;
     std::vector<double> times(p->times, p->times + T);
 
     DevProblem& P = s->P;
@@ -187,13 +189,13 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     P.wsum = wsum;
 
     int rc = 0;
-    double* d_rows; int* d_set; double* d_times; EpochConst* d_ep; GridConst* d_grid; double* d_lf; int* d_toff;
+    double* d_rows; int* d_set; double* d_times; EpochConst* d_ep; GridConst* d_grid; double* d_lf; double* d_rcp; int* d_toff;
     unsigned long long* d_tw; unsigned int* d_tcg;
 #define UP(vec, ptr) do { rc = upload(vec, &ptr); if (rc) { coalgpu_destroy(s); return rc; } s->allocs.push_back(ptr); } while (0)
     UP(s->tab.rows, d_rows); UP(s->tab.set_of_epoch, d_set); UP(times, d_times); UP(ep, d_ep); UP(grid, d_grid);
-    UP(lfact, d_lf); UP(type_off, d_toff); UP(type_w, d_tw); UP(type_cg, d_tcg);
+    UP(lfact, d_lf); UP(rcp, d_rcp); UP(type_off, d_toff); UP(type_w, d_tw); UP(type_cg, d_tcg);
 #undef UP
-    P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf;
+    P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf; P.rcp = d_rcp;
     P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
     CU_OK(cudaMemcpyToSymbol(c_w, s->tab.w.data(), sizeof(double) * kQ));
     CU_OK(cudaMalloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));

@@ -45,6 +45,7 @@ struct DevProblem {
     const EpochConst* ep;     // [T]
     const GridConst* grid;    // [T][G]
     const double* lfact;      // [n_max+2] log factorials
+    const double* rcp;        // [n_max+2] 1/k (rcp[0] = 0): fp64 division is a long instruction sequence
     const int* type_off;      // [T+1]
     const unsigned long long* type_w;
     const unsigned int* type_cg;   // count | gamma << 30, duplicates merged, insertion order

@@ -381,9 +381,10 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
     const int i0 = r * per;
     auto ld = [row](int off) { return __ldg(row + off); };
     ChunkPartial cp = {0, 0, 0, 0, 0, 0};
+    const double inv_n = __ldg(sP.rcp + tot.n);
     if (!empty) {
 #define COAL_FWD(PER) chunk_forward<PER>(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
-                                          cls, 1, nH, tot, sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
+                                          cls, 1, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB), sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
         cp = COAL_FWD(4);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
 #undef COAL_FWD
     }
@@ -403,7 +404,7 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
         acc += __shfl_xor_sync(gm, acc, o, p);
         acc2 += __shfl_xor_sync(gm, acc2, o, p);
     }
-    return empty ? sP.pow2negL : pismc_finish(acc, acc2, tot.n);
+    return empty ? sP.pow2negL : (acc * inv_n + acc2) * inv_n;
 }
 
 __device__ __forceinline__ const double* row_ptr(int set, int n_all) {
@@ -492,7 +493,7 @@ __device__ __forceinline__ void run_group() {
             const double dthA = __ldg(&ecp->dthA), dthB = __ldg(&ecp->dthB), drho_e = __ldg(&ecp->drho);
             type_weights<W>(m, s, dthA, dthB, drho_e);
             const int sx = pick<W>(s.nslots, rng.next(), true);
-            const double p_hap = m.sd[0] / m.sd[1];
+            const double hap_num = m.sd[0], hap_den = m.sd[1];      // p_hap = hap_num / hap_den, folded into qfac
             const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
             const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
             const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
@@ -606,15 +607,17 @@ __device__ __forceinline__ void run_group() {
                     const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
                     double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
                     if (valid) marginal_query<N32>(m, ns, qg, qw, excl, row_m1 + offw, row_alt + offw, num1, num2, ncomp);
-                    const double v1 = marginal_finish(num1, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
-                    const double v2 = marginal_finish(num2, ncomp, nc_alt, powl, sP.wsum);
+                    // fp64 division is a ~25-instruction sequence: reciprocals of lineage counts come from a table
+                    const double inv_nc = __ldg(sP.rcp + ncomp);
+                    const double v1 = marginal_finish_rcp(num1, inv_nc, ncomp, (unsigned int)(n - 1), powl, sP.wsum);
+                    const double v2 = marginal_finish_rcp(num2, inv_nc, ncomp, nc_alt, powl, sP.wsum);
                     if (q0 == 0) {
                         mA1 = G::shfl(v1, 0); mA2 = G::shfl(v2, 0);
                         mB1 = G::shfl(v1, 1); mB2 = G::shfl(v2, 1);
                         if (!isC) pi0 = mA1;
                     }
                     if (!isC && valid) {
-                        if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = dtheta_e * (double)own * v1 / pi0;
+                        if (qi >= 1 && qi <= Lx) m.pv[qi - 1] = dtheta_e * (double)own * v1;   // x 1/pi0 below
                         // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
                         if (partner) m.aux[qi - Lx - 1] = 0.5 * mA2 * v1 + 0.5 * v2 * pi0;
                     }
@@ -661,22 +664,25 @@ __device__ __forceinline__ void run_group() {
                 G::sync();
 
                 int ncand;
+                if (isC) pi0 = m.sd[2];
+                const double inv_pi0 = 1.0 / pi0;
                 if (isC) {
-                    pi0 = m.sd[2];
                     // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
                     const double pj = 0.5 * mA1 * mB2 + 0.5 * mB1 * mA2;
 #pragma unroll 1
-                    for (int k = sub; k < Ltot; k += W) m.pv[k] = dtheta_e * (double)Cij * m.pv[k] / pi0;
+                    for (int k = sub; k < Ltot; k += W) m.pv[k] = dtheta_e * (double)Cij * m.pv[k] * inv_pi0;
                     if (sub == 0) {
-                        m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) / pi0 : 0.0;
+                        m.pv[Ltot] = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
                         m.pv[Ltot + 1] = (Ai > 0) ? (double)(Ai * Cij) / mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
                         m.pv[Ltot + 2] = (Bj > 0) ? (double)(Bj * Cij) / mB1 : 0.0;
-                        m.pv[Ltot + 3] = drho_e * (double)Cij * pj / pi0;
+                        m.pv[Ltot + 3] = drho_e * (double)Cij * pj * inv_pi0;
                     }
                     ncand = Ltot + 4;
                     npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
                 } else {
-                    if (sub == 0) m.pv[Lx + np] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) / pi0 : 0.0;
+#pragma unroll 1
+                    for (int k = sub; k < Lx; k += W) m.pv[k] *= inv_pi0;
+                    if (sub == 0) m.pv[Lx + np] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
                     ncand = Lx + np + 1;
                     npi += (unsigned int)(1 + Lx + 5 * np);
                 }
@@ -685,7 +691,7 @@ __device__ __forceinline__ void run_group() {
                 // ---- sample the move (sampleFromVector :568-583) ----
                 const int idx = pick<W>(ncand, rng.next(), false);
                 // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
-                const double qfac = rate * p_hap * m.sd[0] / m.sd[1];
+                const double qfac = (rate * hap_num * m.sd[0]) / (hap_den * m.sd[1]);
 
                 // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
                 double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
@@ -827,7 +833,8 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
             ChunkPartial cp = {0, 0, 0, 0, 0, 0};
             auto ld = [row](int off) { return __ldg(row + off); };
             if (g == GC && nH > 0) cp = chunk_forward<1>(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
-                                                         col, 32, nH, tot, P.pow2negLA, P.pow2negLB, r, r + 1);
+                                                         col, 32, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0, tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0,
+                                                         P.pow2negLA, P.pow2negLB, r, r + 1);
             double ipre = cp.pre, ipreB = cp.preB;
             for (int o = 1; o < p; o <<= 1) {
                 const double t1 = __shfl_up_sync(kFull, ipre, o, p), t2 = __shfl_up_sync(kFull, ipreB, o, p);

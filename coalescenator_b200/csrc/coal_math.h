@@ -50,10 +50,9 @@ struct ClassTotals {
 template <int PER, class LoadF>
 COAL_HD ChunkPartial chunk_forward(LoadF ld, const double* w, int off_yw, int off_zlow, int off_g, int off_zdiag,
                                    int off_EA, int off_EB, const uint32_t* cls, int cstride, int nH,
-                                   ClassTotals tot, double pow2negLA, double pow2negLB, int i0, int i1) {
+                                   ClassTotals tot, double invA, double invB, double pow2negLA, double pow2negLB, int i0, int i1) {
+    // invA = 1/ncompA, invB = 1/ncompB (0 when the count is 0): the device reads them from a table
     ChunkPartial p = {0, 0, 0, 0, 0, 0};
-    const double invA = tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0;
-    const double invB = tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0;
     const double npartA = (double)(tot.n - tot.ncompA), npartB = (double)(tot.n - tot.ncompB);
     for (int ib = i0; ib < i1; ib += PER) {
         double aAll[PER], bAll[PER], x[PER], aAo[PER], bBo[PER];
@@ -108,6 +107,11 @@ COAL_HD double pismc_finish(double sum_acc, double sum_acc2, uint32_t n) {
 // One-locus query (ConditionalSamplingHMM.cpp:332-370): with hist[d] = lineages at distance d among the
 // classes ancestral at that locus, pi = sum_d hist[d] wE[d] / ncomp, wE[d] = sum_i w_i E[i][d]
 // (the non-ancestral lineages enter through the mean of the complete classes, which cancels).
+COAL_HD double marginal_finish_rcp(double num, double inv_ncomp, uint32_t ncomp, uint32_t n_cond, double pow2negL, double wsum) {
+    if (n_cond == 0) return pow2negL;
+    if (ncomp == 0) return pow2negL * wsum;
+    return num * inv_ncomp;
+}
 COAL_HD double marginal_finish(double num, uint32_t ncomp, uint32_t n_cond, double pow2negL, double wsum) {
     if (n_cond == 0) return pow2negL;               // empty configuration, :277-298
     if (ncomp == 0) return pow2negL * wsum;         // nothing ancestral at this locus, :249-252

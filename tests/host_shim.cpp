@@ -65,7 +65,7 @@ double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int3
     for (int r = 0; r < p; r++) {
         ChunkPartial cp;
 #define HS_CALL(PER) chunk_forward<PER>(ld, t.w.data(), lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB, \
-                                        cls.data(), 1, nH, tot, p2A, p2B, r * per, r * per + per)
+                                        cls.data(), 1, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0, tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, p2A, p2B, r * per, r * per + per)
         if (per == 1) cp = HS_CALL(1); else if (per == 2) cp = HS_CALL(2); else cp = HS_CALL(4);
 #undef HS_CALL
         acc += chunk_finish(cp, pre, preB); acc2 += cp.acc2;
