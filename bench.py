@@ -4,8 +4,8 @@ importance-sampled histories/sec). Contract: see the task description / DESIGN.m
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step = one pass of the hot path over one batch: `--per-step` histories spread evenly over the
-bench locus pairs of configuration cfg2 (5 time points x 50 sequences x 10 kb, --loci-size 100),
+A step = one pass of the hot path over one batch: `--per-step` histories (default 98,304 per locus pair, the
+1e5 importance samples per pair of BASELINE config 2) spread evenly over the bench locus pairs of configuration cfg2 (5 time points x 50 sequences x 10 kb, --loci-size 100),
 every pair its own kernel launch + log-sum-exp reduction. Inputs (problem + HMM tables) are resident
 in HBM for `value`; `e2e` goes through the drop-in entry point coalgpu_run_sampler with host buffers.
 """
@@ -122,7 +122,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-step", type=int, default=98304, help="histories per step PER GPU (weak scaling)")
+    ap.add_argument("--per-step", type=int, default=589824,
+                    help="histories per step PER GPU (weak scaling): 98,304 per bench locus pair, i.e. the 1e5 samples per pair of BASELINE config 2")
     ap.add_argument("--ref-per-pair", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -5,6 +5,7 @@
 #include "coal_tables.h"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,11 +31,31 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                        \
     } while (0)
 
+// Device memory comes from the stream-ordered pool with an unlimited release threshold: cudaMalloc/cudaFree
+// cost up to hundreds of milliseconds per run_sampler call on this driver (measured), the pool costs microseconds.
+cudaError_t dev_alloc(void** p, size_t bytes) {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load() & bit)) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        configured.fetch_or(bit);
+    }
+    return cudaMallocAsync(p, std::max<size_t>(bytes, 16), 0);
+}
+void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+
 template <class T>
 int upload(const std::vector<T>& v, T** out) {
     *out = nullptr;
     const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CU_OK(cudaMalloc((void**)out, bytes));
+    CU_OK(dev_alloc((void**)out, bytes));
     if (!v.empty()) CU_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -66,8 +87,8 @@ uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
 void coalgpu_destroy(coalgpu_sampler* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    for (void* p : s->allocs) cudaFree(p);
-    if (s->d_block_partials) cudaFree(s->d_block_partials);
+    for (void* p : s->allocs) dev_free(p);
+    dev_free(s->d_block_partials);
     delete s;
 }
 
@@ -198,7 +219,7 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf; P.rcp = d_rcp;
     P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
     CU_OK(cudaMemcpyToSymbol(c_w, s->tab.w.data(), sizeof(double) * kQ));
-    CU_OK(cudaMalloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));
+    CU_OK(dev_alloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));
     s->allocs.push_back(s->d_counters);
     CU_OK(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
 
@@ -285,7 +306,7 @@ int coalgpu_fp64_peak(int device, double* tflops) {
     CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     const int blocks = sm_count * 8, threads = 256, iters = 4096;
     double* d = nullptr;
-    CU_OK(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    CU_OK(dev_alloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
     cudaEvent_t e0, e1;
     CU_OK(cudaEventCreate(&e0)); CU_OK(cudaEventCreate(&e1));
     double best = 0;
@@ -299,7 +320,7 @@ int coalgpu_fp64_peak(int device, double* tflops) {
         const double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
         if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); dev_free(d);
     *tflops = best;
     return 0;
 }
@@ -314,9 +335,9 @@ int coalgpu_partials(coalgpu_sampler* s, uint64_t n, void* stream, const double*
     if (nb < 1) nb = 1;
     const size_t need = (size_t)nstat * s->G * nb * 2 * sizeof(double);
     if (need > s->block_partials_cap) {
-        if (s->d_block_partials) CU_OK(cudaFree(s->d_block_partials));
+        dev_free(s->d_block_partials);
         s->d_block_partials = nullptr; s->block_partials_cap = 0;
-        CU_OK(cudaMalloc((void**)&s->d_block_partials, need));
+        CU_OK(dev_alloc((void**)&s->d_block_partials, need));
         s->block_partials_cap = need;
     }
     dim3 grid(nb, s->G, nstat);
@@ -347,9 +368,13 @@ int coalgpu_finalize(int32_t G, int32_t T, const double* hp, coalgpu_result* r) 
 int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
     if (!problem || !result) return fail(COALGPU_EINVAL, "null argument");
     if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
+    const bool timing = std::getenv("COALGPU_TIMING") != nullptr;
+    auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = tick();
     coalgpu_sampler* s = nullptr;
     int rc = coalgpu_create(problem, Q, device, &s);
     if (rc) return rc;
+    const double t_created = tick();
     const int G = s->G, T = s->T, nstat = 3 + T;
     // chunk the batch so that the per-history weight matrix stays below ~2 GiB
     uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n_samples, (2ull << 30) / ((size_t)(G + T + 1) * 8)));
@@ -358,15 +383,15 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     std::vector<double> hp((size_t)nstat * G * 2), acc((size_t)nstat * G * 2);
     for (size_t i = 0; i < acc.size(); i += 2) { acc[i] = -INFINITY; acc[i + 1] = 0.0; }
     auto cleanup = [&]() {
-        if (d_w) cudaFree(d_w); if (d_t) cudaFree(d_t); if (d_l) cudaFree(d_l); if (d_p) cudaFree(d_p);
+        dev_free(d_w); dev_free(d_t); dev_free(d_l); dev_free(d_p);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
         coalgpu_destroy(s);
     };
 #define RS_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return fail(COALGPU_ECUDA, m); } } while (0)
-    RS_OK(cudaMalloc((void**)&d_w, chunk * G * sizeof(double)));
-    RS_OK(cudaMalloc((void**)&d_t, chunk * sizeof(double)));
-    RS_OK(cudaMalloc((void**)&d_l, chunk * T * sizeof(double)));
-    RS_OK(cudaMalloc((void**)&d_p, hp.size() * sizeof(double)));
+    RS_OK(dev_alloc((void**)&d_w, chunk * G * sizeof(double)));
+    RS_OK(dev_alloc((void**)&d_t, chunk * sizeof(double)));
+    RS_OK(dev_alloc((void**)&d_l, chunk * T * sizeof(double)));
+    RS_OK(dev_alloc((void**)&d_p, hp.size() * sizeof(double)));
     RS_OK(cudaEventCreate(&e0)); RS_OK(cudaEventCreate(&e1));
     RS_OK(cudaEventRecord(e0, 0));
     for (uint64_t first = 0; first < n_samples; first += chunk) {
@@ -385,12 +410,17 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     RS_OK(cudaEventSynchronize(e1));
     float ms = 0; RS_OK(cudaEventElapsedTime(&ms, e0, e1));
 #undef RS_OK
+    const double t_sampled = tick();
     uint64_t nev = 0, npi = 0, nov = 0;
     rc = coalgpu_counters(s, &nev, &npi, &nov);
+    const double t_cnt = tick();
     if (!rc) rc = coalgpu_finalize(G, T, acc.data(), result);
     result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
     std::string m = g_err;
+    const double t_fin = tick();
     cleanup();
+    if (timing) fprintf(stderr, "coalgpu_run_sampler: create %.2f ms, alloc+sample+reduce %.2f ms (device %.2f ms), counters %.2f ms, finalize %.2f ms, free %.2f ms\n",
+                        1e3 * (t_created - t_begin), 1e3 * (t_sampled - t_created), (double)ms, 1e3 * (t_cnt - t_sampled), 1e3 * (t_fin - t_cnt), 1e3 * (tick() - t_fin));
     if (rc) return fail(rc, m);
     if (nov) return fail(COALGPU_EOVERFLOW, "a history outgrew the type-store capacity");
     return 0;
@@ -415,7 +445,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         auto cleanup = [&]() {
             for (Job& j : jobs) {
-                if (j.d_w) cudaFree(j.d_w); if (j.d_t) cudaFree(j.d_t); if (j.d_l) cudaFree(j.d_l); if (j.d_p) cudaFree(j.d_p);
+                dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p);
                 if (j.s) coalgpu_destroy(j.s);
             }
             if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
@@ -435,10 +465,10 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             if (n_streams == 0) { for (int i = 0; i < kStreams; i++) WB_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)); n_streams = kStreams; }
             const int T = j.s->T; const size_t nstat = 3 + T;
             j.hp.resize(nstat * G * 2);
-            WB_OK(cudaMalloc((void**)&j.d_w, n_samples * G * sizeof(double)));
-            WB_OK(cudaMalloc((void**)&j.d_t, n_samples * sizeof(double)));
-            WB_OK(cudaMalloc((void**)&j.d_l, n_samples * T * sizeof(double)));
-            WB_OK(cudaMalloc((void**)&j.d_p, j.hp.size() * sizeof(double)));
+            WB_OK(dev_alloc((void**)&j.d_w, n_samples * G * sizeof(double)));
+            WB_OK(dev_alloc((void**)&j.d_t, n_samples * sizeof(double)));
+            WB_OK(dev_alloc((void**)&j.d_l, n_samples * T * sizeof(double)));
+            WB_OK(dev_alloc((void**)&j.d_p, j.hp.size() * sizeof(double)));
         }
         if (!rc) { WB_OK(cudaEventCreate(&e0)); WB_OK(cudaEventCreate(&e1)); WB_OK(cudaDeviceSynchronize()); WB_OK(cudaEventRecord(e0, streams[0])); }
         for (int k = 0; k < nw && !rc; k++) {
@@ -501,8 +531,8 @@ int coalgpu_pismc_classes(coalgpu_sampler* s, int64_t nq, const uint8_t* gamma, 
     const int64_t ncls = offs[nq];
     unsigned char* d_g = nullptr; int *d_n = nullptr, *d_t = nullptr, *d_c = nullptr, *d_a = nullptr, *d_b = nullptr; long long* d_o = nullptr; double* d_out = nullptr;
     std::vector<void*> tmp;
-    auto freeall = [&]() { for (void* p : tmp) cudaFree(p); };
-#define TMP(ptr, bytes, src) do { cudaError_t _e = cudaMalloc((void**)&ptr, std::max<size_t>(bytes, 8)); if (_e == cudaSuccess) { tmp.push_back(ptr); if (src) _e = cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); } if (_e != cudaSuccess) { freeall(); return fail(COALGPU_ECUDA, cudaGetErrorString(_e)); } } while (0)
+    auto freeall = [&]() { for (void* p : tmp) dev_free(p); };
+#define TMP(ptr, bytes, src) do { cudaError_t _e = dev_alloc((void**)&ptr, std::max<size_t>(bytes, 8)); if (_e == cudaSuccess) { tmp.push_back(ptr); if (src) _e = cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); } if (_e != cudaSuccess) { freeall(); return fail(COALGPU_ECUDA, cudaGetErrorString(_e)); } } while (0)
     TMP(d_g, (size_t)nq, gamma); TMP(d_n, (size_t)nq * 4, n_all); TMP(d_t, (size_t)nq * 4, time_idx);
     TMP(d_o, (size_t)(nq + 1) * 8, offs); TMP(d_c, (size_t)ncls * 4, counts); TMP(d_a, (size_t)ncls * 4, dA); TMP(d_b, (size_t)ncls * 4, dB);
     TMP(d_out, (size_t)nq * 8, (const void*)nullptr);

@@ -14,6 +14,9 @@ namespace {
 constexpr int GA = COALGPU_GAMMA_A, GB = COALGPU_GAMMA_B, GC = COALGPU_GAMMA_C;
 constexpr unsigned int kCntMask = 0x3fffffffu;
 constexpr int kAppended = 0x40000000;
+#ifndef COAL_PER
+#define COAL_PER 4          // intervals per forward-pass block (and the minimum per lane)
+#endif
 #ifndef COAL_SLOT_UNROLL
 #define COAL_SLOT_UNROLL 1
 #endif
@@ -385,7 +388,7 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
     if (!empty) {
 #define COAL_FWD(PER) chunk_forward<PER>(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
                                           cls, 1, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB), sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
-        cp = COAL_FWD(4);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
+        cp = COAL_FWD(COAL_PER);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
 #undef COAL_FWD
     }
     // exclusive prefixes of (pre, preB) over the lanes of the sub-group
@@ -641,7 +644,7 @@ __device__ __forceinline__ void run_group() {
                     // (Splitting the batch into several always-full passes costs more in per-pass set-up than the
                     // idle lanes cost here, profiles/r1_kernel_iterations.md.)
                     int p = 1;
-                    while (p < 4 && nqb * (p * 2) <= W) p *= 2;
+                    while (p < 16 / COAL_PER && nqb * (p * 2) <= W) p *= 2;
                     const int ql = sub / p;
                     const bool valid = ql < nqb;
                     const int qloc = valid ? ql : 0;
