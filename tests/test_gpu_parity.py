@@ -196,3 +196,82 @@ def test_batched_pairs_equal_single_calls(cuda_lib):
         np.testing.assert_array_equal(b.tmrca, one.tmrca)
         np.testing.assert_array_equal(b.lineages_remaining, one.lineages_remaining)
         assert b.n_events == one.n_events and b.n_histories == 700
+
+
+def test_pismc_sums_to_one_over_all_haplotypes(cuda_lib):
+    """Reference-free invariant at full size: the conditional sampling distribution is a
+    probability distribution. For a one-locus query it sums to 1 over all 2^L haplotypes for ANY configuration
+    (classes are keyed by the distance itself); for a two-locus query it does whenever no two stored types share
+    dA+dB with different (dA, dB) (the collapse of TypeContainer.hpp:79-86) — here a configuration of one
+    two-locus type plus one-locus types. 2^16 two-locus and 2^9 one-locus queries through the batched kernel."""
+    import itertools
+    from coalescenator_b200.problem import Problem
+    LA, LB = 9, 7
+    p = Problem(LA, LB, [0.0, 30.0], [100.0, 60.0], 1.0, 2.5e-5, 1000.0, 5e-5 * 50, [2.5e-5], [5e-5 * 50], [1000.0],
+                [[(2, 0b1010101_101010101 & ((1 << 16) - 1), 6)], [(2, 3, 6)]], name="invariant")
+    s = _sampler(p)
+    rng = np.random.default_rng(3)
+    # one-locus (A) queries against a random configuration: A types, C types (their A parts), and B lineages
+    a_types = {int(w): int(c) for w, c in zip(rng.integers(0, 1 << LA, 5), rng.integers(1, 4, 5))}
+    ca_types = {int(w): int(c) for w, c in zip(rng.integers(0, 1 << LA, 4), rng.integers(1, 3, 4))}
+    nB = 3
+    n = sum(a_types.values()) + sum(ca_types.values()) + nB
+    gam, nall, tidx, offs, cnt, dA, dB = [], [], [], [0], [], [], []
+    for h in range(1 << LA):
+        red = {}
+        for w, c in list(a_types.items()) + list(ca_types.items()):
+            d = bin(w ^ h).count("1")
+            red[d] = red.get(d, 0) + c
+        for d in sorted(red, reverse=True):
+            cnt.append(red[d]); dA.append(d); dB.append(-1)
+        cnt.append(nB); dA.append(-1); dB.append(-1)
+        gam.append(0); nall.append(n); tidx.append(1); offs.append(len(cnt))
+    pi = s.pismc_classes(gam, nall, tidx, np.array(offs), cnt, dA, dB)
+    assert abs(pi.sum() - 1.0) < 1e-12, pi.sum()
+    # two-locus queries against {one C type x3, A types, B types}: classes (dA,-1), (-1,dB), (dA,dB), no ties by construction
+    cw, cc = 0b0110010_011001101, 3
+    A2 = {0b000011111: 2}
+    B2 = {0b1110000: 1}
+    n2 = cc + sum(A2.values()) + sum(B2.values())
+    gam, nall, tidx, offs, cnt, dA, dB = [], [], [], [0], [], [], []
+    maskA = (1 << LA) - 1
+    total_skipped = 0
+    for h in range(1 << (LA + LB)):
+        ha, hb = h & maskA, h >> LA
+        keys = {}
+        for w, c in A2.items():
+            d = bin(w ^ ha).count("1"); keys.setdefault(d - 1, []).append((d, -1, c))
+        for w, c in B2.items():
+            d = bin(w ^ hb).count("1"); keys.setdefault(d - 1, []).append((-1, d, c))
+        da, db = bin((cw & maskA) ^ ha).count("1"), bin((cw >> LA) ^ hb).count("1")
+        keys.setdefault(da + db, []).append((da, db, cc))
+        if any(len(v) > 1 for v in keys.values()):
+            total_skipped += 1          # a dA+dB tie: the reference (and this build) merge the classes; not a distribution there
+            continue
+        for sm in sorted(keys, reverse=True):
+            a, b, c = keys[sm][0]
+            cnt.append(c); dA.append(a); dB.append(b)
+        gam.append(2); nall.append(n2); tidx.append(0); offs.append(len(cnt))
+    pi2 = s.pismc_classes(gam, nall, tidx, np.array(offs), cnt, dA, dB)
+    assert (pi2 > 0).all() and (pi2 < 1).all()
+    # with ties excluded the mass must be <= 1 and close to it; with this configuration ties are a minority
+    print("two-locus queries", len(pi2), "skipped (ties)", total_skipped, "mass", pi2.sum())
+    assert pi2.sum() <= 1.0 + 1e-12
+    s.close()
+
+
+def test_pismc_two_locus_sums_to_one_without_ties(cuda_lib):
+    """One stored two-locus type only: no class ties are possible, sum over all 2^(LA+LB) haplotypes == 1."""
+    from coalescenator_b200.problem import Problem
+    LA, LB = 6, 8
+    p = Problem(LA, LB, [0.0], [100.0], 1.0, 2.5e-5, 1000.0, 5e-5 * 20, [2.5e-5], [1e-3], [1000.0], [[(2, 0b10110011_010101, 4)]], name="inv2")
+    s = _sampler(p)
+    cw = 0b10110011_010101
+    maskA = (1 << LA) - 1
+    gam, nall, tidx, offs, cnt, dA, dB = [], [], [], [0], [], [], []
+    for h in range(1 << (LA + LB)):
+        cnt.append(4); dA.append(bin((cw ^ h) & maskA).count("1")); dB.append(bin((cw ^ h) >> LA).count("1"))
+        gam.append(2); nall.append(4); tidx.append(0); offs.append(len(cnt))
+    pi = s.pismc_classes(gam, nall, tidx, np.array(offs), cnt, dA, dB)
+    assert abs(pi.sum() - 1.0) < 1e-11, pi.sum()
+    s.close()
