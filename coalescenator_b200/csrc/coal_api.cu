@@ -81,7 +81,11 @@ struct coalgpu_sampler {
 extern "C" {
 
 const char* coalgpu_last_error(void) { return g_err.c_str(); }
+#ifndef COAL_NO_TMA
+const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged table rows)"; }
+#else
 const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
+#endif
 uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
 
 void coalgpu_destroy(coalgpu_sampler* s) {

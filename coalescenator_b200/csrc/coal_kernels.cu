@@ -14,6 +14,9 @@ namespace {
 constexpr int GA = COALGPU_GAMMA_A, GB = COALGPU_GAMMA_B, GC = COALGPU_GAMMA_C;
 constexpr unsigned int kCntMask = 0x3fffffffu;
 constexpr int kAppended = 0x40000000;
+#if !defined(COAL_NO_TMA) && !defined(COAL_TMA_ROWS)
+#define COAL_TMA_ROWS 1     // table rows staged into shared memory by cp.async.bulk (+5 % over ld.global.nc, profiles/r1_kernel_iterations.md)
+#endif
 #ifndef COAL_PER
 #define COAL_PER 4          // intervals per forward-pass block (and the minimum per lane)
 #endif
@@ -40,6 +43,11 @@ struct WarpMem {
     unsigned int* hist;          // [32][hstride] class histogram / class list of each query of the batch (hstride odd)
     double* sd;                  // [4]     scalar results of the out-of-line helpers
     struct HistScalars* hs;      //         per-history scalars that are touched once per event (kept out of registers)
+#ifdef COAL_TMA_ROWS
+    double* rowbuf;              // [row_doubles] table row of the event's two-locus queries, staged by cp.async.bulk
+    double* wbuf;                // [2][wlen]     wEA|wEB tails of the two rows the one-locus queries read
+    unsigned long long* mbar;    // mbarrier the bulk copies complete on
+#endif
 };
 
 // running product with the exponent split off: a sum of logs without a log per factor
@@ -61,8 +69,15 @@ struct HistScalars {
     double qsum, consts, tsum;
 };
 
+#ifdef COAL_TMA_ROWS
+__host__ __device__ inline int tma_wlen(int Ltot) { return (Ltot + 2 + 1) & ~1; }           // doubles, 16-byte multiple
+__host__ __device__ inline int tma_row_doubles(int Ltot) { return ((4 * 16 + 16 * (Ltot + 2) + (Ltot + 2)) + 1) & ~1; }
+#endif
 __host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W) {
     size_t b = 0;
+#ifdef COAL_TMA_ROWS
+    b += (size_t)tma_row_doubles(Ltot) * 8 + 2 * (size_t)tma_wlen(Ltot) * 8 + 16;   // rowbuf, wbuf, mbarrier
+#endif
     b += (size_t)kmax * 8;                 // words
     b += (size_t)pvmax * 8;                // pv
     b += (size_t)kmax * 8;                 // aux
@@ -106,6 +121,11 @@ __device__ __forceinline__ WarpMem wm() {
     unsigned char* base = smem_dyn + (size_t)(threadIdx.x / W) * sP.warp_bytes;
     const int kmax = sP.kmax, pvmax = sP.pvmax;
     WarpMem m;
+#ifdef COAL_TMA_ROWS
+    m.rowbuf = reinterpret_cast<double*>(base); base += (size_t)sP.row_doubles * 8;          // 16-byte aligned: first in the block
+    m.wbuf = reinterpret_cast<double*>(base); base += 2 * (size_t)tma_wlen(sP.Ltot) * 8;
+    m.mbar = reinterpret_cast<unsigned long long*>(base); base += 16;
+#endif
     m.words = reinterpret_cast<unsigned long long*>(base); base += (size_t)kmax * 8;
     m.pv = reinterpret_cast<double*>(base); base += (size_t)pvmax * 8;
     m.aux = reinterpret_cast<double*>(base); base += (size_t)kmax * 8;
@@ -124,6 +144,32 @@ struct HState {
 };
 
 __device__ __noinline__ double dlog(double x) { return log(x); }
+
+#ifdef COAL_TMA_ROWS
+// Table rows staged into shared memory by the TMA unit (1-D bulk copies completing on an mbarrier).
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ double tab_ld(const double* p) { return *p; }
+#else
+__device__ __forceinline__ double tab_ld(const double* p) { return __ldg(p); }
+#endif
 
 // Haplotype words in the hot loops over stored types: when LA + LB <= 32 only the low half of the 64-bit
 // word is populated and the xor / mask / popcount chain runs on 32-bit registers (half the ALU and XU work).
@@ -301,8 +347,8 @@ __device__ __forceinline__ void marginal_query(const WarpMem& m, int nslots, int
             if (excl && gj == qg && wj == qw) c -= 1;
             const int d = WO::popc((wj ^ qw) & mask);
             const double cf = (double)c;
-            num1 += cf * __ldg(wE1 + d);
-            num2 += cf * __ldg(wE2 + d);
+            num1 += cf * tab_ld(wE1 + d);
+            num2 += cf * tab_ld(wE2 + d);
             ncomp += c;
         }
     }
@@ -382,7 +428,7 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
     const int r = Grp<W>::sub() & (p - 1);
     const int per = kQd / p;
     const int i0 = r * per;
-    auto ld = [row](int off) { return __ldg(row + off); };
+    auto ld = [row](int off) { return tab_ld(row + off); };
     ChunkPartial cp = {0, 0, 0, 0, 0, 0};
     const double inv_n = __ldg(sP.rcp + tot.n);
     if (!empty) {
@@ -434,6 +480,11 @@ __device__ __forceinline__ void run_group() {
     bool have = false;
     unsigned long long h = 0;
     PhiloxStream rng; rng.init(0, 0);
+#ifdef COAL_TMA_ROWS
+    unsigned int tma_phase = 0;
+    if (sub == 0) mbar_init(m.mbar);
+    G::sync();
+#endif
     HState s; s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
     bool tracing = false, injecting = false, post = true;
     unsigned int nev = 0, npi = 0, ncq = 0;
@@ -549,6 +600,22 @@ __device__ __forceinline__ void run_group() {
                 const unsigned int xcg = m.cg[sx], xxc = m.xc[sx];
                 const int xg = (int)(xcg >> 30);
                 const unsigned int xcount = xcg & kCntMask;
+#ifdef COAL_TMA_ROWS
+                // Stage what this event reads from the tables — the full row of its two-locus queries (n-1 lineages
+                // for a C lineage, n-2 for a one-locus lineage) and the wEA|wEB tails of the two rows of its
+                // one-locus queries — with three TMA bulk copies; they overlap the count / remove / partner-list work.
+                if (sub == 0) {
+                    const bool c_chosen = (xg == GC);
+                    const double* g_m1 = row_ptr(tset, n - 1);
+                    const double* g_alt = row_ptr(tset, c_chosen ? n : n - 2);
+                    const unsigned int rb = (unsigned int)sP.row_doubles * 8u, wb = (unsigned int)(sP.row_doubles - sP.off_wEA) * 8u;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect(m.mbar, rb + 2u * wb);
+                    bulk_g2s(m.rowbuf, c_chosen ? g_m1 : g_alt, rb, m.mbar);
+                    bulk_g2s(m.wbuf, g_m1 + sP.off_wEA, wb, m.mbar);
+                    bulk_g2s(m.wbuf + tma_wlen(Ltot), g_alt + sP.off_wEA, wb, m.mbar);
+                }
+#endif
                 const unsigned long long xa = xw & sP.maskA, xb = xw & sP.maskB;
                 unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
                 if (xg == GC) {
@@ -573,8 +640,15 @@ __device__ __forceinline__ void run_group() {
                 const int Lx = isC ? Ltot : (isA ? LA : LB), offb = (xg == GB) ? LA : 0;
                 const int pg = isA ? GB : GA;
                 const unsigned int own = isA ? Ai : Bj, ownC = isA ? Ci : Cj;
+#ifdef COAL_TMA_ROWS
+                // pointers laid out so that (ptr + off_wEA/off_wEB) lands in the staged tails
+                const int wlen = tma_wlen(Ltot);
+                const double* row_m1 = m.wbuf - sP.off_wEA;
+                const double* row_alt = m.wbuf + wlen - sP.off_wEA;
+#else
                 const double* row_m1 = row_ptr(tset, n - 1);
                 const double* row_alt = row_ptr(tset, isC ? n : n - 2);      // second row of the one-locus queries
+#endif
                 const unsigned int nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
 
                 // partner list = stored types of the other one-locus class, slot order (:300 / :377)
@@ -595,6 +669,9 @@ __device__ __forceinline__ void run_group() {
                 //  C chosen: lane 0 = A part, lane 1 = B part, rows n-1 and n (:198-238 with :120-132)
                 //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
                 //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
+#ifdef COAL_TMA_ROWS
+                mbar_wait(m.mbar, tma_phase); tma_phase ^= 1u;
+#endif
                 const int nm = isC ? 2 : 1 + Lx + np;
                 double pi0 = 0.0, mA1 = 0.0, mA2 = 0.0, mB1 = 0.0, mB2 = 0.0;
 #pragma unroll 1
@@ -631,7 +708,11 @@ __device__ __forceinline__ void run_group() {
                 //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
                 //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
                 const int nq = isC ? Ltot + 1 : np;
+#ifdef COAL_TMA_ROWS
+                const double* crow = m.rowbuf;
+#else
                 const double* crow = isC ? row_m1 : row_alt;
+#endif
                 const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
                 const int hstride = (Ltot + 2) | 1;
 #pragma unroll 1
