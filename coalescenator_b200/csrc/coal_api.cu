@@ -517,8 +517,8 @@ int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* 
     if (y) std::memcpy(y, yy, sizeof(double) * kQ);
     if (z) for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
         z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? s->tab.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
-    if (EA) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LA; d++) EA[i * (s->LA + 1) + d] = row[lay.off_EA + d * kQ + i];
-    if (EB) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LB; d++) EB[i * (s->LB + 1) + d] = row[lay.off_EB + d * kQ + i];
+    if (EA) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LA; d++) EA[i * (s->LA + 1) + d] = row[lay.off_EA + d * kEStride + i];
+    if (EB) for (int i = 0; i < kQ; i++) for (int d = 0; d <= s->LB; d++) EB[i * (s->LB + 1) + d] = row[lay.off_EB + d * kEStride + i];
     return 0;
 }
 

@@ -71,7 +71,7 @@ struct HistScalars {
 
 #ifdef COAL_TMA_ROWS
 __host__ __device__ inline int tma_wlen(int Ltot) { return (Ltot + 2 + 1) & ~1; }           // doubles, 16-byte multiple
-__host__ __device__ inline int tma_row_doubles(int Ltot) { return ((4 * 16 + 16 * (Ltot + 2) + (Ltot + 2)) + 1) & ~1; }
+__host__ __device__ inline int tma_row_doubles(int Ltot) { return ((4 * 16 + kEStride * (Ltot + 2) + (Ltot + 2)) + 1) & ~1; }
 #endif
 __host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W) {
     size_t b = 0;

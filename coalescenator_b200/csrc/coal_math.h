@@ -24,6 +24,13 @@
 
 namespace coalgpu {
 
+// Stride (in doubles) between the emission-table rows of consecutive distances (must be even: rows are copied with
+// 16-byte granularity). Padding to 18 removes shared-memory bank conflicts but was 0.7 % slower (larger copies).
+#ifndef COAL_ESTRIDE
+#define COAL_ESTRIDE 16
+#endif
+constexpr int kEStride = COAL_ESTRIDE;
+
 // packed class: count | (dA+1) << 16 | (dB+1) << 24   (dA/dB = -1 when the locus is not ancestral)
 COAL_HD uint32_t pack_class(uint32_t count, int dA, int dB) { return count | ((uint32_t)(dA + 1) << 16) | ((uint32_t)(dB + 1) << 24); }
 
@@ -45,7 +52,7 @@ struct ClassTotals {
 // Forward sweep over intervals [i0, i1) for one query, in blocks of PER intervals (PER divides i1 - i0).
 // The loop nest is class-outer / interval-inner so that the class word is decoded once per block and the
 // PER table reads of a class are independent loads. Emission tables are stored distance-major
-// (E[d*16 + i], see coal_tables.h), i.e. the intervals of one class are contiguous.
+// (E[d*kEStride + i], see coal_tables.h), i.e. the intervals of one class are contiguous.
 // `cls` is read with stride `cstride` (32 on the device: one shared-memory column per query).
 template <int PER, class LoadF>
 COAL_HD ChunkPartial chunk_forward(LoadF ld, const double* w, int off_yw, int off_zlow, int off_g, int off_zdiag,
@@ -62,7 +69,7 @@ COAL_HD ChunkPartial chunk_forward(LoadF ld, const double* w, int off_yw, int of
             const uint32_t v = cls[k * cstride];
             const double c = (double)(v & 0xffffu);
             const int dA = (int)((v >> 16) & 0xffu) - 1, dB = (int)(v >> 24) - 1;
-            const int ea_base = off_EA + (dA < 0 ? 0 : dA) * 16 + ib, eb_base = off_EB + (dB < 0 ? 0 : dB) * 16 + ib;
+            const int ea_base = off_EA + (dA < 0 ? 0 : dA) * kEStride + ib, eb_base = off_EB + (dB < 0 ? 0 : dB) * kEStride + ib;
             const double ca0 = dA >= 0 ? c : 0.0, cb0 = dB >= 0 ? c : 0.0;
 #pragma unroll
             for (int ii = 0; ii < PER; ii++) {

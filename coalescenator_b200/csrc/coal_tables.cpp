@@ -81,7 +81,7 @@ void emission_table(const double* t, const double* w, const std::vector<double>&
             }
             e /= (w[i - 1] * two_L);
             e = std::max(e, std::numeric_limits<double>::epsilon());
-            E[(size_t)j * kQ + (i - 1)] = e;   // distance-major: the intervals of one distance are contiguous
+            E[(size_t)j * kEStride + (i - 1)] = e;   // distance-major: the intervals of one distance are contiguous
         }
     }
 }
@@ -126,8 +126,8 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
             for (int i = 0; i < kQ; i++) row[lay.off_yw + i] = y[i] * w[i];
             emission_table(t, w, bin, bw, thetas[rep[s]], (unsigned)n, LA, row + lay.off_EA);
             emission_table(t, w, bin, bw, thetas[rep[s]], (unsigned)n, LB, row + lay.off_EB);
-            for (int d = 0; d <= LA; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EA + d * kQ + i]; row[lay.off_wEA + d] = a; }
-            for (int d = 0; d <= LB; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EB + d * kQ + i]; row[lay.off_wEB + d] = a; }
+            for (int d = 0; d <= LA; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EA + d * kEStride + i]; row[lay.off_wEA + d] = a; }
+            for (int d = 0; d <= LB; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EB + d * kEStride + i]; row[lay.off_wEB + d] = a; }
         }
     };
     const int total = out.n_sets * n_max;

@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "coal_math.h"
+
 namespace coalgpu {
 
 constexpr int kQ = 16;   // quadrature intervals (main.cpp:103 hard-codes 16)
@@ -15,12 +17,12 @@ constexpr int kQ = 16;   // quadrature intervals (main.cpp:103 hard-codes 16)
 struct TableLayout {
     int LA = 0, LB = 0;
     int off_yw = 0, off_zlow = kQ, off_g = 2 * kQ, off_zdiag = 3 * kQ;
-    int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;   // EA: [(LA+1)][kQ], EB: [(LB+1)][kQ] (distance-major)
+    int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;   // EA: [(LA+1)][kEStride], EB: [(LB+1)][kEStride] (distance-major, padded)
     int row_doubles = 0;   // multiple of 2 (16-byte rows for bulk copies)
     void init(int la, int lb) {
         LA = la; LB = lb;
-        off_EB = off_EA + kQ * (LA + 1);
-        off_wEA = off_EB + kQ * (LB + 1);
+        off_EB = off_EA + kEStride * (LA + 1);
+        off_wEA = off_EB + kEStride * (LB + 1);
         off_wEB = off_wEA + (LA + 1);
         row_doubles = off_wEB + (LB + 1);
         row_doubles = (row_doubles + 1) & ~1;

@@ -32,8 +32,8 @@ int hs_tables(void* hp, int n_all, int time_idx, double* w, double* y, double* z
     std::memcpy(y, t.y.data() + ((size_t)set * t.n_max + (n_all - 1)) * kQ, sizeof(double) * kQ);
     for (int i = 0; i < kQ; i++) for (int j = 0; j < kQ; j++)
         z[i * kQ + j] = (i > j) ? row[lay.off_zlow + j] : (i < j ? t.w[j] * row[lay.off_g + i] : row[lay.off_zdiag + i]);
-    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LA; d++) EA[i * (lay.LA + 1) + d] = row[lay.off_EA + d * kQ + i];
-    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LB; d++) EB[i * (lay.LB + 1) + d] = row[lay.off_EB + d * kQ + i];
+    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LA; d++) EA[i * (lay.LA + 1) + d] = row[lay.off_EA + d * kEStride + i];
+    for (int i = 0; i < kQ; i++) for (int d = 0; d <= lay.LB; d++) EB[i * (lay.LB + 1) + d] = row[lay.off_EB + d * kEStride + i];
     return t.n_sets;
 }
 
