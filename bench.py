@@ -90,7 +90,7 @@ def run_reference_arm(args, rank, world):
     probs = bench_problems()
     cores = os.cpu_count() or 1
     kind = "reference" if O.ref_binary() else "port"
-    per_pair = max(cores, args.ref_per_pair)
+    per_pair = max(8 * cores, args.ref_per_pair)      # >= 8 histories per host thread, so table set-up per thread does not dominate
     def step():
         n = 0
         for p in probs:
@@ -283,7 +283,7 @@ def main():
         cores = os.cpu_count() or 1
         kind = "reference" if O.ref_binary() else "port"
         n_cpu, t_cpu = 0, 0.0
-        per = max(cores, 16)
+        per = 8 * cores                                  # 8 histories per host thread
         for p in probs:
             t0 = time.perf_counter()
             if kind == "reference":

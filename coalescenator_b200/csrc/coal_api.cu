@@ -71,7 +71,7 @@ struct coalgpu_sampler {
     unsigned long long* d_counters = nullptr;
     double* d_block_partials = nullptr;
     size_t block_partials_cap = 0;
-    int warp_bytes = 0, warps_per_cta = 4, grid = 0, group = 32;   // group = lanes per history (16 or 32)
+    int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history (16 or 32)
     size_t smem_bytes = 0;
     unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
     // K2 scratch smem

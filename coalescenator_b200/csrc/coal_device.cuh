@@ -1,14 +1,15 @@
 // Device-side data layout and kernels of the importance-sampling likelihood path (sm_100a).
 //
-// One WARP draws one coalescent history (ProposalEngine::calculateLikelihood,
-// /root/reference/src/ProposalEngine.cpp:643-861). The ancestral configuration (TypeContainer,
-// TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed haplotypes; the
-// candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:
+// One GROUP of W lanes (W = 16: two histories per warp) draws one coalescent history
+// (ProposalEngine::calculateLikelihood, /root/reference/src/ProposalEngine.cpp:643-861). The ancestral
+// configuration (TypeContainer, TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed
+// haplotypes; the candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:
 //  * marginal (one-locus) conditional sampling probabilities collapse to a dot product of a distance
 //    histogram with a precomputed weight vector (ConditionalSamplingHMM.cpp:332-370),
 //  * two-locus ones run the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) with the
-//    interval axis split over a power-of-two lane group and the structured transition matrix folded
-//    into running prefix sums exchanged by warp shuffles.
+//    interval axis split over a power-of-two lane sub-group and the structured transition matrix folded
+//    into running prefix sums exchanged by warp shuffles,
+//  * the table rows an event reads are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier).
 // fp64 throughout; no tensor cores (the recursion is a diagonal + rank-1 update, not a contraction).
 #pragma once
 #include <cstdint>
