@@ -275,3 +275,39 @@ def test_pismc_two_locus_sums_to_one_without_ties(cuda_lib):
     pi = s.pismc_classes(gam, nall, tidx, np.array(offs), cnt, dA, dB)
     assert abs(pi.sum() - 1.0) < 1e-11, pi.sum()
     s.close()
+
+
+def _random_problem(rng, k):
+    from coalescenator_b200.problem import Problem
+    LA = int(rng.integers(1, 9)); LB = int(rng.integers(1, 9))
+    if k % 7 == 3:
+        LA, LB = int(rng.integers(14, 20)), int(rng.integers(14, 19))       # > 32 sites: wide words, 32 lanes per history
+    T = int(rng.integers(1, 5))
+    times = np.concatenate([[0.0], np.cumsum(rng.uniform(5.0, 60.0, T - 1))]).tolist()
+    viral = rng.choice([40.0, 100.0, 250.0], size=T).tolist() if k % 2 else [100.0] * T
+    n_founders = int(rng.integers(2, 6))
+    fa = rng.integers(0, 1 << LA, n_founders); fb = rng.integers(0, 1 << LB, n_founders)
+    types = []
+    for t in range(T):
+        cnt = {}
+        for _ in range(int(rng.integers(1 if t else 2, 9))):
+            f = int(rng.integers(0, n_founders))
+            a = int(fa[f]) ^ (int(rng.integers(0, 1 << LA)) if rng.random() < 0.15 else 0)
+            b = int(fb[f]) ^ (int(rng.integers(0, 1 << LB)) if rng.random() < 0.15 else 0)
+            u = rng.random()
+            key = (2, a | (b << LA)) if u < 0.6 else ((0, a) if u < 0.8 else (1, b << LA))
+            cnt[key] = cnt.get(key, 0) + 1
+        types.append([(g, w, c) for (g, w), c in cnt.items()])
+    scale = float(rng.integers(1, 200))
+    grid = ([1e-5, 4e-5], [2e-5 * scale], [500.0, 2000.0]) if k % 3 == 0 else ([2.5e-5], [5e-5 * scale], [1000.0])
+    return Problem(LA, LB, times, viral, float(rng.choice([1.0, 1.7])), 2.5e-5, 1000.0, 5e-5 * scale, grid[0], grid[1], grid[2], types, name="fuzz%d" % k)
+
+
+def test_random_problems_differential(oracle, cuda_lib):
+    """Differential fuzz: random small problems (1-4 sampling times, A/B/C initial types, unequal viral loads,
+    1-18 sites per locus incl. LA+LB > 32, 1- and 4-point grids); events bit-exact, weights 1e-9 vs the oracle."""
+    rng = np.random.default_rng(2026)
+    for k in range(24):
+        p = _random_problem(rng, k)
+        n = 6 if p.LA + p.LB > 32 else 24
+        _compare_histories(oracle, p, n, seed=1000 + k, max_events=1 << 15)
