@@ -227,18 +227,18 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     s->allocs.push_back(s->d_counters);
     CU_OK(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
 
-    // launch geometry: persistent CTAs of 128 threads = 128/W groups of W lanes, one history per group.
+    // launch geometry: persistent CTAs of kCtaThreads threads = kCtaThreads/W groups of W lanes, one history per group.
     // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
     // The width that keeps more histories in flight per SM wins (shared memory per group grows with the
     // lineage bound: 200 sequences need ~15 KB per group and W = 16 would leave one CTA per SM).
     auto geometry = [&](int W, size_t& smem, int& occ) -> int {
         const size_t gb = history_group_bytes(P.kmax, P.pvmax, P.Ltot, W);
-        smem = gb * (128 / W); occ = 0;
+        smem = gb * (kCtaThreads / W); occ = 0;
         if (smem > 227 * 1024) return -1;
         const void* fn = (const void*)history_kernel_select(W, P.Ltot <= 32);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem) != cudaSuccess) return -1;
-        return occ * (128 / W);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem) != cudaSuccess) return -1;
+        return occ * (kCtaThreads / W);
     };
     size_t smem16 = 0, smem32 = 0; int occ16 = 0, occ32 = 0;
     const int g16 = (P.Ltot + 1 <= 16) ? geometry(16, smem16, occ16) : -1;
@@ -269,14 +269,14 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
     a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
     a.counters = s->d_counters;
-    const int groups_per_cta = 128 / s->group;
+    const int groups_per_cta = kCtaThreads / s->group;
     int grid = s->grid;
     const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
     // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
     history_kernel_fn kfn = history_kernel_select(s->group, s->P.Ltot <= 32);
     CU_OK(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    kfn<<<grid, 128, s->smem_bytes, st>>>(s->P, a);
+    kfn<<<grid, kCtaThreads, s->smem_bytes, st>>>(s->P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
     return 0;

@@ -866,8 +866,16 @@ __device__ __forceinline__ void run_group() {
 #ifndef COAL_MIN_CTAS
 #define COAL_MIN_CTAS 3
 #endif
+#ifndef COAL_CTA_THREADS
+#define COAL_CTA_THREADS 128
+#endif
+constexpr int kCtaThreads = COAL_CTA_THREADS;   // threads per CTA of the history kernel
 template <int W, bool N32>
-__global__ void __launch_bounds__(128, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
+#ifdef COAL_MAXNREG
+__global__ void __maxnreg__(COAL_MAXNREG) history_kernel(const DevProblem P, const SampleArgs A) {
+#else
+__global__ void __launch_bounds__(COAL_CTA_THREADS, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
+#endif
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
     run_group<W, N32>();

@@ -177,49 +177,67 @@ int main(int argc, char** argv) {
             pairwise << "locus1\tlocus2\tmu\trho\tlambda\tloglikelihood\ttmrca\tlineages_remaining\tloglikelihoodSq" << (o.ess ? "\tess" : "") << "\n";   // :240
         }
 
+        // Sub-samples of all eligible pairs first (main.cpp:254-279), then ONE batched call: the pairs run
+        // concurrently on the GPU instead of one after another (coalgpu_run_sampler_batch), rows are written in
+        // the reference's order afterwards.
+        struct Job { PairProblem sp; std::vector<double> rho_scaled; double drho; std::string l1, l2;
+                     std::vector<double> like, likesq, tm, lin, ess; };
+        std::vector<Job> jobs(pairs.size());
         size_t remaining = pairs.size();
-        for (const Pair& pr : pairs) {
-            PairProblem sp = aln.sub_sample(loci[pr.i], loci[pr.j]);                  // :254
-            std::vector<double> rho_scaled = rho_list;
-            for (double& r : rho_scaled) r *= pr.dist + 1;                            // :260-271
-            const double drho = o.rho_driving * (pr.dist + 1);
+        for (size_t q = 0; q < pairs.size(); q++) {
+            const Pair& pr = pairs[q];
+            Job& j = jobs[q];
+            j.sp = aln.sub_sample(loci[pr.i], loci[pr.j]);                            // :254
+            j.rho_scaled = rho_list;
+            for (double& r : j.rho_scaled) r *= pr.dist + 1;                          // :260-271
+            j.drho = o.rho_driving * (pr.dist + 1);
             remaining--;
             std::ostringstream l1, l2;
             l1 << "(" << orig[pr.i].first << ", " << orig[pr.i].second << ")";
             l2 << "(" << orig[pr.j].first << ", " << orig[pr.j].second << ")";
-            std::cout << "[" << now() << "] Working on locus " << l1.str() << " and " << l2.str() << " having " << sp.nA << ", " << sp.nB << " and " << sp.nC
-                      << " sequences with ancentry A, B and C respectively taken at " << sp.times.size() << " different time points. " << remaining
+            j.l1 = l1.str(); j.l2 = l2.str();
+            std::cout << "[" << now() << "] Working on locus " << j.l1 << " and " << j.l2 << " having " << j.sp.nA << ", " << j.sp.nB << " and " << j.sp.nC
+                      << " sequences with ancentry A, B and C respectively taken at " << j.sp.times.size() << " different time points. " << remaining
                       << " remaining pairwise combinations." << std::endl;
             if (!o.dump_dir.empty()) {
                 std::ostringstream path;
                 path << o.dump_dir << "/pair_" << orig[pr.i].first << "-" << orig[pr.i].second << "_" << orig[pr.j].first << "-" << orig[pr.j].second << ".coalprob";
-                dump_problem(path.str(), sp, o.generation_time, o.mutation_driving, o.scale_driving, drho, mu_list, rho_scaled, lambda_list);
-                continue;
+                dump_problem(path.str(), j.sp, o.generation_time, o.mutation_driving, o.scale_driving, j.drho, mu_list, j.rho_scaled, lambda_list);
             }
-
-            coalgpu_problem p = {};
-            const int T = (int)sp.times.size();
-            p.T = T; p.LA = (int)sp.LA; p.LB = (int)sp.LB;
-            p.times = sp.times.data(); p.viral = sp.viral.data(); p.tau = o.generation_time;
-            p.driving_mu = o.mutation_driving; p.driving_lambda = o.scale_driving; p.driving_rho = drho;
-            p.n_mu = (int)nmu; p.n_rho = (int)nrho; p.n_lambda = (int)nlam;
-            p.mu = mu_list.data(); p.rho = rho_scaled.data(); p.lambda = lambda_list.data();
-            p.type_offsets = sp.type_offsets.data(); p.type_gamma = sp.type_gamma.data();
-            p.type_words = sp.type_words.data(); p.type_counts = sp.type_counts.data();
-            std::vector<double> like(G), likesq(G), tm(G), lin(G * T), ess(G);
-            coalgpu_result r = {like.data(), likesq.data(), tm.data(), lin.data(), ess.data(), 0, 0, 0, 0.0};
-            const int rc = coalgpu_run_sampler(&p, o.mc_samples, 16, o.seed, o.device, &r);   // replaces :281-283
+        }
+        if (o.dump_dir.empty()) {
+            std::vector<coalgpu_problem> probs(jobs.size());
+            std::vector<coalgpu_result> results(jobs.size());
+            for (size_t q = 0; q < jobs.size(); q++) {
+                Job& j = jobs[q];
+                const int T = (int)j.sp.times.size();
+                coalgpu_problem p = {};
+                p.T = T; p.LA = (int)j.sp.LA; p.LB = (int)j.sp.LB;
+                p.times = j.sp.times.data(); p.viral = j.sp.viral.data(); p.tau = o.generation_time;
+                p.driving_mu = o.mutation_driving; p.driving_lambda = o.scale_driving; p.driving_rho = j.drho;
+                p.n_mu = (int)nmu; p.n_rho = (int)nrho; p.n_lambda = (int)nlam;
+                p.mu = mu_list.data(); p.rho = j.rho_scaled.data(); p.lambda = lambda_list.data();
+                p.type_offsets = j.sp.type_offsets.data(); p.type_gamma = j.sp.type_gamma.data();
+                p.type_words = j.sp.type_words.data(); p.type_counts = j.sp.type_counts.data();
+                probs[q] = p;
+                j.like.resize(G); j.likesq.resize(G); j.tm.resize(G); j.lin.resize(G * T); j.ess.resize(G);
+                results[q] = coalgpu_result{j.like.data(), j.likesq.data(), j.tm.data(), j.lin.data(), j.ess.data(), 0, 0, 0, 0.0};
+            }
+            const int rc = coalgpu_run_sampler_batch((int)probs.size(), probs.data(), o.mc_samples, 16, o.seed, o.device, results.data());   // replaces :281-283
             if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
-
-            size_t g = 0;
-            for (size_t i = 0; i < nmu; i++) for (size_t j = 0; j < nrho; j++) for (size_t k = 0; k < nlam; k++, g++) {   // :285-310
-                composite[g] += like[g];
-                mean_tmrca[g] = log_addition(mean_tmrca[g], tm[g]);
-                pairwise << l1.str() << "\t" << l2.str() << "\t" << mu_list[i] << "\t" << rho_list[j] << "\t" << lambda_list[k] << "\t" << like[g] << "\t" << std::exp(tm[g]) << "\t";
-                for (int l = 0; l < T; l++) pairwise << (l ? "," : "") << std::exp(lin[(size_t)l * G + g]);
-                pairwise << "\t" << likesq[g];
-                if (o.ess) pairwise << "\t" << ess[g];
-                pairwise << "\n";
+            for (size_t q = 0; q < jobs.size(); q++) {
+                const Job& j = jobs[q];
+                const int T = (int)j.sp.times.size();
+                size_t g = 0;
+                for (size_t i = 0; i < nmu; i++) for (size_t jj = 0; jj < nrho; jj++) for (size_t k = 0; k < nlam; k++, g++) {   // :285-310
+                    composite[g] += j.like[g];
+                    mean_tmrca[g] = log_addition(mean_tmrca[g], j.tm[g]);
+                    pairwise << j.l1 << "\t" << j.l2 << "\t" << mu_list[i] << "\t" << rho_list[jj] << "\t" << lambda_list[k] << "\t" << j.like[g] << "\t" << std::exp(j.tm[g]) << "\t";
+                    for (int l = 0; l < T; l++) pairwise << (l ? "," : "") << std::exp(j.lin[(size_t)l * G + g]);
+                    pairwise << "\t" << j.likesq[g];
+                    if (o.ess) pairwise << "\t" << j.ess[g];
+                    pairwise << "\n";
+                }
             }
         }
         if (!o.dump_dir.empty()) { std::cout << "[" << now() << "] Wrote " << pairs.size() << " problem file(s) to " << o.dump_dir << std::endl; return 0; }
