@@ -99,7 +99,7 @@ void coalgpu_destroy(coalgpu_sampler* s) {
 int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
     if (!p || !out) return fail(COALGPU_EINVAL, "null argument");
     *out = nullptr;
-    if (Q != 16) return fail(COALGPU_EINVAL, "only 16 quadrature points are supported (main.cpp:103 hard-codes 16)");
+    if (Q != 4 && Q != 8 && Q != 16) return fail(COALGPU_EINVAL, "quadrature_points must be 4, 8 or 16 (ConditionalSamplingHMM.cpp:39-58)");
     if (p->T < 1 || p->LA < 1 || p->LB < 1 || p->LA + p->LB > 64) return fail(COALGPU_EINVAL, "need T >= 1, LA, LB >= 1 and LA + LB <= 64");
     if (p->n_mu < 1 || p->n_rho < 1 || p->n_lambda < 1) return fail(COALGPU_EINVAL, "empty target grid");
     if (!(p->tau > 0) || !(p->driving_mu > 0) || !(p->driving_lambda > 0) || !(p->driving_rho > 0)) return fail(COALGPU_EINVAL, "driving values and tau must be positive (main.cpp:147-150)");

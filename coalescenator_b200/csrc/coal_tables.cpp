@@ -8,7 +8,9 @@
 namespace coalgpu {
 namespace {
 
-// Abramowitz & Stegun table 25.9 nodes as the reference lists them (ConditionalSamplingHMM.cpp:51)
+// Abramowitz & Stegun table 25.9 nodes as the reference lists them (ConditionalSamplingHMM.cpp:41,46,51)
+const double kNodes4[5] = {0, 0.415774556783, 2.294280360279, 6.289945082937, 1E+300};
+const double kNodes8[9] = {0, 0.193043676560, 1.026664895339, 2.567876744951, 4.900353084526, 8.182153444563, 12.7344180291798, 19.3957278622, 1E+300};
 const double kNodes16[kQ + 1] = {0, 0.093307812017, 0.492691740302, 1.215595412071, 2.269949526204,
     3.667622721751, 5.425336627414, 7.565916226613, 10.120228568019, 13.130282482176, 16.6544077083,
     20.7764788994, 25.6238942267, 31.407519169754, 38.530683306486, 48.026085572686, 1E+300};
@@ -29,10 +31,10 @@ bool nearly_equal(double a, double b) {   // Utils.hpp:206-209
 }
 
 // y[i], and z in structured form, ConditionalSamplingHMM.cpp:85-182
-void transition_row(const double* t, const double* w, double r, unsigned n, double* y, double* zlow, double* g, double* zdiag) {
+void transition_row(int Q, const double* t, const double* w, double r, unsigned n, double* y, double* zlow, double* g, double* zdiag) {
     const double c1 = n / (r + n);
     if (nearly_equal(r, n)) {
-        for (int i = 0; i < kQ; i++) {
+        for (int i = 0; i < Q; i++) {
             y[i] = c1 / w[i] * (std::exp(-t[i] / c1) - std::exp(-t[i + 1] / c1));
             const double core = (w[i] + (t[i] * std::exp(-t[i]) - t[i + 1] * std::exp(-t[i + 1])));
             zlow[i] = core;                 // z(i',i) for i' > i  (:114)
@@ -45,7 +47,7 @@ void transition_row(const double* t, const double* w, double r, unsigned n, doub
     } else {
         const double c2 = r / (r - n);
         const double c3 = n / r;
-        for (int i = 0; i < kQ; i++) {
+        for (int i = 0; i < Q; i++) {
             y[i] = c1 / w[i] * (std::exp(-t[i] / c1) - std::exp(-t[i + 1] / c1));
             const double inner = (w[i] - c3 * (std::exp(-t[i] / c3) - std::exp(-t[i + 1] / c3)));
             zlow[i] = c2 * inner;           // :156
@@ -60,15 +62,15 @@ void transition_row(const double* t, const double* w, double r, unsigned n, doub
 
 // E[i][d], ConditionalSamplingHMM.cpp:184-226. The exponentials depend on (k+l) only, so they are
 // evaluated once per (k+l, i) — same arguments, hence the same values, as the reference's inner loop.
-void emission_table(const double* t, const double* w, const std::vector<double>& bin, int bw, double theta,
-                    unsigned n, int L, double* E /*[kQ][L+1]*/) {
+void emission_table(int Q, const double* t, const double* w, const std::vector<double>& bin, int bw, double theta,
+                    unsigned n, int L, double* E /*[L+1][kEStride]*/) {
     std::vector<double> rate(L + 1), ex((size_t)(L + 1) * (kQ + 1));
     for (int m = 0; m <= L; m++) {
         rate[m] = (2 * theta * (unsigned)m / n) + 1;
-        for (int i = 0; i <= kQ; i++) ex[(size_t)m * (kQ + 1) + i] = std::exp(-rate[m] * t[i]);
+        for (int i = 0; i <= Q; i++) ex[(size_t)m * (kQ + 1) + i] = std::exp(-rate[m] * t[i]);
     }
     const double two_L = std::pow(2, (double)L);
-    for (int i = 1; i <= kQ; i++) {
+    for (int i = 1; i <= Q; i++) {
         for (int j = 0; j <= L; j++) {
             double e = 0;
             for (int l = 0; l <= j; l++) {
@@ -90,12 +92,17 @@ void emission_table(const double* t, const double* w, const std::vector<double>&
 
 bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
                   const std::vector<double>& r_rates, HostTables& out) {
-    if (Q != kQ || LA < 1 || LB < 1 || n_max < 1 || thetas.size() != r_rates.size()) return false;
+    if ((Q != 4 && Q != 8 && Q != kQ) || LA < 1 || LB < 1 || n_max < 1 || thetas.size() != r_rates.size()) return false;
     out.lay.init(LA, LB);
     out.n_max = n_max;
-    out.quad.assign(kNodes16, kNodes16 + kQ + 1);
-    out.w.resize(kQ);
-    for (int i = 1; i <= kQ; i++) out.w[i - 1] = std::exp(-out.quad[i - 1]) - std::exp(-out.quad[i]);   // :63-71
+    // Q = 4 or 8 (ConditionalSamplingHMM.cpp:39-47): the kernels always sweep 16 intervals; intervals beyond Q carry
+    // weight 0 and all-zero table entries, so they contribute nothing.
+    out.Q = Q;
+    const double* nodes = Q == 4 ? kNodes4 : (Q == 8 ? kNodes8 : kNodes16);
+    out.quad.assign(kQ + 1, 1E+300);
+    for (int i = 0; i <= Q; i++) out.quad[i] = nodes[i];
+    out.w.assign(kQ, 0.0);
+    for (int i = 1; i <= Q; i++) out.w[i - 1] = std::exp(-out.quad[i - 1]) - std::exp(-out.quad[i]);   // :63-71
 
     // epochs with identical scaled rates share one table set
     const int T = (int)thetas.size();
@@ -122,10 +129,10 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
             const int s = idx / n_max, n = idx % n_max + 1;
             double* row = out.rows.data() + (size_t)idx * lay.row_doubles;
             double* y = out.y.data() + (size_t)idx * kQ;
-            transition_row(t, w, r_rates[rep[s]], (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
+            transition_row(Q, t, w, r_rates[rep[s]], (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
             for (int i = 0; i < kQ; i++) row[lay.off_yw + i] = y[i] * w[i];
-            emission_table(t, w, bin, bw, thetas[rep[s]], (unsigned)n, LA, row + lay.off_EA);
-            emission_table(t, w, bin, bw, thetas[rep[s]], (unsigned)n, LB, row + lay.off_EB);
+            emission_table(Q, t, w, bin, bw, thetas[rep[s]], (unsigned)n, LA, row + lay.off_EA);
+            emission_table(Q, t, w, bin, bw, thetas[rep[s]], (unsigned)n, LB, row + lay.off_EB);
             for (int d = 0; d <= LA; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EA + d * kEStride + i]; row[lay.off_wEA + d] = a; }
             for (int d = 0; d <= LB; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EB + d * kEStride + i]; row[lay.off_wEB + d] = a; }
         }

@@ -12,7 +12,7 @@
 
 namespace coalgpu {
 
-constexpr int kQ = 16;   // quadrature intervals (main.cpp:103 hard-codes 16)
+constexpr int kQ = 16;   // interval slots the kernels sweep (main.cpp:103 hard-codes 16; 4 and 8 are padded)
 
 struct TableLayout {
     int LA = 0, LB = 0;
@@ -31,6 +31,7 @@ struct TableLayout {
 
 struct HostTables {
     TableLayout lay;
+    int Q = kQ;                    // quadrature intervals in use (4, 8 or 16); tables are padded to kQ
     int n_max = 0;                 // rows for n_all = 1..n_max
     int n_sets = 0;                // distinct (theta, r) epochs
     std::vector<int> set_of_epoch; // [T]

@@ -98,7 +98,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
 
 /* ---- staged API --------------------------------------------------------------------------------*/
 /* Build the HMM tables on the host (ConditionalSamplingHMM.cpp:36-226, same operation order),
- * upload problem + tables to `device`. */
+ * upload problem + tables to `device`. quadrature_points must be 4, 8 or 16 (ConditionalSamplingHMM.cpp:39-58). */
 int coalgpu_create(const coalgpu_problem* problem, uint32_t quadrature_points, int device, coalgpu_sampler** out);
 void coalgpu_destroy(coalgpu_sampler* s);
 

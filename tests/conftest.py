@@ -65,6 +65,8 @@ def host_shim():
     L = C.CDLL(lib)
     L.hs_build.restype = C.c_void_p
     L.hs_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hs_build_q.restype = C.c_void_p
+    L.hs_build_q.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.hs_free.argtypes = [C.c_void_p]
     L.hs_tables.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
     L.hs_pismc.restype = C.c_double

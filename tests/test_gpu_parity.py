@@ -19,9 +19,9 @@ RTOL_HMM = 1e-9      # north_star: HMM forward probabilities within 1e-9 relativ
 RTOL_WEIGHT = 1e-9   # per-history log-weights
 
 
-def _sampler(p):
+def _sampler(p, Q=16):
     import coalescenator_b200 as cb
-    return cb.DeviceSampler(p)
+    return cb.DeviceSampler(p, quadrature_points=Q)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -53,15 +53,15 @@ def test_pismc_kernel_matches_reference_values(cuda_lib, name):
     s.close()
 
 
-def _compare_histories(oracle, p, n, seed, first=0, n_trace=None, max_events=8192):
+def _compare_histories(oracle, p, n, seed, first=0, n_trace=None, max_events=8192, Q=16):
     import torch
     n_trace = n if n_trace is None else n_trace
-    s = _sampler(p)
+    s = _sampler(p, Q)
     buf = s.alloc(n, n_trace=n_trace, max_events=max_events)
     s.sample(buf, seed, first, n)
     torch.cuda.synchronize()
     assert s.counters()["n_overflow"] == 0
-    ref = oracle.run(p, n, seed, mode=oracle.MODE_CANONICAL, first=first, n_event_hist=n_trace, max_events=max_events)
+    ref = oracle.run(p, n, seed, mode=oracle.MODE_CANONICAL, first=first, Q=Q, n_event_hist=n_trace, max_events=max_events)
     ev = s.events(buf)
     for h in range(n_trace):
         a, b = ev[h], ref["events"][h]
@@ -311,3 +311,10 @@ def test_random_problems_differential(oracle, cuda_lib):
         p = _random_problem(rng, k)
         n = 6 if p.LA + p.LB > 32 else 24
         _compare_histories(oracle, p, n, seed=1000 + k, max_events=1 << 15)
+
+
+@pytest.mark.parametrize("Q", [4, 8])
+def test_fewer_quadrature_points_histories(oracle, cuda_lib, Q):
+    """runSampler's quadrature_points argument (ImportanceSampler.cpp:110; 4 and 8 per ConditionalSamplingHMM.cpp:39-47)."""
+    p, _, _ = load_golden("cfg1_pair0")
+    _compare_histories(oracle, p, 48, seed=17, Q=Q)

@@ -109,3 +109,36 @@ def test_oracle_pismc_from_classes_matches_reference_values(oracle):
     for r in parse_pismc_records(trace, limit=400):
         v = oracle.pismc_classes(op, r["gamma"], r["n"], r["c"], r["cnt"], r["dA"], r["dB"])
         assert v == r["pi"]
+
+
+@pytest.mark.parametrize("Q", [4, 8])
+def test_fewer_quadrature_points(oracle, host_shim, Q):
+    """quadrature_points 4 and 8 (ConditionalSamplingHMM.cpp:39-47): the product pads its tables to the 16 interval
+    slots the kernels sweep; the padded slots must contribute nothing — tables equal the oracle's on the first Q
+    intervals and piSMC equals the oracle's literal evaluation with Q intervals."""
+    p, trace, _ = load_golden("cfg2_pair0")
+    th, rr = thetas_rrates(p)
+    h = host_shim.hs_build_q(Q, p.LA, p.LB, n_bound(p), p.T, _vp(th), _vp(rr))
+    assert h
+    try:
+        for n in (1, 4, 9):
+            mine, ref = _host_tables(host_shim, h, p, n, 0), oracle.tables(p, n, 0, Q=Q)
+            assert np.array_equal(mine["w"][:Q], ref["w"]) and not mine["w"][Q:].any()
+            assert np.array_equal(mine["y"][:Q], ref["y"]) and not mine["y"][Q:].any()
+            assert np.array_equal(mine["EA"][:Q], ref["EA"]) and not mine["EA"][Q:].any()
+            np.testing.assert_allclose(mine["z"][:Q, :Q], ref["z"], rtol=1e-15, atol=1e-300)
+        op = oracle.OracleProblem(p)
+        recs = parse_pismc_records(trace, limit=1500)
+        seen = set()
+        for r in recs:
+            key = (r["gamma"], r["n"], r["c"], tuple(r["cnt"]), tuple(r["dA"]), tuple(r["dB"]))
+            if key in seen:
+                continue
+            seen.add(key)
+            cnt = np.asarray(r["cnt"], dtype=np.int32); dA = np.asarray(r["dA"], dtype=np.int32); dB = np.asarray(r["dB"], dtype=np.int32)
+            want = oracle.pismc_classes(op, r["gamma"], r["n"], r["c"], r["cnt"], r["dA"], r["dB"], Q=Q)
+            for parts in ((1, 4) if r["gamma"] == 2 else (1,)):
+                v = host_shim.hs_pismc(h, r["gamma"], r["n"], r["c"], len(cnt), _vp(cnt), _vp(dA), _vp(dB), parts)
+                assert abs(v - want) / want < 1e-12, (Q, r, v, want)
+    finally:
+        host_shim.hs_free(h)
