@@ -20,6 +20,9 @@
 #include "SamplerOutput.hpp"
 #include "ImportanceSampler.hpp"
 #include "Matrix3d.hpp"
+#ifdef COALREF_GPU_BINDING
+#include "GpuImportanceSampler.hpp"   // include/: the binding a maintainer adds
+#endif
 
 // implemented in ref_trace.cpp (tracing build) or ref_notrace.cpp (plain build)
 void coalref_trace_open(const char* path, long max_histories, const std::vector<AncestralTypeMaps>* type_data);
@@ -99,14 +102,23 @@ int main(int argc, char** argv) {
     if (argc > 5) coalref_trace_open(argv[5], argc > 6 ? atol(argv[6]) : 1000000000L, &p.maps);
 
     Sample sample(p.maps, p.times, p.viral, std::pair<uint, uint>(p.LA, p.LB));
+#ifdef COALREF_GPU_BINDING
+    GpuImportanceSampler sampler;       // the one-line change of main.cpp:281
+#else
     ImportanceSampler sampler;
+#endif
     auto t0 = std::chrono::steady_clock::now();
     SamplerOutput<double> res = sampler.runSampler(&sample, p.mp, n_samples, n_threads, 16, seed);
     auto t1 = std::chrono::steady_clock::now();
     double secs = std::chrono::duration<double>(t1 - t0).count();
     coalref_trace_close();
 
-    printf("{\n\"impl\": \"reference\", \"n_samples\": %u, \"n_threads\": %u, \"seed\": %u, \"seconds\": %.6f,\n", n_samples, n_threads, seed, secs);
+#ifdef COALREF_GPU_BINDING
+    const char* impl = "reference-binding-gpu";
+#else
+    const char* impl = "reference";
+#endif
+    printf("{\n\"impl\": \"%s\", \"n_samples\": %u, \"n_threads\": %u, \"seed\": %u, \"seconds\": %.6f,\n", impl, n_samples, n_threads, seed, secs);
     printf("\"dims\": [%u, %u, %u], \"T\": %u,\n", res.likelihood().dim1(), res.likelihood().dim2(), res.likelihood().dim3(), p.T);
     print_grid("likelihood", res.likelihood(), false);
     print_grid("likelihoodSq", res.likelihoodSq(), false);

@@ -2,6 +2,7 @@
 include/coalgpu.h declares, and refuses to compute without a GPU (no CPU fallback)."""
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -51,3 +52,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_py" not in src and "coal_oracle" not in src and "liboracle" not in src, os.path.join(dirpath, f)
+
+
+BINDING = os.path.join(ROOT, "oracle", "_ref", "coalref_gpu")
+
+
+@pytest.mark.skipif(not os.path.exists(BINDING), reason="oracle/_ref/coalref_gpu not built (needs /root/reference)")
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_reference_side_binding_links_and_fails_loudly_without_gpu():
+    """include/GpuImportanceSampler.hpp compiled against the reference's own headers and linked into the reference
+    driver in place of ImportanceSampler (oracle/Makefile): it must link, and without a GPU it must raise, not fall
+    back to the CPU sampler that is linked into the same binary."""
+    r = subprocess.run([BINDING, os.path.join(ROOT, "tests", "golden", "cfg1_pair0.coalprob"), "10", "1", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "coalgpu: no CUDA device" in r.stderr
+    assert "likelihood" not in r.stdout

@@ -318,3 +318,29 @@ def test_fewer_quadrature_points_histories(oracle, cuda_lib, Q):
     """runSampler's quadrature_points argument (ImportanceSampler.cpp:110; 4 and 8 per ConditionalSamplingHMM.cpp:39-47)."""
     p, _, _ = load_golden("cfg1_pair0")
     _compare_histories(oracle, p, 48, seed=17, Q=Q)
+
+
+def test_reference_side_binding_equals_python_mirror(cuda_lib):
+    """The binding a reference maintainer would add (include/GpuImportanceSampler.hpp: Sample/ModelParameters ->
+    coalgpu_run_sampler -> SamplerOutput<double>) compiled against the reference's headers and driven by the reference
+    driver: the grids it returns through the reference's own Matrix3d are those of the Python mirror, bit for bit,
+    and agree with the CPU reference's golden result within Monte-Carlo error."""
+    import json, os, subprocess
+    import coalescenator_b200 as cb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "coalref_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/coalref_gpu not built")
+    for name, n, seed in (("cfg1_pair0", 3000, 5), ("grid_pair5", 2000, 9)):
+        p, _, _ = load_golden(name)
+        r = subprocess.run([exe, os.path.join(root, "tests", "golden", name + ".coalprob"), str(n), "1", str(seed)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = json.loads(r.stdout)
+        assert got["impl"] == "reference-binding-gpu"
+        out = cb.ImportanceSampler().run_sampler(p, n, seed=seed)
+        assert np.array_equal(np.array(got["likelihood"]), out.likelihood.ravel())
+        assert np.array_equal(np.array(got["likelihoodSq"]), out.likelihoodSq.ravel())
+        assert np.array_equal(np.array(got["tmrca"]), out.tmrca.ravel())
+        for l in range(p.T):
+            assert np.array_equal(np.array(got["lineages_remaining"][str(l)]), out.lineages_remaining[l].ravel())
