@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace coalgpu;
@@ -33,7 +36,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 // Device memory comes from the stream-ordered pool with an unlimited release threshold: cudaMalloc/cudaFree
 // cost up to hundreds of milliseconds per run_sampler call on this driver (measured), the pool costs microseconds.
-cudaError_t dev_alloc(void** p, size_t bytes) {
+cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream = 0) {
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -47,7 +50,7 @@ cudaError_t dev_alloc(void** p, size_t bytes) {
         }
         configured.fetch_or(bit);
     }
-    return cudaMallocAsync(p, std::max<size_t>(bytes, 16), 0);
+    return cudaMallocAsync(p, std::max<size_t>(bytes, 16), stream);
 }
 void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
@@ -78,57 +81,53 @@ struct coalgpu_sampler {
     size_t k2_smem = 0;
 };
 
-extern "C" {
+namespace {
 
-const char* coalgpu_last_error(void) { return g_err.c_str(); }
-#ifndef COAL_NO_TMA
-const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged table rows)"; }
-#else
-const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
-#endif
-uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
+// Everything coalgpu_create computes on the CPU (no CUDA call): the batch entry point runs this part for the
+// next locus pairs on host threads while the GPU works on the current ones.
+struct HostPrep {
+    int T = 0, LA = 0, LB = 0, G = 0;
+    DevProblem P{};
+    HostTables tab;
+    std::vector<int> type_off;
+    std::vector<unsigned long long> type_w;
+    std::vector<unsigned int> type_cg;
+    std::vector<EpochConst> ep;
+    std::vector<GridConst> grid;
+    std::vector<double> lfact, rcp, times;
+};
 
-void coalgpu_destroy(coalgpu_sampler* s) {
-    if (!s) return;
-    cudaSetDevice(s->device);
-    for (void* p : s->allocs) dev_free(p);
-    dev_free(s->d_block_partials);
-    delete s;
+int validate_problem(const coalgpu_problem* p, uint32_t Q, std::string& err) {
+    auto bad = [&](const char* m) { err = m; return COALGPU_EINVAL; };
+    if (Q != 4 && Q != 8 && Q != 16) return bad("quadrature_points must be 4, 8 or 16 (ConditionalSamplingHMM.cpp:39-58)");
+    if (p->T < 1 || p->LA < 1 || p->LB < 1 || p->LA + p->LB > 64) return bad("need T >= 1, LA, LB >= 1 and LA + LB <= 64");
+    if (p->n_mu < 1 || p->n_rho < 1 || p->n_lambda < 1) return bad("empty target grid");
+    if (!(p->tau > 0) || !(p->driving_mu > 0) || !(p->driving_lambda > 0) || !(p->driving_rho > 0)) return bad("driving values and tau must be positive (main.cpp:147-150)");
+    for (int t = 1; t < p->T; t++) if (!(p->times[t] > p->times[t - 1])) return bad("sampling times must be strictly ascending");
+    return 0;
 }
 
-int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
-    if (!p || !out) return fail(COALGPU_EINVAL, "null argument");
-    *out = nullptr;
-    if (Q != 4 && Q != 8 && Q != 16) return fail(COALGPU_EINVAL, "quadrature_points must be 4, 8 or 16 (ConditionalSamplingHMM.cpp:39-58)");
-    if (p->T < 1 || p->LA < 1 || p->LB < 1 || p->LA + p->LB > 64) return fail(COALGPU_EINVAL, "need T >= 1, LA, LB >= 1 and LA + LB <= 64");
-    if (p->n_mu < 1 || p->n_rho < 1 || p->n_lambda < 1) return fail(COALGPU_EINVAL, "empty target grid");
-    if (!(p->tau > 0) || !(p->driving_mu > 0) || !(p->driving_lambda > 0) || !(p->driving_rho > 0)) return fail(COALGPU_EINVAL, "driving values and tau must be positive (main.cpp:147-150)");
-    for (int t = 1; t < p->T; t++) if (!(p->times[t] > p->times[t - 1])) return fail(COALGPU_EINVAL, "sampling times must be strictly ascending");
+int device_check(int device) {
     int ndev = 0;
-    {
-        cudaError_t e = cudaGetDeviceCount(&ndev);
-        if (e != cudaSuccess || ndev == 0) return fail(COALGPU_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
-    }
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(COALGPU_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(COALGPU_ENODEV, "device index out of range");
-    CU_OK(cudaSetDevice(device));
-    // cudaGetDeviceProperties costs tens of milliseconds per call; two attributes are all that is needed
-    int cc_major = 0, sm_count = 0;
-    CU_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
-    CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (cc_major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
+    return 0;
+}
 
-    coalgpu_sampler* s = new coalgpu_sampler;
-    s->device = device; s->T = p->T; s->LA = p->LA; s->LB = p->LB;
-    s->G = p->n_mu * p->n_rho * p->n_lambda;
-    const int T = p->T, LA = p->LA, LB = p->LB, G = s->G;
+int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPrep& h, std::string& err) {
+    auto bad = [&](const char* m) { err = m; return COALGPU_EINVAL; };
+    if (int rc = validate_problem(p, Q, err)) return rc;
+    h.T = p->T; h.LA = p->LA; h.LB = p->LB; h.G = p->n_mu * p->n_rho * p->n_lambda;
+    const int T = p->T, LA = p->LA, LB = p->LB, G = h.G;
     const uint64_t maskA = (LA == 64) ? ~0ull : ((1ull << LA) - 1);
     const uint64_t maskB = ((LB == 64) ? ~0ull : ((1ull << LB) - 1)) << LA;
 
     // merge duplicate input types per sampling time, keep insertion order; bound the lineage count:
     // every sampled two-locus lineage can split once into an A and a B lineage
-    std::vector<int> type_off(T + 1, 0);
-    std::vector<unsigned long long> type_w;
-    std::vector<unsigned int> type_cg;
+    std::vector<int>& type_off = h.type_off; type_off.assign(T + 1, 0);
+    std::vector<unsigned long long>& type_w = h.type_w;
+    std::vector<unsigned int>& type_cg = h.type_cg;
     long long n_bound = 0;
     double perm = 0.0;
     for (int t = 0; t < T; t++) {
@@ -137,9 +136,9 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
             const int g = p->type_gamma[k];
             const uint64_t w = p->type_words[k];
             const unsigned int c = p->type_counts[k];
-            if (g > 2 || c == 0) { delete s; return fail(COALGPU_EINVAL, "bad type record"); }
+            if (g > 2 || c == 0) return bad("bad type record");
             const uint64_t allowed = g == COALGPU_GAMMA_A ? maskA : (g == COALGPU_GAMMA_B ? maskB : (maskA | maskB));
-            if (w & ~allowed) { delete s; return fail(COALGPU_EINVAL, "haplotype word has bits outside its loci"); }
+            if (w & ~allowed) return bad("haplotype word has bits outside its loci");
             bool hit = false;
             for (size_t i = start; i < type_w.size(); i++)
                 if (type_w[i] == w && (int)(type_cg[i] >> 30) == g) { type_cg[i] += c; hit = true; break; }
@@ -154,8 +153,8 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
             perm -= std::lgamma((double)tot + 1.0);
         }
     }
-    if (type_off[1] == 0) { delete s; return fail(COALGPU_EINVAL, "first sampling time has no sequences"); }
-    if (n_bound < 1 || n_bound > 60000) { delete s; return fail(COALGPU_EINVAL, "lineage bound out of range (1..60000)"); }
+    if (type_off[1] == 0) return bad("first sampling time has no sequences");
+    if (n_bound < 1 || n_bound > 60000) return bad("lineage bound out of range (1..60000)");
     const int n_max = (int)n_bound;
 
     // HMM constants per (epoch, lineage count): ImportanceSampler.cpp:69-76, ConditionalSamplingHMM.cpp:36-226
@@ -164,9 +163,9 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
         thetas[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_mu;
         rrates[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_rho;
     }
-    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, s->tab)) { delete s; return fail(COALGPU_EINVAL, "table construction failed"); }
+    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, h.tab, table_threads)) return bad("table construction failed");
 
-    std::vector<EpochConst> ep(T);
+    h.ep.resize(T);
     for (int c = 0; c < T; c++) {
         const double V = p->viral[c];
         EpochConst e{};
@@ -175,9 +174,9 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
         e.drho = 4 * p->driving_rho * e.dN;
         e.dthA = e.dtheta * LA; e.dthB = e.dtheta * LB;
         e.inv2Ntau = 1.0 / (2 * e.dN * p->tau);
-        ep[c] = e;
+        h.ep[c] = e;
     }
-    std::vector<GridConst> grid((size_t)T * G);
+    h.grid.resize((size_t)T * G);
     for (int c = 0; c < T; c++) {
         const double V = p->viral[c];
         size_t g = 0;
@@ -188,17 +187,17 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
             gc.rho = 4 * p->rho[j] * p->lambda[z] * V;
             gc.inv2Ntau = 1.0 / (2 * N * p->tau);
             gc.log_theta = std::log(gc.theta); gc.log_rho = std::log(gc.rho); gc.log_2Ntau = std::log(2 * N * p->tau);
-            grid[(size_t)c * G + g] = gc;
+            h.grid[(size_t)c * G + g] = gc;
         }
     }
-    std::vector<double> lfact(n_max + 2);
-    for (int i = 0; i < n_max + 2; i++) lfact[i] = std::lgamma((double)i + 1.0);
-    std::vector<double> rcp(n_max + 2, 0.0);
-    for (int i = 1; i < n_max + 2; i++) rcp[i] = 1.0 / (double)i;
-    std::vector<double> times(p->times, p->times + T);
+    h.lfact.resize(n_max + 2);
+    for (int i = 0; i < n_max + 2; i++) h.lfact[i] = std::lgamma((double)i + 1.0);
+    h.rcp.assign(n_max + 2, 0.0);
+    for (int i = 1; i < n_max + 2; i++) h.rcp[i] = 1.0 / (double)i;
+    h.times.assign(p->times, p->times + T);
 
-    DevProblem& P = s->P;
-    const TableLayout& lay = s->tab.lay;
+    DevProblem& P = h.P;
+    const TableLayout& lay = h.tab.lay;
     P.T = T; P.LA = LA; P.LB = LB; P.Ltot = LA + LB; P.G = G;
     P.n_max = n_max;
     P.kmax = ((n_max + 2 + 31) / 32) * 32;
@@ -210,22 +209,41 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     P.maskA = maskA; P.maskB = maskB;
     P.perm_const = perm;
     P.pow2negLA = std::ldexp(1.0, -LA); P.pow2negLB = std::ldexp(1.0, -LB); P.pow2negL = std::ldexp(1.0, -(LA + LB));
-    double wsum = 0; for (int i = 0; i < kQ; i++) wsum += s->tab.w[i];
+    double wsum = 0; for (int i = 0; i < kQ; i++) wsum += h.tab.w[i];
     P.wsum = wsum;
+    for (int i = 0; i < kQ; i++) P.w[i] = h.tab.w[i];
+    return 0;
+}
+
+// Device half of coalgpu_create: checks the device, uploads what prepare_host built, picks the launch geometry.
+int finish_device(HostPrep& h, int device, coalgpu_sampler** out) {
+    if (int rc = device_check(device)) return rc;
+    CU_OK(cudaSetDevice(device));
+    // cudaGetDeviceProperties costs tens of milliseconds per call; two attributes are all that is needed
+    int cc_major = 0, sm_count = 0;
+    CU_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
+
+    coalgpu_sampler* s = new coalgpu_sampler;
+    s->device = device; s->T = h.T; s->LA = h.LA; s->LB = h.LB; s->G = h.G;
+    s->P = h.P;
+    s->tab = std::move(h.tab);
+    DevProblem& P = s->P;
 
     int rc = 0;
     double* d_rows; int* d_set; double* d_times; EpochConst* d_ep; GridConst* d_grid; double* d_lf; double* d_rcp; int* d_toff;
     unsigned long long* d_tw; unsigned int* d_tcg;
 #define UP(vec, ptr) do { rc = upload(vec, &ptr); if (rc) { coalgpu_destroy(s); return rc; } s->allocs.push_back(ptr); } while (0)
-    UP(s->tab.rows, d_rows); UP(s->tab.set_of_epoch, d_set); UP(times, d_times); UP(ep, d_ep); UP(grid, d_grid);
-    UP(lfact, d_lf); UP(rcp, d_rcp); UP(type_off, d_toff); UP(type_w, d_tw); UP(type_cg, d_tcg);
+    UP(s->tab.rows, d_rows); UP(s->tab.set_of_epoch, d_set); UP(h.times, d_times); UP(h.ep, d_ep); UP(h.grid, d_grid);
+    UP(h.lfact, d_lf); UP(h.rcp, d_rcp); UP(h.type_off, d_toff); UP(h.type_w, d_tw); UP(h.type_cg, d_tcg);
 #undef UP
     P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf; P.rcp = d_rcp;
     P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
-    CU_OK(cudaMemcpyToSymbol(c_w, s->tab.w.data(), sizeof(double) * kQ));
     CU_OK(dev_alloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));
     s->allocs.push_back(s->d_counters);
-    CU_OK(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CU_OK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), 0));
+    CU_OK(cudaStreamSynchronize(0));   // uploads and the memset are complete before any stream uses the sampler
 
     // launch geometry: persistent CTAs of kCtaThreads threads = kCtaThreads/W groups of W lanes, one history per group.
     // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
@@ -254,6 +272,38 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* coalgpu_last_error(void) { return g_err.c_str(); }
+#ifndef COAL_NO_TMA
+const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged table rows)"; }
+#else
+const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
+#endif
+uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
+
+void coalgpu_destroy(coalgpu_sampler* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) dev_free(p);
+    dev_free(s->d_block_partials);
+    delete s;
+}
+
+int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
+    if (!p || !out) return fail(COALGPU_EINVAL, "null argument");
+    *out = nullptr;
+    HostPrep h; std::string err;
+    int rc = validate_problem(p, Q, err);
+    if (rc) return fail(rc, err);
+    if ((rc = device_check(device))) return rc;
+    rc = prepare_host(p, Q, 0, h, err);
+    if (rc) return fail(rc, err);
+    return finish_device(h, device, out);
 }
 
 int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
@@ -341,7 +391,7 @@ int coalgpu_partials(coalgpu_sampler* s, uint64_t n, void* stream, const double*
     if (need > s->block_partials_cap) {
         dev_free(s->d_block_partials);
         s->d_block_partials = nullptr; s->block_partials_cap = 0;
-        CU_OK(dev_alloc((void**)&s->d_block_partials, need));
+        CU_OK(dev_alloc((void**)&s->d_block_partials, need, st));
         s->block_partials_cap = need;
     }
     dim3 grid(nb, s->G, nstat);
@@ -431,77 +481,135 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
 }
 
 // Locus-pair batching: the reference runs its pairs one after another (main.cpp:242-311);
-// a pair with a few thousand importance samples cannot fill 148 SMs, so the pairs of a wave are launched
-// on separate streams and run concurrently. Results are identical to n_problems calls of coalgpu_run_sampler.
+// a pair with a few thousand importance samples cannot fill 148 SMs and its HMM tables take the host longer to
+// build than the GPU needs to sample it. So: host threads prepare the next pairs (tables, merged types) while the
+// GPU samples the current ones, every pair runs on one of 16 streams, at most 32 pairs are in flight, and the only
+// host<-device transfer per pair is one pinned copy of its (max, sum) partials and counters.
+// Results are identical to n_problems calls of coalgpu_run_sampler.
 int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples, uint32_t Q,
                               uint64_t seed, int device, coalgpu_result* results) {
     if (n_problems < 0 || (n_problems > 0 && (!problems || !results))) return fail(COALGPU_EINVAL, "null argument");
     if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
-    const int kWave = 32, kStreams = 16;
-    struct Job { coalgpu_sampler* s = nullptr; double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr; std::vector<double> hp; };
+    if (n_problems == 0) return 0;
+    {   // argument and device errors before any thread is started
+        std::string verr;
+        for (int k = 0; k < n_problems; k++) if (int vrc = validate_problem(problems + k, Q, verr)) return fail(vrc, verr);
+        if (int drc = device_check(device)) return drc;
+    }
+    constexpr int kWindow = 32, kStreams = 16;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int lookahead = (int)std::min<unsigned>(std::max(2u, hw), 32u);   // pairs being prepared ahead of the GPU
+    struct Prep { HostPrep h; int rc = 0; std::string err; };
+    struct Job {
+        coalgpu_sampler* s = nullptr;
+        double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
+        double* h_p = nullptr;            // slot of the pinned slab: partials [nstat*G*2] then 8 counters
+        size_t np = 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        int index = -1;
+    };
+    auto is_big = [&](const coalgpu_problem* p) {   // a pair whose weight matrix is large fills the device on its own
+        const size_t G = (size_t)p->n_mu * p->n_rho * p->n_lambda;
+        return n_samples * (G + p->T + 1) * 8 > (256ull << 20);
+    };
+    std::vector<std::future<std::unique_ptr<Prep>>> preps(n_problems);
+    int next_prep = 0;
+    auto schedule = [&](int upto) {
+        for (; next_prep < n_problems && next_prep < upto; next_prep++) {
+            const coalgpu_problem* p = problems + next_prep;
+            if (is_big(p)) continue;
+            // one table thread per pair: the pairs are the parallel axis here
+            auto work = [p, Q]() {
+                std::unique_ptr<Prep> r(new Prep);
+                r->rc = prepare_host(p, Q, 1, r->h, r->err);
+                return r;
+            };
+            try { preps[next_prep] = std::async(std::launch::async, work); }
+            catch (...) { preps[next_prep] = std::async(std::launch::deferred, work); }   // no thread to be had: prepare on demand
+        }
+    };
     cudaStream_t streams[kStreams] = {};
     int n_streams = 0;
     int rc = 0; std::string err;
-    for (int w0 = 0; w0 < n_problems && !rc; w0 += kWave) {
-        const int nw = std::min(kWave, n_problems - w0);
-        // a pair whose weight matrix is large already fills the device: run it through the chunked path
-        std::vector<Job> jobs(nw);
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        auto cleanup = [&]() {
-            for (Job& j : jobs) {
-                dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p);
-                if (j.s) coalgpu_destroy(j.s);
-            }
-            if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
-        };
+    std::vector<Job> window;
+    auto release = [&](Job& j) {
+        dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p);
+        if (j.e0) cudaEventDestroy(j.e0); if (j.e1) cudaEventDestroy(j.e1);
+        if (j.s) coalgpu_destroy(j.s);
+        j = Job();
+    };
 #define WB_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess && !rc) { rc = COALGPU_ECUDA; err = std::string(#expr) + ": " + cudaGetErrorString(_e); } } while (0)
-        for (int k = 0; k < nw && !rc; k++) {
-            const coalgpu_problem* p = problems + w0 + k;
-            const size_t G = (size_t)p->n_mu * p->n_rho * p->n_lambda;
-            if (n_samples * (G + p->T + 1) * 8 > (256ull << 20)) {        // big pair: sequential, chunked
-                rc = coalgpu_run_sampler(p, n_samples, Q, seed, device, results + w0 + k);
+    auto retire = [&](Job& j) {            // wait for the pair, turn its partials into the result grids
+        if (j.s && !rc) {
+            WB_OK(cudaEventSynchronize(j.e1));
+            float ms = 0;
+            if (!rc) WB_OK(cudaEventElapsedTime(&ms, j.e0, j.e1));
+            if (!rc) {
+                coalgpu_result* r = results + j.index;
+                unsigned long long cnt[8];
+                std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
+                rc = coalgpu_finalize(j.s->G, j.s->T, j.h_p, r);
                 if (rc) err = g_err;
-                continue;
+                r->n_histories = n_samples; r->n_events = cnt[1]; r->n_pismc = cnt[2]; r->seconds_device = ms * 1e-3;
+                if (!rc && cnt[3]) { rc = COALGPU_EOVERFLOW; err = "a history outgrew the type-store capacity"; }
             }
-            Job& j = jobs[k];
-            rc = coalgpu_create(p, Q, device, &j.s);
-            if (rc) { err = g_err; break; }
-            if (n_streams == 0) { for (int i = 0; i < kStreams; i++) WB_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)); n_streams = kStreams; }
-            const int T = j.s->T; const size_t nstat = 3 + T;
-            j.hp.resize(nstat * G * 2);
-            WB_OK(dev_alloc((void**)&j.d_w, n_samples * G * sizeof(double)));
-            WB_OK(dev_alloc((void**)&j.d_t, n_samples * sizeof(double)));
-            WB_OK(dev_alloc((void**)&j.d_l, n_samples * T * sizeof(double)));
-            WB_OK(dev_alloc((void**)&j.d_p, j.hp.size() * sizeof(double)));
         }
-        if (!rc) { WB_OK(cudaEventCreate(&e0)); WB_OK(cudaEventCreate(&e1)); WB_OK(cudaDeviceSynchronize()); WB_OK(cudaEventRecord(e0, streams[0])); }
-        for (int k = 0; k < nw && !rc; k++) {
-            Job& j = jobs[k];
-            if (!j.s) continue;
-            cudaStream_t st = streams[k % kStreams];
-            rc = coalgpu_sample(j.s, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0);
-            if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
-            if (rc) { err = g_err; break; }
-            WB_OK(cudaMemcpyAsync(j.hp.data(), j.d_p, j.hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
-        WB_OK(cudaDeviceSynchronize());
-        float ms = 0;
-        if (!rc && e0) { WB_OK(cudaEventRecord(e1, streams[0])); WB_OK(cudaEventSynchronize(e1)); WB_OK(cudaEventElapsedTime(&ms, e0, e1)); }
-#undef WB_OK
-        for (int k = 0; k < nw && !rc; k++) {
-            Job& j = jobs[k];
-            if (!j.s) continue;
-            coalgpu_result* r = results + w0 + k;
-            uint64_t nev = 0, npi = 0, nov = 0;
-            rc = coalgpu_counters(j.s, &nev, &npi, &nov);
-            if (!rc) rc = coalgpu_finalize(j.s->G, j.s->T, j.hp.data(), r);
-            if (rc) { err = g_err; break; }
-            r->n_histories = n_samples; r->n_events = nev; r->n_pismc = npi; r->seconds_device = ms * 1e-3 / nw;
-            if (nov) { rc = COALGPU_EOVERFLOW; err = "a history outgrew the type-store capacity"; }
-        }
-        cleanup();
+        release(j);
+    };
+    // one pinned slab for the partials of the pairs in flight (pinned allocations synchronise the device: once per call)
+    size_t slot_doubles = 0;
+    for (int k = 0; k < n_problems; k++)
+        if (!is_big(problems + k)) slot_doubles = std::max(slot_doubles, (size_t)(3 + problems[k].T) * problems[k].n_mu * problems[k].n_rho * problems[k].n_lambda * 2 + 8);
+    double* slab = nullptr;
+    if (slot_doubles) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&slab, slot_doubles * kWindow * sizeof(double));
+        if (e != cudaSuccess) return fail(COALGPU_ECUDA, std::string("pinned host buffer: ") + cudaGetErrorString(e));
     }
-    for (int i = 0; i < n_streams; i++) cudaStreamDestroy(streams[i]);
+    long launched = 0;
+    schedule(lookahead);
+    for (int k = 0; k < n_problems && !rc; k++) {
+        const coalgpu_problem* p = problems + k;
+        if (is_big(p)) {                   // sequential, chunked
+            rc = coalgpu_run_sampler(p, n_samples, Q, seed, device, results + k);
+            if (rc) err = g_err;
+            schedule(k + 1 + lookahead);
+            continue;
+        }
+        std::unique_ptr<Prep> pr = preps[k].get();
+        schedule(k + 1 + lookahead);
+        if (pr->rc) { rc = pr->rc; err = pr->err; break; }
+        if ((int)window.size() == kWindow) { retire(window.front()); window.erase(window.begin()); if (rc) break; }
+        window.emplace_back();
+        Job& j = window.back();
+        j.index = k;
+        rc = finish_device(pr->h, device, &j.s);
+        if (rc) { err = g_err; break; }
+        if (n_streams == 0) { for (int i = 0; i < kStreams; i++) WB_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)); n_streams = kStreams; }
+        cudaStream_t st = streams[k % kStreams];
+        const int T = j.s->T; const size_t G = j.s->G;
+        j.np = (size_t)(3 + T) * G * 2;
+        WB_OK(cudaMallocAsync((void**)&j.d_w, n_samples * G * sizeof(double), st));
+        WB_OK(cudaMallocAsync((void**)&j.d_t, n_samples * sizeof(double), st));
+        WB_OK(cudaMallocAsync((void**)&j.d_l, n_samples * T * sizeof(double), st));
+        WB_OK(cudaMallocAsync((void**)&j.d_p, (j.np + 8) * sizeof(double), st));
+        j.h_p = slab + (size_t)(launched++ % kWindow) * slot_doubles;   // free again: its previous user was retired above
+        WB_OK(cudaEventCreate(&j.e0)); WB_OK(cudaEventCreate(&j.e1));
+        if (rc) break;
+        WB_OK(cudaEventRecord(j.e0, st));
+        rc = coalgpu_sample(j.s, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0);
+        if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
+        if (rc) { err = g_err; break; }
+        WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WB_OK(cudaEventRecord(j.e1, st));
+    }
+    if (rc) cudaDeviceSynchronize();       // error path: nothing may still be running on buffers that are about to be freed
+    for (Job& j : window) retire(j);
+#undef WB_OK
+    for (int k = 0; k < n_problems; k++) if (preps[k].valid()) preps[k].wait();   // no worker may outlive the call
+    if (n_streams) { cudaDeviceSynchronize(); for (int i = 0; i < n_streams; i++) cudaStreamDestroy(streams[i]); }
+    if (slab) cudaFreeHost(slab);
     if (rc) return fail(rc, err);
     return 0;
 }

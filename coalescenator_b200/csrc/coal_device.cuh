@@ -40,6 +40,7 @@ struct DevProblem {
     unsigned long long maskA, maskB;
     double perm_const;        // sum_t probabilitySamplePermutation (ProposalEngine.cpp:88-118,822-828)
     double pow2negLA, pow2negLB, pow2negL, wsum;
+    double w[kQd];            // interval weights (ConditionalSamplingHMM.cpp:63-71); per sampler: they depend on quadrature_points
     const double* rows;       // [n_sets][n_max][row_doubles]
     const int* set_of_epoch;  // [T]
     const double* times;      // [T]
@@ -63,8 +64,6 @@ struct SampleArgs {
     unsigned int n_trace, max_events;
     unsigned long long* counters;   // [0] next history, [1] events, [2] pismc, [3] overflow, [4] two-locus queries, [5] their classes
 };
-
-__constant__ double c_w[kQd];   // interval weights (ConditionalSamplingHMM.cpp:63-71)
 
 #ifndef COAL_PHILOX_UNROLL
 #define COAL_PHILOX_UNROLL 2

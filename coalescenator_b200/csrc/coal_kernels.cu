@@ -432,7 +432,7 @@ __device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, 
     ChunkPartial cp = {0, 0, 0, 0, 0, 0};
     const double inv_n = __ldg(sP.rcp + tot.n);
     if (!empty) {
-#define COAL_FWD(PER) chunk_forward<PER>(ld, c_w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
+#define COAL_FWD(PER) chunk_forward<PER>(ld, sP.w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
                                           cls, 1, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB), sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
         cp = COAL_FWD(COAL_PER);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
 #undef COAL_FWD
@@ -924,7 +924,7 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
         {
             ChunkPartial cp = {0, 0, 0, 0, 0, 0};
             auto ld = [row](int off) { return __ldg(row + off); };
-            if (g == GC && nH > 0) cp = chunk_forward<1>(ld, c_w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
+            if (g == GC && nH > 0) cp = chunk_forward<1>(ld, P.w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
                                                          col, 32, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0, tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0,
                                                          P.pow2negLA, P.pow2negLB, r, r + 1);
             double ipre = cp.pre, ipreB = cp.preB;

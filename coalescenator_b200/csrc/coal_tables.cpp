@@ -2,8 +2,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
+#include <tuple>
 
 namespace coalgpu {
 namespace {
@@ -30,13 +35,18 @@ bool nearly_equal(double a, double b) {   // Utils.hpp:206-209
     return (a == b) || (std::fabs(a - b) < std::fabs(std::min(a, b)) * std::numeric_limits<double>::epsilon());
 }
 
-// y[i], and z in structured form, ConditionalSamplingHMM.cpp:85-182
-void transition_row(int Q, const double* t, const double* w, double r, unsigned n, double* y, double* zlow, double* g, double* zdiag) {
+// y[i], and z in structured form, ConditionalSamplingHMM.cpp:85-182. The reference evaluates exp(-t[i]/c1),
+// exp(-t[i]/c3) and exp(-t[i]) at both ends of every interval; each distinct argument is evaluated once here
+// (e1, e3, e0) -- same arguments, same values, a quarter of the calls.
+void transition_row(int Q, const double* t, const double* w, const double* e0 /*exp(-t[i])*/, double r, unsigned n,
+                    double* y, double* zlow, double* g, double* zdiag) {
     const double c1 = n / (r + n);
+    double e1[kQ + 1];
+    for (int i = 0; i <= Q; i++) e1[i] = std::exp(-t[i] / c1);
     if (nearly_equal(r, n)) {
         for (int i = 0; i < Q; i++) {
-            y[i] = c1 / w[i] * (std::exp(-t[i] / c1) - std::exp(-t[i + 1] / c1));
-            const double core = (w[i] + (t[i] * std::exp(-t[i]) - t[i + 1] * std::exp(-t[i + 1])));
+            y[i] = c1 / w[i] * (e1[i] - e1[i + 1]);
+            const double core = (w[i] + (t[i] * e0[i] - t[i + 1] * e0[i + 1]));
             zlow[i] = core;                 // z(i',i) for i' > i  (:114)
             g[i] = core / w[i];             // z(i,j) = w[j]/w[i]*core for j > i  (:118)
             const double term1 = w[i] * core;
@@ -47,52 +57,135 @@ void transition_row(int Q, const double* t, const double* w, double r, unsigned 
     } else {
         const double c2 = r / (r - n);
         const double c3 = n / r;
+        double e3[kQ + 1];
+        for (int i = 0; i <= Q; i++) e3[i] = std::exp(-t[i] / c3);
         for (int i = 0; i < Q; i++) {
-            y[i] = c1 / w[i] * (std::exp(-t[i] / c1) - std::exp(-t[i + 1] / c1));
-            const double inner = (w[i] - c3 * (std::exp(-t[i] / c3) - std::exp(-t[i + 1] / c3)));
+            y[i] = c1 / w[i] * (e1[i] - e1[i + 1]);
+            const double inner = (w[i] - c3 * (e3[i] - e3[i + 1]));
             zlow[i] = c2 * inner;           // :156
             g[i] = c2 / w[i] * inner;       // :160 without the w[j] factor
             const double term1 = w[i] * inner;
-            const double term2 = c1 / c2 * (std::exp(-t[i] / c1) - std::exp(-t[i + 1] / c1));
-            const double term3 = c3 * (std::exp(-t[i]) * std::exp(-t[i + 1] / c3) - std::exp(-t[i + 1]) * std::exp(-t[i] / c3));
+            const double term2 = c1 / c2 * (e1[i] - e1[i + 1]);
+            const double term3 = c3 * (e0[i] * e3[i + 1] - e0[i + 1] * e3[i]);
             zdiag[i] = c2 / w[i] * (term1 - term2 - term3);   // :164-168
         }
     }
 }
 
-// E[i][d], ConditionalSamplingHMM.cpp:184-226. The exponentials depend on (k+l) only, so they are
-// evaluated once per (k+l, i) — same arguments, hence the same values, as the reference's inner loop.
+// E[i][d], ConditionalSamplingHMM.cpp:184-226. The reference evaluates, per interval i and distance j,
+//   e = sum_l ( sum_k bin(L-j,k) / rate(k+l) * (ex(k+l,i-1) - ex(k+l,i)) ) * bin(j,l) * (-1)^l.
+// The exponentials depend on (k+l, i) and the quotient bin/rate on (j,k,l) only, so they are hoisted out of the loops
+// they do not depend on; every sum still adds the same values in the same order (k inner, l outer, per interval), hence
+// the table is bit-identical to the reference's while the interval loop is the innermost, vectorisable one.
 void emission_table(int Q, const double* t, const double* w, const std::vector<double>& bin, int bw, double theta,
                     unsigned n, int L, double* E /*[L+1][kEStride]*/) {
-    std::vector<double> rate(L + 1), ex((size_t)(L + 1) * (kQ + 1));
+    std::vector<double> rate(L + 1), diff((size_t)(L + 1) * kQ, 0.0);
+    double ex[kQ + 1];
     for (int m = 0; m <= L; m++) {
         rate[m] = (2 * theta * (unsigned)m / n) + 1;
-        for (int i = 0; i <= Q; i++) ex[(size_t)m * (kQ + 1) + i] = std::exp(-rate[m] * t[i]);
+        for (int i = 0; i <= Q; i++) ex[i] = std::exp(-rate[m] * t[i]);
+        for (int i = 0; i < Q; i++) diff[(size_t)m * kQ + i] = ex[i] - ex[i + 1];
     }
     const double two_L = std::pow(2, (double)L);
-    for (int i = 1; i <= Q; i++) {
-        for (int j = 0; j <= L; j++) {
-            double e = 0;
-            for (int l = 0; l <= j; l++) {
-                double inner = 0;
-                for (int k = 0; k <= L - j; k++) {
-                    const int m = k + l;
-                    inner += bin[(size_t)(L - j) * bw + k] / rate[m] * (ex[(size_t)m * (kQ + 1) + i - 1] - ex[(size_t)m * (kQ + 1) + i]);
-                }
-                e += inner * bin[(size_t)j * bw + l] * ((l & 1) ? -1.0 : 1.0);
+    for (int j = 0; j <= L; j++) {
+        double e[kQ], inner[kQ];
+        for (int i = 0; i < kQ; i++) e[i] = 0;
+        for (int l = 0; l <= j; l++) {
+            for (int i = 0; i < kQ; i++) inner[i] = 0;
+            for (int k = 0; k <= L - j; k++) {
+                const double c = bin[(size_t)(L - j) * bw + k] / rate[k + l];
+                const double* d = &diff[(size_t)(k + l) * kQ];
+                for (int i = 0; i < kQ; i++) inner[i] += c * d[i];
             }
-            e /= (w[i - 1] * two_L);
-            e = std::max(e, std::numeric_limits<double>::epsilon());
-            E[(size_t)j * kEStride + (i - 1)] = e;   // distance-major: the intervals of one distance are contiguous
+            const double b = bin[(size_t)j * bw + l], sgn = (l & 1) ? -1.0 : 1.0;
+            for (int i = 0; i < kQ; i++) e[i] += inner[i] * b * sgn;
+        }
+        for (int i = 0; i < Q; i++) {
+            double v = e[i] / (w[i] * two_L);
+            v = std::max(v, std::numeric_limits<double>::epsilon());
+            E[(size_t)j * kEStride + i] = v;   // distance-major: the intervals of one distance are contiguous
         }
     }
 }
 
+// ---- emission cache ---------------------------------------------------------------------------------------------
+// E depends on (quadrature, L, theta, n) only -- not on the locus pair: theta = 4 lambda V mu is the same for every pair
+// of a data set and the pairs of main.cpp:242-311 have a handful of distinct L. The blocks are therefore kept in a
+// process-wide cache, so that a batch of pairs builds each of them once (the host table
+// builder is the serial section that shows once sampling is fast). Values are the same doubles either way.
+struct EmissionBlock {
+    std::mutex m;
+    int n_built = 0;                 // blocks for n = 1..n_built are valid
+    int stride = 0;                  // doubles per n: (L+1)*kEStride table + (L+1) weighted sums
+    std::vector<double> data;
+};
+struct EmissionKey {
+    int Q, L; uint64_t theta_bits;
+    bool operator<(const EmissionKey& o) const { return std::tie(Q, L, theta_bits) < std::tie(o.Q, o.L, o.theta_bits); }
+};
+std::mutex g_cache_mutex;
+std::map<EmissionKey, std::shared_ptr<EmissionBlock>> g_cache;
+size_t g_cache_doubles = 0;
+constexpr size_t kCacheMaxDoubles = (size_t)1 << 26;   // 512 MiB; the cache is dropped when it grows past this
+
+std::shared_ptr<EmissionBlock> emission_block(int Q, int L, double theta, int n_max, const double* t, const double* w,
+                                              const std::vector<double>& bin, int bw, int threads) {
+    EmissionKey key{Q, L, 0};
+    std::memcpy(&key.theta_bits, &theta, sizeof(double));
+    std::shared_ptr<EmissionBlock> b;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mutex);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            if (g_cache_doubles > kCacheMaxDoubles) { g_cache.clear(); g_cache_doubles = 0; }
+            b = std::make_shared<EmissionBlock>();
+            b->stride = (L + 1) * kEStride + (L + 1);
+            g_cache[key] = b;
+        } else {
+            b = it->second;
+        }
+    }
+    std::lock_guard<std::mutex> lk(b->m);
+    if (b->n_built < n_max) {
+        const int lo = b->n_built;
+        b->data.resize((size_t)n_max * b->stride, 0.0);
+        auto fill = [&](int a, int e) {
+            for (int n = a + 1; n <= e; n++) {
+                double* E = b->data.data() + (size_t)(n - 1) * b->stride;
+                emission_table(Q, t, w, bin, bw, theta, (unsigned)n, L, E);
+                double* wE = E + (L + 1) * kEStride;
+                for (int d = 0; d <= L; d++) { double acc = 0; for (int i = 0; i < kQ; i++) acc += w[i] * E[d * kEStride + i]; wE[d] = acc; }
+            }
+        };
+        const int total = n_max - lo;
+        const int nthr = std::max(1, std::min(threads, total / 16));
+        if (nthr <= 1) {
+            fill(lo, n_max);
+        } else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nthr; k++) th.emplace_back(fill, lo + (int)((long)total * k / nthr), lo + (int)((long)total * (k + 1) / nthr));
+            for (auto& x : th) x.join();
+        }
+        {
+            std::lock_guard<std::mutex> lk2(g_cache_mutex);
+            g_cache_doubles += (size_t)total * b->stride;
+        }
+        b->n_built = n_max;
+    }
+    return b;
+}
+
 }  // namespace
 
+void clear_table_cache() {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    g_cache.clear(); g_cache_doubles = 0;
+}
+
 bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
-                  const std::vector<double>& r_rates, HostTables& out) {
+                  const std::vector<double>& r_rates, HostTables& out, int threads) {
     if ((Q != 4 && Q != 8 && Q != kQ) || LA < 1 || LB < 1 || n_max < 1 || thetas.size() != r_rates.size()) return false;
+    if (threads <= 0) { const unsigned hw = std::thread::hardware_concurrency(); threads = (int)std::min<unsigned>(hw ? hw : 1, 16); }
     out.lay.init(LA, LB);
     out.n_max = n_max;
     // Q = 4 or 8 (ConditionalSamplingHMM.cpp:39-47): the kernels always sweep 16 intervals; intervals beyond Q carry
@@ -102,7 +195,9 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
     out.quad.assign(kQ + 1, 1E+300);
     for (int i = 0; i <= Q; i++) out.quad[i] = nodes[i];
     out.w.assign(kQ, 0.0);
-    for (int i = 1; i <= Q; i++) out.w[i - 1] = std::exp(-out.quad[i - 1]) - std::exp(-out.quad[i]);   // :63-71
+    double e0[kQ + 1];
+    for (int i = 0; i <= kQ; i++) e0[i] = std::exp(-out.quad[i]);
+    for (int i = 1; i <= Q; i++) out.w[i - 1] = e0[i - 1] - e0[i];   // :63-71
 
     // epochs with identical scaled rates share one table set
     const int T = (int)thetas.size();
@@ -124,28 +219,23 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
     out.y.assign((size_t)out.n_sets * n_max * kQ, 0.0);
     const double* t = out.quad.data(); const double* w = out.w.data();
 
-    auto build_range = [&](int lo, int hi) {
-        for (int idx = lo; idx < hi; idx++) {
-            const int s = idx / n_max, n = idx % n_max + 1;
-            double* row = out.rows.data() + (size_t)idx * lay.row_doubles;
-            double* y = out.y.data() + (size_t)idx * kQ;
-            transition_row(Q, t, w, r_rates[rep[s]], (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
+    for (int s = 0; s < out.n_sets; s++) {
+        const double theta = thetas[rep[s]], r = r_rates[rep[s]];
+        const std::shared_ptr<EmissionBlock> bA = emission_block(Q, LA, theta, n_max, t, w, bin, bw, threads);
+        const std::shared_ptr<EmissionBlock> bB = (LB == LA) ? bA : emission_block(Q, LB, theta, n_max, t, w, bin, bw, threads);
+        for (int n = 1; n <= n_max; n++) {
+            const size_t idx = (size_t)s * n_max + (n - 1);
+            double* row = out.rows.data() + idx * lay.row_doubles;
+            double* y = out.y.data() + idx * kQ;
+            transition_row(Q, t, w, e0, r, (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
             for (int i = 0; i < kQ; i++) row[lay.off_yw + i] = y[i] * w[i];
-            emission_table(Q, t, w, bin, bw, thetas[rep[s]], (unsigned)n, LA, row + lay.off_EA);
-            emission_table(Q, t, w, bin, bw, thetas[rep[s]], (unsigned)n, LB, row + lay.off_EB);
-            for (int d = 0; d <= LA; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EA + d * kEStride + i]; row[lay.off_wEA + d] = a; }
-            for (int d = 0; d <= LB; d++) { double a = 0; for (int i = 0; i < kQ; i++) a += w[i] * row[lay.off_EB + d * kEStride + i]; row[lay.off_wEB + d] = a; }
+            const double* a = bA->data.data() + (size_t)(n - 1) * bA->stride;
+            const double* b = bB->data.data() + (size_t)(n - 1) * bB->stride;
+            std::memcpy(row + lay.off_EA, a, sizeof(double) * (LA + 1) * kEStride);
+            std::memcpy(row + lay.off_EB, b, sizeof(double) * (LB + 1) * kEStride);
+            std::memcpy(row + lay.off_wEA, a + (LA + 1) * kEStride, sizeof(double) * (LA + 1));
+            std::memcpy(row + lay.off_wEB, b + (LB + 1) * kEStride, sizeof(double) * (LB + 1));
         }
-    };
-    const int total = out.n_sets * n_max;
-    unsigned hw = std::thread::hardware_concurrency();
-    int nthr = (int)std::min<unsigned>(hw ? hw : 1, 16);
-    if (total < 64 || nthr <= 1) {
-        build_range(0, total);
-    } else {
-        std::vector<std::thread> th;
-        for (int k = 0; k < nthr; k++) th.emplace_back(build_range, (int)((long)total * k / nthr), (int)((long)total * (k + 1) / nthr));
-        for (auto& x : th) x.join();
     }
     return true;
 }

@@ -967,8 +967,17 @@ int coalo_tables(const coalo_problem* p, int Q, int n_all, int time_idx, double*
 
 double coalo_pismc_classes(const coalo_problem* p, int Q, int gamma, int n_all, int time_idx, int n_classes,
                            const int32_t* counts, const int32_t* dA, const int32_t* dB) {
-    static thread_local std::unique_ptr<Ctx> cache; static thread_local const coalo_problem* cache_for = nullptr;
-    if (!cache || cache_for != p) { cache.reset(new Ctx); if (!init_ctx(*cache, p, Q)) { cache.reset(); return std::nan(""); } cache_for = p; }
+    // The context (lazily built tables) is reused between calls for the same problem AND quadrature. The key is a
+    // fingerprint of what the tables depend on, not the pointer: a freed problem's address can be handed out again.
+    static thread_local std::unique_ptr<Ctx> cache; static thread_local uint64_t cache_key = 0;
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&key](const void* data, size_t bytes) { const unsigned char* b = (const unsigned char*)data; for (size_t i = 0; i < bytes; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+    mix(&Q, sizeof Q); mix(&p->T, sizeof p->T); mix(&p->LA, sizeof p->LA); mix(&p->LB, sizeof p->LB);
+    mix(p->times, sizeof(double) * p->T); mix(p->viral, sizeof(double) * p->T);
+    mix(&p->tau, sizeof(double)); mix(&p->driving_mu, sizeof(double)); mix(&p->driving_lambda, sizeof(double)); mix(&p->driving_rho, sizeof(double));
+    mix(p->type_offsets, sizeof(int32_t) * (p->T + 1));
+    mix(p->type_counts, sizeof(uint32_t) * p->type_offsets[p->T]);
+    if (!cache || cache_key != key) { cache.reset(new Ctx); if (!init_ctx(*cache, p, Q)) { cache.reset(); return std::nan(""); } cache_key = key; }
     Classes k;
     k.cnt.assign(counts, counts + n_classes); k.dA.assign(dA, dA + n_classes); k.dB.assign(dB, dB + n_classes);
     return pismc_classes(*cache, gamma, n_all, time_idx, k);

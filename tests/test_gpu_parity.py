@@ -344,3 +344,46 @@ def test_reference_side_binding_equals_python_mirror(cuda_lib):
         assert np.array_equal(np.array(got["tmrca"]), out.tmrca.ravel())
         for l in range(p.T):
             assert np.array_equal(np.array(got["lineages_remaining"][str(l)]), out.lineages_remaining[l].ravel())
+
+
+def test_batch_pipeline_more_pairs_than_the_window(cuda_lib):
+    """coalgpu_run_sampler_batch keeps at most 32 pairs in flight while host threads prepare the next ones: 70 pairs of
+    mixed shapes (cfg1 and cfg2 data, different grids and T) come back in order and equal to single calls."""
+    import coalescenator_b200 as cb
+    from coalescenator_b200.problem import make_config, sub_problem
+    aln1, loci1, pairs1 = make_config(1)
+    aln2, loci2, pairs2 = make_config(2)
+    probs = []
+    for i in range(35):
+        probs.append(sub_problem(aln1, loci1, *pairs1[i % len(pairs1)], target_mu=[1e-5, 2e-5 + 1e-6 * i]))
+        probs.append(sub_problem(aln2, loci2, *pairs2[(7 * i) % len(pairs2)], target_lambda=[400.0 + i, 900.0, 1500.0]))
+    smp = cb.ImportanceSampler()
+    batch = smp.run_sampler_batch(probs, 96, seed=11)
+    assert len(batch) == 70
+    for k in (0, 1, 31, 32, 33, 64, 69):
+        one = smp.run_sampler(probs[k], 96, seed=11)
+        np.testing.assert_array_equal(batch[k].likelihood, one.likelihood)
+        np.testing.assert_array_equal(batch[k].lineages_remaining, one.lineages_remaining)
+        assert batch[k].n_events == one.n_events and batch[k].n_pismc == one.n_pismc
+    # an invalid pair anywhere in the batch is reported before anything runs
+    bad = sub_problem(aln1, loci1, *pairs1[0])
+    bad.times = list(bad.times); bad.times[-1] = bad.times[0]
+    with pytest.raises(cb.CoalGpuError) as e:
+        smp.run_sampler_batch(probs[:3] + [bad], 10, seed=1)
+    assert e.value.code == -1
+
+
+def test_samplers_with_different_quadrature_coexist(oracle, cuda_lib):
+    """Interval weights belong to the sampler (they depend on quadrature_points): creating a Q = 4 sampler must not
+    change what an existing Q = 16 sampler computes."""
+    import torch
+    p, _, _ = load_golden("cfg1_pair0")
+    s16 = _sampler(p, 16)
+    s4 = _sampler(p, 4)
+    for s, Q in ((s16, 16), (s4, 4), (s16, 16)):
+        buf = s.alloc(32)
+        s.sample(buf, 23, 0, 32)
+        torch.cuda.synchronize()
+        ref = oracle.run(p, 32, 23, mode=oracle.MODE_CANONICAL, Q=Q)
+        np.testing.assert_allclose(buf["weights"].cpu().numpy(), ref["weights"], rtol=RTOL_WEIGHT)
+    s16.close(); s4.close()
