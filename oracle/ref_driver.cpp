@@ -120,6 +120,24 @@ int main(int argc, char** argv) {
 #endif
     printf("{\n\"impl\": \"%s\", \"n_samples\": %u, \"n_threads\": %u, \"seed\": %u, \"seconds\": %.6f,\n", impl, n_samples, n_threads, seed, secs);
     printf("\"dims\": [%u, %u, %u], \"T\": %u,\n", res.likelihood().dim1(), res.likelihood().dim2(), res.likelihood().dim3(), p.T);
+#ifdef COALREF_GPU_BINDING
+    {   // the order in which the binding walked the reference's unordered_maps (the sampler's draws depend on it)
+        std::vector<AncestralTypeMaps> maps = sample.getTypeMaps();
+        printf("\"type_order\": [");
+        for (size_t t = 0; t < maps.size(); t++) {
+            printf("%s[", t ? ", " : "");
+            bool first = true;
+            TypeMap* ms[3] = {&maps[t].A, &maps[t].B, &maps[t].C};
+            for (int g = 0; g < 3; g++) for (TypeMap::iterator it = ms[g]->begin(); it != ms[g]->end(); ++it) {
+                std::string bits; for (size_t k = 0; k < it->first.size(); k++) bits += it->first[k] ? '1' : '0';
+                printf("%s[\"%c\", \"%s\", %u]", first ? "" : ", ", "ABC"[g], bits.c_str(), it->second);
+                first = false;
+            }
+            printf("]");
+        }
+        printf("],\n");
+    }
+#endif
     print_grid("likelihood", res.likelihood(), false);
     print_grid("likelihoodSq", res.likelihoodSq(), false);
     print_grid("tmrca", res.tmrca(), false);

@@ -323,27 +323,37 @@ def test_fewer_quadrature_points_histories(oracle, cuda_lib, Q):
 def test_reference_side_binding_equals_python_mirror(cuda_lib):
     """The binding a reference maintainer would add (include/GpuImportanceSampler.hpp: Sample/ModelParameters ->
     coalgpu_run_sampler -> SamplerOutput<double>) compiled against the reference's headers and driven by the reference
-    driver: the grids it returns through the reference's own Matrix3d are those of the Python mirror, bit for bit,
-    and agree with the CPU reference's golden result within Monte-Carlo error."""
-    import json, os, subprocess
+    driver. The binding walks the reference's unordered_maps, so its type order differs from the file's (and the draws
+    depend on the order): with the Python problem put into the order the binding reports, the grids it returns through
+    the reference's own Matrix3d are those of the Python mirror bit for bit; in file order they agree within
+    Monte-Carlo error."""
+    import copy, json, os, subprocess
     import coalescenator_b200 as cb
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "oracle", "_ref", "coalref_gpu")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/coalref_gpu not built")
-    for name, n, seed in (("cfg1_pair0", 3000, 5), ("grid_pair5", 2000, 9)):
+    for name, n, seed in (("cfg1_pair0", 20000, 5), ("grid_pair5", 20000, 9)):
         p, _, _ = load_golden(name)
         r = subprocess.run([exe, os.path.join(root, "tests", "golden", name + ".coalprob"), str(n), "1", str(seed)],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         got = json.loads(r.stdout)
         assert got["impl"] == "reference-binding-gpu"
-        out = cb.ImportanceSampler().run_sampler(p, n, seed=seed)
+        q = copy.deepcopy(p)
+        q.types = [[("ABC".index(g), p.word("ABC".index(g), bits), c) for g, bits, c in tp] for tp in got["type_order"]]
+        assert [sorted(tp) for tp in q.types] == [sorted(tp) for tp in p.types]
+        out = cb.ImportanceSampler().run_sampler(q, n, seed=seed)
         assert np.array_equal(np.array(got["likelihood"]), out.likelihood.ravel())
         assert np.array_equal(np.array(got["likelihoodSq"]), out.likelihoodSq.ravel())
         assert np.array_equal(np.array(got["tmrca"]), out.tmrca.ravel())
         for l in range(p.T):
             assert np.array_equal(np.array(got["lineages_remaining"][str(l)]), out.lineages_remaining[l].ravel())
+        # file order: another Monte-Carlo sample of the same estimator
+        alt = cb.ImportanceSampler().run_sampler(p, n, seed=seed)
+        ok = alt.ess.ravel() >= 10
+        se = np.hypot(alt.standard_error().ravel(), out.standard_error().ravel())
+        assert ok.any() and np.all(np.abs(alt.likelihood.ravel() - out.likelihood.ravel())[ok] < 5 * se[ok])
 
 
 def test_batch_pipeline_more_pairs_than_the_window(cuda_lib):
