@@ -54,12 +54,22 @@ cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream = 0) {
 }
 void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
 
-template <class T>
-int upload(const std::vector<T>& v, T** out) {
-    *out = nullptr;
-    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    CU_OK(dev_alloc((void**)out, bytes));
-    if (!v.empty()) CU_OK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+// The dynamic shared memory limit is a property of the kernel function, not of a launch: raise it to the device's
+// opt-in maximum once per device for every instantiation. (Changing it per launch serialises against the launches of
+// the same function that are still running -- measured: it made the pairs of a batch run one after another.)
+int ensure_kernel_attributes(int device) {
+    static std::atomic<unsigned long long> done{0};
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done.load() & bit) return 0;
+    int optin = 0;
+    CU_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    for (int W : {8, 16, 32}) for (int narrow = 0; narrow < 2; narrow++) {
+        const void* fn = (const void*)history_kernel_select(W, narrow != 0);
+        cudaFuncAttributes fa;
+        CU_OK(cudaFuncGetAttributes(&fa, fn));            // static shared memory (problem constants) counts against the limit
+        CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    }
+    done.fetch_or(bit);
     return 0;
 }
 
@@ -216,7 +226,9 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
 }
 
 // Device half of coalgpu_create: checks the device, uploads what prepare_host built, picks the launch geometry.
-int finish_device(HostPrep& h, int device, coalgpu_sampler** out) {
+// Everything goes into ONE stream-ordered allocation filled by asynchronous copies on `up`; nothing here waits for
+// kernels of other samplers. The caller orders its launches after `up` (stream wait or synchronize).
+int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** out) {
     if (int rc = device_check(device)) return rc;
     CU_OK(cudaSetDevice(device));
     // cudaGetDeviceProperties costs tens of milliseconds per call; two attributes are all that is needed
@@ -224,6 +236,7 @@ int finish_device(HostPrep& h, int device, coalgpu_sampler** out) {
     CU_OK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
     CU_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     if (cc_major != 10) return fail(COALGPU_ENODEV, "this library carries sm_100a code only (Blackwell B200 required)");
+    if (int rc = ensure_kernel_attributes(device)) return rc;
 
     coalgpu_sampler* s = new coalgpu_sampler;
     s->device = device; s->T = h.T; s->LA = h.LA; s->LB = h.LB; s->G = h.G;
@@ -231,19 +244,40 @@ int finish_device(HostPrep& h, int device, coalgpu_sampler** out) {
     s->tab = std::move(h.tab);
     DevProblem& P = s->P;
 
-    int rc = 0;
-    double* d_rows; int* d_set; double* d_times; EpochConst* d_ep; GridConst* d_grid; double* d_lf; double* d_rcp; int* d_toff;
-    unsigned long long* d_tw; unsigned int* d_tcg;
-#define UP(vec, ptr) do { rc = upload(vec, &ptr); if (rc) { coalgpu_destroy(s); return rc; } s->allocs.push_back(ptr); } while (0)
-    UP(s->tab.rows, d_rows); UP(s->tab.set_of_epoch, d_set); UP(h.times, d_times); UP(h.ep, d_ep); UP(h.grid, d_grid);
-    UP(h.lfact, d_lf); UP(h.rcp, d_rcp); UP(h.type_off, d_toff); UP(h.type_w, d_tw); UP(h.type_cg, d_tcg);
-#undef UP
-    P.rows = d_rows; P.set_of_epoch = d_set; P.times = d_times; P.ep = d_ep; P.grid = d_grid; P.lfact = d_lf; P.rcp = d_rcp;
-    P.type_off = d_toff; P.type_w = d_tw; P.type_cg = d_tcg;
-    CU_OK(dev_alloc((void**)&s->d_counters, 8 * sizeof(unsigned long long)));
-    s->allocs.push_back(s->d_counters);
-    CU_OK(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), 0));
-    CU_OK(cudaStreamSynchronize(0));   // uploads and the memset are complete before any stream uses the sampler
+    // arena layout (every part 256-byte aligned: the table rows are the source of bulk copies)
+    size_t off = 0;
+    auto place = [&off](size_t bytes) { const size_t o = off; off += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return o; };
+    const size_t o_rows = place(s->tab.rows.size() * sizeof(double)), o_set = place(s->tab.set_of_epoch.size() * sizeof(int));
+    const size_t o_times = place(h.times.size() * sizeof(double)), o_ep = place(h.ep.size() * sizeof(EpochConst));
+    const size_t o_grid = place(h.grid.size() * sizeof(GridConst)), o_lf = place(h.lfact.size() * sizeof(double));
+    const size_t o_rcp = place(h.rcp.size() * sizeof(double)), o_toff = place(h.type_off.size() * sizeof(int));
+    const size_t o_tw = place(h.type_w.size() * sizeof(unsigned long long)), o_tcg = place(h.type_cg.size() * sizeof(unsigned int));
+    const size_t o_cnt = place(8 * sizeof(unsigned long long));
+    char* base = nullptr;
+    {
+        cudaError_t e = dev_alloc((void**)&base, off, up);
+        if (e != cudaSuccess) { delete s; return fail(e == cudaErrorMemoryAllocation ? COALGPU_ENOMEM : COALGPU_ECUDA, std::string("device arena: ") + cudaGetErrorString(e)); }
+    }
+    s->allocs.push_back(base);
+    cudaError_t ue = cudaSuccess;
+    auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes && ue == cudaSuccess) ue = cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, up); };
+    put(o_rows, s->tab.rows.data(), s->tab.rows.size() * sizeof(double));
+    put(o_set, s->tab.set_of_epoch.data(), s->tab.set_of_epoch.size() * sizeof(int));
+    put(o_times, h.times.data(), h.times.size() * sizeof(double));
+    put(o_ep, h.ep.data(), h.ep.size() * sizeof(EpochConst));
+    put(o_grid, h.grid.data(), h.grid.size() * sizeof(GridConst));
+    put(o_lf, h.lfact.data(), h.lfact.size() * sizeof(double));
+    put(o_rcp, h.rcp.data(), h.rcp.size() * sizeof(double));
+    put(o_toff, h.type_off.data(), h.type_off.size() * sizeof(int));
+    put(o_tw, h.type_w.data(), h.type_w.size() * sizeof(unsigned long long));
+    put(o_tcg, h.type_cg.data(), h.type_cg.size() * sizeof(unsigned int));
+    if (ue == cudaSuccess) ue = cudaMemsetAsync(base + o_cnt, 0, 8 * sizeof(unsigned long long), up);
+    if (ue != cudaSuccess) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, std::string("upload: ") + cudaGetErrorString(ue)); }
+    P.rows = (const double*)(base + o_rows); P.set_of_epoch = (const int*)(base + o_set); P.times = (const double*)(base + o_times);
+    P.ep = (const EpochConst*)(base + o_ep); P.grid = (const GridConst*)(base + o_grid); P.lfact = (const double*)(base + o_lf);
+    P.rcp = (const double*)(base + o_rcp); P.type_off = (const int*)(base + o_toff);
+    P.type_w = (const unsigned long long*)(base + o_tw); P.type_cg = (const unsigned int*)(base + o_tcg);
+    s->d_counters = (unsigned long long*)(base + o_cnt);
 
     // launch geometry: persistent CTAs of kCtaThreads threads = kCtaThreads/W groups of W lanes, one history per group.
     // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
@@ -254,7 +288,6 @@ int finish_device(HostPrep& h, int device, coalgpu_sampler** out) {
         smem = gb * (kCtaThreads / W); occ = 0;
         if (smem > 227 * 1024) return -1;
         const void* fn = (const void*)history_kernel_select(W, P.Ltot <= 32);
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem) != cudaSuccess) return -1;
         return occ * (kCtaThreads / W);
     };
@@ -303,7 +336,11 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     if ((rc = device_check(device))) return rc;
     rc = prepare_host(p, Q, 0, h, err);
     if (rc) return fail(rc, err);
-    return finish_device(h, device, out);
+    rc = finish_device(h, device, 0, out);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(0);   // uploads complete: the sampler may be used on any stream
+    if (e != cudaSuccess) { coalgpu_destroy(*out); *out = nullptr; return fail(COALGPU_ECUDA, std::string("upload: ") + cudaGetErrorString(e)); }
+    return 0;
 }
 
 int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
@@ -323,9 +360,7 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     int grid = s->grid;
     const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
-    // the attribute is per function, not per sampler: samplers of different problem sizes share the kernel
-    history_kernel_fn kfn = history_kernel_select(s->group, s->P.Ltot <= 32);
-    CU_OK(cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    history_kernel_fn kfn = history_kernel_select(s->group, s->P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
     kfn<<<grid, kCtaThreads, s->smem_bytes, st>>>(s->P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
@@ -499,19 +534,34 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     constexpr int kWindow = 32, kStreams = 16;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const int lookahead = (int)std::min<unsigned>(std::max(2u, hw), 32u);   // pairs being prepared ahead of the GPU
-    struct Prep { HostPrep h; int rc = 0; std::string err; };
+    struct Prep { coalgpu_sampler* s = nullptr; int rc = 0; std::string err; };
     struct Job {
         coalgpu_sampler* s = nullptr;
         double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
         double* h_p = nullptr;            // slot of the pinned slab: partials [nstat*G*2] then 8 counters
         size_t np = 0;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, eu = nullptr;
         int index = -1;
     };
     auto is_big = [&](const coalgpu_problem* p) {   // a pair whose weight matrix is large fills the device on its own
         const size_t G = (size_t)p->n_mu * p->n_rho * p->n_lambda;
         return n_samples * (G + p->T + 1) * 8 > (256ull << 20);
     };
+    // Streams first: the workers upload on `up`. A pageable host-to-device copy blocks its caller until the stream gets
+    // to it, and streams share hardware queues with each other (8 by default), so a copy can sit behind a running
+    // kernel of another pair: that wait lands on a worker thread here, never on the thread that feeds the GPU.
+    cudaStream_t streams[kStreams] = {}, up = nullptr;
+    {
+        cudaError_t e = cudaSetDevice(device);
+        for (int i = 0; i < kStreams && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+        int arc = e == cudaSuccess ? ensure_kernel_attributes(device) : 0;
+        if (e != cudaSuccess || arc) {
+            for (int i = 0; i < kStreams; i++) if (streams[i]) cudaStreamDestroy(streams[i]);
+            if (up) cudaStreamDestroy(up);
+            return e != cudaSuccess ? fail(COALGPU_ECUDA, std::string("stream creation: ") + cudaGetErrorString(e)) : arc;
+        }
+    }
     std::vector<std::future<std::unique_ptr<Prep>>> preps(n_problems);
     int next_prep = 0;
     auto schedule = [&](int upto) {
@@ -519,22 +569,22 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             const coalgpu_problem* p = problems + next_prep;
             if (is_big(p)) continue;
             // one table thread per pair: the pairs are the parallel axis here
-            auto work = [p, Q]() {
+            auto work = [p, Q, device, up]() {
                 std::unique_ptr<Prep> r(new Prep);
-                r->rc = prepare_host(p, Q, 1, r->h, r->err);
+                HostPrep h;
+                r->rc = prepare_host(p, Q, 1, h, r->err);
+                if (!r->rc) { r->rc = finish_device(h, device, up, &r->s); if (r->rc) r->err = g_err; }
                 return r;
             };
             try { preps[next_prep] = std::async(std::launch::async, work); }
             catch (...) { preps[next_prep] = std::async(std::launch::deferred, work); }   // no thread to be had: prepare on demand
         }
     };
-    cudaStream_t streams[kStreams] = {};
-    int n_streams = 0;
     int rc = 0; std::string err;
     std::vector<Job> window;
     auto release = [&](Job& j) {
         dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p);
-        if (j.e0) cudaEventDestroy(j.e0); if (j.e1) cudaEventDestroy(j.e1);
+        if (j.e0) cudaEventDestroy(j.e0); if (j.e1) cudaEventDestroy(j.e1); if (j.eu) cudaEventDestroy(j.eu);
         if (j.s) coalgpu_destroy(j.s);
         j = Job();
     };
@@ -564,9 +614,16 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     if (slot_doubles) {
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = cudaMallocHost((void**)&slab, slot_doubles * kWindow * sizeof(double));
-        if (e != cudaSuccess) return fail(COALGPU_ECUDA, std::string("pinned host buffer: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
+            cudaStreamDestroy(up);
+            return fail(COALGPU_ECUDA, std::string("pinned host buffer: ") + cudaGetErrorString(e));
+        }
     }
     long launched = 0;
+    const bool timing = std::getenv("COALGPU_TIMING") != nullptr;
+    auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_wait_prep = 0, t_finish = 0, t_alloc = 0, t_launch = 0, t_retire = 0; const double t_start = tick();
     schedule(lookahead);
     for (int k = 0; k < n_problems && !rc; k++) {
         const coalgpu_problem* p = problems + k;
@@ -576,17 +633,23 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             schedule(k + 1 + lookahead);
             continue;
         }
+        double t0 = tick();
         std::unique_ptr<Prep> pr = preps[k].get();
         schedule(k + 1 + lookahead);
+        t_wait_prep += tick() - t0; t0 = tick();
         if (pr->rc) { rc = pr->rc; err = pr->err; break; }
         if ((int)window.size() == kWindow) { retire(window.front()); window.erase(window.begin()); if (rc) break; }
+        t_retire += tick() - t0; t0 = tick();
         window.emplace_back();
         Job& j = window.back();
         j.index = k;
-        rc = finish_device(pr->h, device, &j.s);
-        if (rc) { err = g_err; break; }
-        if (n_streams == 0) { for (int i = 0; i < kStreams; i++) WB_OK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)); n_streams = kStreams; }
         cudaStream_t st = streams[k % kStreams];
+        j.s = pr->s; pr->s = nullptr;
+        WB_OK(cudaEventCreateWithFlags(&j.eu, cudaEventDisableTiming));
+        if (rc) break;
+        WB_OK(cudaEventRecord(j.eu, up));
+        WB_OK(cudaStreamWaitEvent(st, j.eu, 0));     // the pair's stream starts after its upload
+        t_finish += tick() - t0; t0 = tick();
         const int T = j.s->T; const size_t G = j.s->G;
         j.np = (size_t)(3 + T) * G * 2;
         WB_OK(cudaMallocAsync((void**)&j.d_w, n_samples * G * sizeof(double), st));
@@ -596,20 +659,31 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         j.h_p = slab + (size_t)(launched++ % kWindow) * slot_doubles;   // free again: its previous user was retired above
         WB_OK(cudaEventCreate(&j.e0)); WB_OK(cudaEventCreate(&j.e1));
         if (rc) break;
+        t_alloc += tick() - t0; t0 = tick();
         WB_OK(cudaEventRecord(j.e0, st));
+        // Full grid per pair (one history per group when n_samples is small). Capping the grid so that every group pulls
+        // several histories was measured 25 % slower: only ~8 kernels run side by side (hardware queues), so smaller grids
+        // leave SMs empty (profiles/r1_batch_pipeline.md).
         rc = coalgpu_sample(j.s, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0);
         if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
         if (rc) { err = g_err; break; }
         WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, st));
         WB_OK(cudaEventRecord(j.e1, st));
+        t_launch += tick() - t0;
     }
+    const double t_loop = tick();
     if (rc) cudaDeviceSynchronize();       // error path: nothing may still be running on buffers that are about to be freed
     for (Job& j : window) retire(j);
 #undef WB_OK
-    for (int k = 0; k < n_problems; k++) if (preps[k].valid()) preps[k].wait();   // no worker may outlive the call
-    if (n_streams) { cudaDeviceSynchronize(); for (int i = 0; i < n_streams; i++) cudaStreamDestroy(streams[i]); }
+    for (int k = 0; k < n_problems; k++)       // no worker may outlive the call; samplers that were never launched go away
+        if (preps[k].valid()) { std::unique_ptr<Prep> pr = preps[k].get(); if (pr && pr->s) { cudaStreamSynchronize(up); coalgpu_destroy(pr->s); } }
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kStreams; i++) cudaStreamDestroy(streams[i]);
+    cudaStreamDestroy(up);
     if (slab) cudaFreeHost(slab);
+    if (timing) fprintf(stderr, "coalgpu_run_sampler_batch: %d pairs, %.1f ms total: wait for host preparation + upload %.1f, retire (in loop) %.1f, stream order %.1f, alloc %.1f, launch %.1f, drain %.1f ms\n",
+                        n_problems, 1e3 * (tick() - t_start), 1e3 * t_wait_prep, 1e3 * t_retire, 1e3 * t_finish, 1e3 * t_alloc, 1e3 * t_launch, 1e3 * (tick() - t_loop));
     if (rc) return fail(rc, err);
     return 0;
 }
