@@ -3,7 +3,10 @@
 // where the reference calls ImportanceSampler::runSampler (main.cpp:281-283).
 //
 // Same options as the reference (main.cpp:54-88); additions: --device N, --dump-problems DIR (write one
-// .coalprob file per eligible locus pair and stop: needs no GPU), --ess (append an ESS column).
+// .coalprob file per eligible locus pair and stop: needs no GPU), --ess (append an ESS column), --summary (side-car
+// <prefix>_summary.txt: the grid point that maximises the composite likelihood, per-pair work and ESS, throughput).
+#include <chrono>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +34,7 @@ struct Options {
     std::string scale_list = "250,500,750,1000,2000,4000";
     std::string rho_list = "1e-10,1e-9,1e-8,1e-7,1e-6,5e-6,1e-5,5e-5,1e-4,5e-4,1e-3";
     double generation_time = 0, mutation_driving = 2.5e-5, scale_driving = 1000, rho_driving = 5e-5;
-    bool have_coords = false, have_generation_time = false, ess = false;
+    bool have_coords = false, have_generation_time = false, ess = false, summary = false;
     int device = 0;
     std::string dump_dir;
 };
@@ -49,7 +52,7 @@ void usage() {
               << "  --coordinate-list [l-r],... | bp1,bp2   --loci-size N (1)\n"
               << "  -i [ --mc-samples ] N (500000)  --mutation-list L  --mutation-driving X (2.5e-5)  --scale-list L  --scale-driving X (1000)\n"
               << "  --rho-list L  --rho-driving X (5e-5)  --min-comp-dist N (1)  --max-comp-dist N (400)\n"
-              << "  --dump-problems DIR  --ess\n";
+              << "  --dump-problems DIR  --ess  --summary\n";
 }
 
 Options parse(int argc, char** argv) {
@@ -63,6 +66,7 @@ Options parse(int argc, char** argv) {
         if (alias.count(k)) k = alias[k];
         if (k == "--help") { usage(); exit(1); }
         if (k == "--ess") { o.ess = true; continue; }
+        if (k == "--summary") { o.summary = true; continue; }
         if (v.empty() && eq == std::string::npos) { if (i + 1 >= argc) throw std::runtime_error("the required argument for option '" + k + "' is missing"); v = argv[++i]; }
         if (k == "--num-threads") o.num_threads = (unsigned)std::stoul(v);
         else if (k == "--seed") o.seed = (unsigned)std::stoul(v);
@@ -180,6 +184,9 @@ int main(int argc, char** argv) {
         // Sub-samples of all eligible pairs first (main.cpp:254-279), then ONE batched call: the pairs run
         // concurrently on the GPU instead of one after another (coalgpu_run_sampler_batch), rows are written in
         // the reference's order afterwards.
+        struct PairStat { unsigned long long events, pismc; double ess_min, ess_max; };
+        std::vector<PairStat> pair_stats;
+        double sampling_seconds = 0.0;
         struct Job { PairProblem sp; std::vector<double> rho_scaled; double drho; std::string l1, l2;
                      std::vector<double> like, likesq, tm, lin, ess; };
         std::vector<Job> jobs(pairs.size());
@@ -223,8 +230,17 @@ int main(int argc, char** argv) {
                 j.like.resize(G); j.likesq.resize(G); j.tm.resize(G); j.lin.resize(G * T); j.ess.resize(G);
                 results[q] = coalgpu_result{j.like.data(), j.likesq.data(), j.tm.data(), j.lin.data(), j.ess.data(), 0, 0, 0, 0.0};
             }
+            const auto tb0 = std::chrono::steady_clock::now();
             const int rc = coalgpu_run_sampler_batch((int)probs.size(), probs.data(), o.mc_samples, 16, o.seed, o.device, results.data());   // replaces :281-283
             if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+            sampling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
+            for (size_t q = 0; q < jobs.size(); q++) {
+                PairStat st;
+                st.events = results[q].n_events; st.pismc = results[q].n_pismc;
+                st.ess_min = *std::min_element(jobs[q].ess.begin(), jobs[q].ess.end());
+                st.ess_max = *std::max_element(jobs[q].ess.begin(), jobs[q].ess.end());
+                pair_stats.push_back(st);
+            }
             for (size_t q = 0; q < jobs.size(); q++) {
                 const Job& j = jobs[q];
                 const int T = (int)j.sp.times.size();
@@ -251,6 +267,22 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < nmu; i++) for (size_t j = 0; j < nrho; j++) for (size_t k = 0; k < nlam; k++, g++)
             comp << mu_list[i] << "\t" << rho_list[j] << "\t" << lambda_list[k] << "\t" << composite[g] << "\t" << std::exp(mean_tmrca[g] - norm) << "\n";
         comp.close();
+
+        if (o.summary) {        // not in the reference: diagnostics next to the two result files
+            std::ofstream sm((o.prefix + "_summary.txt").c_str());
+            if (!sm.is_open()) throw std::runtime_error("cannot open the summary output file");
+            size_t best = 0;
+            for (size_t q = 1; q < G; q++) if (composite[q] > composite[best]) best = q;
+            const size_t bi = best / (nrho * nlam), bj = (best / nlam) % nrho, bk = best % nlam;
+            sm << "composite_maximum\tmu\t" << mu_list[bi] << "\trho\t" << rho_list[bj] << "\tlambda\t" << lambda_list[bk] << "\tloglikelihood\t" << composite[best]
+               << "\ton_grid_edge\t" << (((nmu > 1 && (bi == 0 || bi + 1 == nmu)) || (nrho > 1 && (bj == 0 || bj + 1 == nrho)) || (nlam > 1 && (bk == 0 || bk + 1 == nlam))) ? 1 : 0) << "\n";
+            sm << "pairs\t" << jobs.size() << "\tsamples_per_pair\t" << o.mc_samples << "\tsampling_seconds\t" << sampling_seconds << "\thistories_per_second\t"
+               << (sampling_seconds > 0 ? (double)jobs.size() * (double)o.mc_samples / sampling_seconds : 0.0) << "\n";
+            sm << "locus1\tlocus2\tevents_per_history\tpismc_per_history\tess_min\tess_max\n";
+            for (size_t q = 0; q < jobs.size(); q++)
+                sm << jobs[q].l1 << "\t" << jobs[q].l2 << "\t" << (double)pair_stats[q].events / (double)o.mc_samples << "\t" << (double)pair_stats[q].pismc / (double)o.mc_samples
+                   << "\t" << pair_stats[q].ess_min << "\t" << pair_stats[q].ess_max << "\n";
+        }
     } catch (std::exception& e) {
         std::cerr << "ERROR: " << e.what() << std::endl;                              // :343-346
         return 1;

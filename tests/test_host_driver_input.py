@@ -145,7 +145,7 @@ def test_host_driver_end_to_end_outputs(tmp_path):
     dump = tmp_path / "dump"; dump.mkdir()
     assert subprocess.run([HOST] + common + ["--dump-problems", str(dump)], capture_output=True).returncode == 0
     prefix = str(tmp_path / "run")
-    r = subprocess.run([HOST] + common + ["--output-file-prefix", prefix], capture_output=True, text=True)
+    r = subprocess.run([HOST] + common + ["--output-file-prefix", prefix, "--summary"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "Coalescenated succesfully." in r.stdout
     rows = [l.rstrip("\n").split("\t") for l in open(prefix + "_pairwise_loglikelihood.txt")]
@@ -171,3 +171,9 @@ def test_host_driver_end_to_end_outputs(tmp_path):
     # composite = sum over pairs of the pairwise log-likelihoods (main.cpp:285)
     tot = sum(float(x[5]) for x in rows[1:] if (x[2], x[3], x[4]) == (rows[1][2], rows[1][3], rows[1][4]))
     assert float(comp[1][3]) == pytest.approx(tot, rel=1e-4)
+    # --summary side-car: the composite maximum is the arg-max of the composite file
+    summ = [l.rstrip("\n").split("\t") for l in open(prefix + "_summary.txt")]
+    assert summ[0][0] == "composite_maximum" and summ[1][0] == "pairs" and int(summ[1][1]) == len(problems)
+    best = max(comp[1:], key=lambda c: float(c[3]))
+    assert (summ[0][2], summ[0][4], summ[0][6]) == (best[0], best[1], best[2])
+    assert len(summ) == 3 + len(problems) and all(float(x[4]) >= 1.0 - 1e-9 for x in summ[3:])
