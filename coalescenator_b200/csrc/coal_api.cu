@@ -86,6 +86,11 @@ struct coalgpu_sampler {
     size_t block_partials_cap = 0;
     int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history (16 or 32)
     size_t smem_bytes = 0;
+    // reduced-capacity first pass (see finish_device): same problem with a smaller type store
+    bool fast = false;
+    DevProblem P_fast{};
+    int fast_grid = 0, fast_group = 32;
+    size_t fast_smem = 0;
     unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
     // K2 scratch smem
     size_t k2_smem = 0;
@@ -283,25 +288,64 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
     // The width that keeps more histories in flight per SM wins (shared memory per group grows with the
     // lineage bound: 200 sequences need ~15 KB per group and W = 16 would leave one CTA per SM).
-    auto geometry = [&](int W, size_t& smem, int& occ) -> int {
-        const size_t gb = history_group_bytes(P.kmax, P.pvmax, P.Ltot, W);
-        smem = gb * (kCtaThreads / W); occ = 0;
-        if (smem > 227 * 1024) return -1;
-        const void* fn = (const void*)history_kernel_select(W, P.Ltot <= 32);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem) != cudaSuccess) return -1;
-        return occ * (kCtaThreads / W);
+    struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; };
+    auto geometry_for = [&](int kmax, int pvmax) -> Geometry {
+        Geometry best;
+        for (int W : {32, 16}) {
+            if (W == 16 && P.Ltot + 1 > 16) continue;
+            const size_t smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (kCtaThreads / W);
+            int occ = 0;
+            if (smem > 227 * 1024) continue;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)history_kernel_select(W, P.Ltot <= 32), kCtaThreads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+            const int per_sm = occ * (kCtaThreads / W);
+            if (per_sm > best.per_sm) { best.group = W; best.occ = occ; best.per_sm = per_sm; best.smem = smem; }   // ties keep W = 32
+        }
+        if (const char* g = std::getenv("COALGPU_GROUP")) {
+            const int W = std::atoi(g);
+            if (W == 8 || W == 16 || W == 32) {
+                Geometry f; f.group = W; f.smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (kCtaThreads / W);
+                if (f.smem <= 227 * 1024 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f.occ, (const void*)history_kernel_select(W, P.Ltot <= 32), kCtaThreads, f.smem) == cudaSuccess) {
+                    f.per_sm = f.occ * (kCtaThreads / W);
+                    if (f.per_sm > 0) best = f;
+                } else cudaGetLastError();
+            }
+        }
+        return best;
     };
-    size_t smem16 = 0, smem32 = 0; int occ16 = 0, occ32 = 0;
-    const int g16 = (P.Ltot + 1 <= 16) ? geometry(16, smem16, occ16) : -1;
-    const int g32 = geometry(32, smem32, occ32);
-    s->group = (g16 > g32) ? 16 : 32;
-    if (const char* g = std::getenv("COALGPU_GROUP")) { const int v = std::atoi(g); if (v == 8 || v == 16 || v == 32) s->group = v; }
-    size_t smem = 0; int occ = 0;
-    if (geometry(s->group, smem, occ) < 1) { cudaGetLastError(); coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
+    const Geometry full = geometry_for(P.kmax, P.pvmax);
+    if (full.per_sm < 1) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
+    s->group = full.group; s->smem_bytes = full.smem; s->grid = sm_count * full.occ;
     s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
-    s->smem_bytes = smem;
     P.warp_bytes = s->warp_bytes;
-    s->grid = sm_count * occ;
+
+    // Two-pass capacity scheme. kmax is the worst case (every sampled two-locus lineage split by recombination and all
+    // types distinct); real histories hold far fewer distinct types. When a smaller type store lets more histories run
+    // per SM, the first pass uses it and defers the rare history that outgrows it to a second pass with the full store;
+    // a history's draws depend on (seed, index) only, so the results do not depend on the scheme.
+    {
+        int inj_max = 0;
+        for (int t = 0; t < h.T; t++) inj_max = std::max(inj_max, h.type_off[t + 1] - h.type_off[t]);
+        int forced = 0;
+        if (const char* e = std::getenv("COALGPU_KMAX_FAST")) forced = std::atoi(e);
+        Geometry bestf = full; int best_k = 0;
+        for (int kf : {256, 128, 64}) {       // descending: the largest store among those that reach an occupancy level
+            if (forced > 0) kf = ((forced + 7) / 8) * 8;          // tests force small stores so that histories ARE deferred
+            if (kf >= P.kmax || (forced <= 0 && kf < 2 * inj_max + 8)) { if (forced > 0) break; continue; }
+            int pvf = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + kf + 1); pvf = (pvf + 1) & ~1;
+            const Geometry g = geometry_for(kf, pvf);
+            if (g.per_sm > bestf.per_sm || (forced > 0 && g.per_sm > 0)) { bestf = g; best_k = kf; }
+            if (forced > 0) break;
+        }
+        if (best_k > 0 && forced >= 0) {
+            s->fast = true;
+            s->P_fast = P;
+            s->P_fast.kmax = best_k;
+            int pvf = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + best_k + 1); pvf = (pvf + 1) & ~1;
+            s->P_fast.pvmax = pvf;
+            s->fast_group = bestf.group; s->fast_smem = bestf.smem; s->fast_grid = sm_count * bestf.occ;
+            s->P_fast.warp_bytes = (int)history_group_bytes(best_k, pvf, P.Ltot, bestf.group);
+        }
+    }
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
     return 0;
@@ -351,20 +395,36 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     CU_OK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU_OK(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st));
+    CU_OK(cudaMemsetAsync(s->d_counters + 6, 0, 2 * sizeof(unsigned long long), st));
     SampleArgs a{};
     a.seed = seed; a.first = first; a.n = n;
     a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
     a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
     a.counters = s->d_counters;
-    const int groups_per_cta = kCtaThreads / s->group;
-    int grid = s->grid;
-    const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
-    if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
-    history_kernel_fn kfn = history_kernel_select(s->group, s->P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
-    kfn<<<grid, kCtaThreads, s->smem_bytes, st>>>(s->P, a);
-    g_launches++;
-    CU_OK(cudaGetLastError());
-    return 0;
+    auto launch = [&](const DevProblem& P, const SampleArgs& args, int group, int full_grid, size_t smem) -> int {
+        const int groups_per_cta = kCtaThreads / group;
+        int grid = full_grid;
+        const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
+        if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
+        history_kernel_fn kfn = history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+        kfn<<<grid, kCtaThreads, smem, st>>>(P, args);
+        g_launches++;
+        CU_OK(cudaGetLastError());
+        return 0;
+    };
+    if (!s->fast) return launch(s->P, a, s->group, s->grid, s->smem_bytes);
+    // first pass with the reduced type store, second pass (full store) over the histories it deferred: usually none,
+    // then its CTAs find the list empty and leave
+    unsigned long long* d_defer = nullptr;
+    CU_OK(dev_alloc((void**)&d_defer, n * sizeof(unsigned long long), st));
+    SampleArgs a1 = a; a1.defer_list = d_defer;
+    int rc = launch(s->P_fast, a1, s->fast_group, s->fast_grid, s->fast_smem);
+    if (!rc) {
+        SampleArgs a2 = a; a2.list = d_defer; a2.list_count = s->d_counters + 6;
+        rc = launch(s->P, a2, s->group, s->grid, s->smem_bytes);
+    }
+    cudaFreeAsync(d_defer, st);
+    return rc;
 }
 
 int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow) {
@@ -385,6 +445,15 @@ int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n
     CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
     if (n_two_locus) *n_two_locus = h[4];
     if (n_classes) *n_classes = h[5];
+    return 0;
+}
+
+int coalgpu_deferred_count(coalgpu_sampler* s, uint64_t* n_deferred) {
+    if (!s || !n_deferred) return fail(COALGPU_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(s->device));
+    unsigned long long h[8];
+    CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    *n_deferred = s->fast ? h[6] : 0;
     return 0;
 }
 
@@ -506,6 +575,12 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     if (!rc) rc = coalgpu_finalize(G, T, acc.data(), result);
     result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
     std::string m = g_err;
+    if (timing && s->fast) {
+        unsigned long long h[8] = {0};
+        cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "coalgpu_run_sampler: first pass with a type store of %d (full %d), W = %d (full %d), %d CTAs; %llu histories of the last chunk deferred to the full store\n",
+                s->P_fast.kmax, s->P.kmax, s->fast_group, s->group, s->fast_grid, h[6]);
+    }
     const double t_fin = tick();
     cleanup();
     if (timing) fprintf(stderr, "coalgpu_run_sampler: create %.2f ms, alloc+sample+reduce %.2f ms (device %.2f ms), counters %.2f ms, finalize %.2f ms, free %.2f ms\n",

@@ -491,14 +491,16 @@ __device__ __forceinline__ void run_group() {
     int inj_lo = 0, inj_hi = 0, e = 0, tset = 0;
     HistScalars* const hs = m.hs;
     double* wout = nullptr;
+    const unsigned long long n_todo = sA.list ? *sA.list_count : sA.n;
 
 #pragma unroll 1
     for (;;) {
         if (!have) {
             unsigned long long h0 = 0;
-            if (sub == 0) h0 = atomicAdd(sA.counters, 1ull);
+            if (sub == 0) h0 = atomicAdd(sA.counters + (sA.list ? 7 : 0), 1ull);
             h = G::shfl(h0, 0);
-            if (h >= sA.n) break;
+            if (h >= n_todo) break;
+            if (sA.list) h = sA.list[h];
             have = true;
             rng.init(sA.seed, sA.first + h);
             s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
@@ -847,9 +849,12 @@ __device__ __forceinline__ void run_group() {
                 if (sA.tmrca) sA.tmrca[h] = hs->tsum;
                 if (sA.nevents) sA.nevents[h] = nev;
                 if (tracing && sA.event_counts) sA.event_counts[h] = nev;
-                if (s.overflow) atomicAdd(sA.counters + 3, 1ull);
+                if (s.overflow) {
+                    if (sA.defer_list) sA.defer_list[atomicAdd(sA.counters + 6, 1ull)] = h;   // drawn again with the full capacity
+                    else atomicAdd(sA.counters + 3, 1ull);
+                }
             }
-            ev_total += nev; pi_total += npi; cq_total += ncq;
+            if (!(s.overflow && sA.defer_list)) { ev_total += nev; pi_total += npi; cq_total += ncq; }
             have = false;
         }
     }

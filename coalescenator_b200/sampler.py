@@ -54,7 +54,8 @@ _lib = None
 
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
-           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak"]
+           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
+           "coalgpu_deferred_count"]
 
 
 def load_library():
@@ -80,6 +81,7 @@ def load_library():
         L.coalgpu_tables.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
         L.coalgpu_pismc_classes.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
         L.coalgpu_work_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.coalgpu_deferred_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.coalgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -253,7 +255,9 @@ class DeviceSampler:
         _check(self.L.coalgpu_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         d, e = C.c_uint64(), C.c_uint64()
         _check(self.L.coalgpu_work_counters(self._h, C.byref(d), C.byref(e)))
-        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value, n_two_locus=d.value, n_classes=e.value)
+        f = C.c_uint64()
+        _check(self.L.coalgpu_deferred_count(self._h, C.byref(f)))
+        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value, n_two_locus=d.value, n_classes=e.value, n_deferred=f.value)
 
     def events(self, buf) -> List[np.ndarray]:
         """Traced event records per history (the integer history encoding)."""

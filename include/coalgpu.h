@@ -128,6 +128,10 @@ int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, 
  * (the quantities the algorithmic FLOP model of DESIGN.md §5 is written in). */
 int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n_classes);
 
+/* Histories of the LAST coalgpu_sample call that outgrew the reduced type store of the first pass and were drawn
+ * again with the full one (two-pass capacity scheme); 0 when the sampler runs single-pass. */
+int coalgpu_deferred_count(coalgpu_sampler* s, uint64_t* n_deferred);
+
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (dependent-FMA chains, best of 3): the roofline
  * denominator of this fp64-ALU-bound path (MEASURED_PEAKS.json only carries HBM and bf16 peaks). */
 int coalgpu_fp64_peak(int device, double* tflops);

@@ -398,3 +398,36 @@ def test_samplers_with_different_quadrature_coexist(oracle, cuda_lib):
         ref = oracle.run(p, 32, 23, mode=oracle.MODE_CANONICAL, Q=Q)
         np.testing.assert_allclose(buf["weights"].cpu().numpy(), ref["weights"], rtol=RTOL_WEIGHT)
     s16.close(); s4.close()
+
+
+def test_two_pass_capacity_scheme_defers_and_reproduces(oracle, cuda_lib, monkeypatch):
+    """The first pass runs with a type store smaller than the worst case and defers the histories that outgrow it to
+    a second pass with the full store. Forced here to a store of 16 types so that histories ARE
+    deferred: event encodings stay bit-identical to the oracle's and to the single-pass run, nothing is reported as
+    overflow, and the default configuration (cfg4 shape) is covered by test_cfg4_shape_200_sequences_10_time_points."""
+    import torch
+    p, _, _ = load_golden("cfg2_pair0")
+    n = 600
+    monkeypatch.setenv("COALGPU_KMAX_FAST", "-1")        # single pass
+    s1 = _sampler(p)
+    monkeypatch.setenv("COALGPU_KMAX_FAST", "16")        # read when the sampler is created
+    s2 = _sampler(p)
+    monkeypatch.delenv("COALGPU_KMAX_FAST")
+    outs = []
+    for s in (s1, s2):
+        buf = s.alloc(n, n_trace=n, max_events=4096)
+        s.sample(buf, 31, 0, n)
+        torch.cuda.synchronize()
+        outs.append((buf["weights"].cpu().numpy(), buf["tmrca"].cpu().numpy(), buf["lineages"].cpu().numpy(), s.events(buf), s.counters()))
+    (w1, t1, l1, e1, c1), (w2, t2, l2, e2, c2) = outs
+    assert c1["n_deferred"] == 0 and c2["n_deferred"] > 0, (c1, c2)
+    print("deferred", c2["n_deferred"], "of", n)
+    assert c2["n_overflow"] == 0 and c1["n_events"] == c2["n_events"] and c1["n_pismc"] == c2["n_pismc"]
+    assert np.array_equal(w1, w2) and np.array_equal(t1, t2) and np.array_equal(l1, l2)
+    for h in range(n):
+        assert np.array_equal(e1[h], e2[h])
+    ref = oracle.run(p, 64, 31, mode=oracle.MODE_CANONICAL, n_event_hist=64, max_events=4096)
+    for h in range(64):
+        assert np.array_equal(e2[h], ref["events"][h])
+    np.testing.assert_allclose(w2[:64], ref["weights"], rtol=RTOL_WEIGHT)
+    s1.close(); s2.close()
