@@ -180,8 +180,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    caps = None
     for k in range(args.warmup):
         step(k)
+        if k == 0:
+            # size the reduced type store / lanes per history from what the first warm-up histories needed
+            # (coalgpu_tune; results never depend on it). coalgpu_run_sampler (the e2e leg) does the same after a pilot chunk.
+            sync()
+            caps = [s.tune() for s in samplers]
     sync()
     l0 = launch_count()
     with ClockSampler(local) as clk:
@@ -272,7 +278,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs": list(BENCH_PAIRS), "histories_per_step": per_pair * npairs * world,
                        "l2": "per-history state is on chip; every step writes fresh outputs (inputs are L2-resident tables by design)",
-                       "parallelism": "dp%d over histories" % world},
+                       "parallelism": "dp%d over histories" % world,
+                       "capacity": "two-pass type store tuned after warm-up step 1: (first-pass store, full store, lanes per history, peak types) per pair = %s"
+                                   % ([(c["store_first_pass"], c["store_full"], c["lanes_per_history"], c["peak_types"]) for c in caps] if caps else "untuned")},
             "clocks": clk.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "histories/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "histories": e2e_n * npairs * world, "wall_s_rank0": e2e_dt, "device_s_rank0": e2e_dev},

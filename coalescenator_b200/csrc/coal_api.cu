@@ -20,6 +20,7 @@ using namespace coalgpu;
 
 namespace {
 
+constexpr int kCounters = 16;     // device counters per sampler (SampleArgs::counters)
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 
@@ -87,7 +88,8 @@ struct coalgpu_sampler {
     int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history (16 or 32)
     size_t smem_bytes = 0;
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
-    bool fast = false;
+    int inj_max = 0, sm_count = 0;    // most input types of one sampling time; SMs of the device
+    bool fast = false, fast_forced = false;   // forced: COALGPU_KMAX_FAST > 0 (tests), two passes whatever the launch size
     DevProblem P_fast{};
     int fast_grid = 0, fast_group = 32;
     size_t fast_smem = 0;
@@ -230,6 +232,73 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
     return 0;
 }
 
+// Launch geometry: persistent CTAs of cta_threads(W) threads = cta_threads(W)/W groups of W lanes, one history per group.
+// W = 32, 16 or 8 lanes per history. More histories in flight per SM is better, but narrower groups take longer over
+// the loops that the lanes of a group share (look-ups, draws, lineage weights: ceil(slots / W) steps). Measured per
+// pair on cfg1/cfg2/cfg4 with tuned stores (profiles/r1_kernel_iterations.md): W = 8 (40-48 histories per SM) over
+// W = 16 (24 per SM) is 1.24-1.42x when histories hold at most ~26 distinct types, 1.03-1.11x at 32-40, 1.00x at 51
+// and 0.93x at 61. So W = 8 is used only once the sampler knows what its histories need (coalgpu_tune) and that is at
+// most 44 types, and only if it puts at least 1.3x the histories on an SM. W = 16 needs a batch of two-locus queries
+// (Ltot + 1) to fit 16 lanes.
+//
+// Two-pass capacity scheme. kmax is the worst case (every sampled two-locus lineage split by recombination and all
+// types distinct); real histories hold far fewer distinct types. When a smaller type store lets more histories run
+// per SM, the first pass uses it and defers the rare history that outgrows it to a second pass with the full store;
+// a history's draws depend on (seed, index) only, so the results do not depend on the scheme. `peak` > 0 (coalgpu_tune)
+// is the largest store any history of this sampler has needed so far: the reduced store is then sized from it.
+struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; };
+Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
+    int forced_w = 0;
+    if (const char* g = std::getenv("COALGPU_GROUP")) { const int W = std::atoi(g); if (W == 8 || W == 16 || W == 32) forced_w = W; }
+    auto eval = [&](int W) {
+        Geometry g; g.group = W;
+        g.smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (cta_threads(W) / W);
+        if (g.smem > 227 * 1024) return Geometry();
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_kernel_select(W, P.Ltot <= 32), cta_threads(W), g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
+        g.per_sm = g.occ * (cta_threads(W) / W);
+        return g;
+    };
+    if (forced_w) return eval(forced_w);
+    Geometry best = eval(32);
+    if (P.Ltot + 1 <= 16) { const Geometry g16 = eval(16); if (g16.per_sm > best.per_sm) best = g16; }
+    if (allow8) { const Geometry g8 = eval(8); if (10 * g8.per_sm >= 13 * best.per_sm) best = g8; }
+    return best;
+}
+
+int choose_geometry(coalgpu_sampler* s, int peak) {
+    DevProblem& P = s->P;
+    const Geometry full = geometry_for(P, P.kmax, P.pvmax, false);
+    if (full.per_sm < 1) return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA");
+    s->group = full.group; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
+    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
+    P.warp_bytes = s->warp_bytes;
+    s->fast = false; s->fast_forced = false;
+
+    auto pv_for = [&](int k) { int pv = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + k + 1); return (pv + 1) & ~1; };
+    int forced = 0;
+    if (const char* e = std::getenv("COALGPU_KMAX_FAST")) forced = std::atoi(e);
+    if (forced < 0) return 0;                                       // single pass
+    std::vector<int> cand; bool allow8 = false;
+    if (forced > 0) cand.push_back(((forced + 7) / 8) * 8);          // tests force small stores so that histories ARE deferred
+    else if (peak > 0) { cand.push_back(std::max(32, ((peak + peak / 4 + 8 + 7) / 8) * 8)); allow8 = peak <= 44; }   // 25 % + 8 above what was ever needed
+    else for (int kf : {256, 128, 64}) if (kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // descending: the largest store per occupancy level
+    Geometry bestf = full; int best_k = 0;
+    for (int kf : cand) {
+        kf = std::min(kf, P.kmax);                                   // kf == kmax: same store, possibly narrower groups
+        const Geometry g = geometry_for(P, kf, pv_for(kf), allow8);
+        if (g.per_sm > bestf.per_sm || (forced > 0 && kf < P.kmax && g.per_sm > 0)) { bestf = g; best_k = kf; }
+    }
+    if (best_k > 0) {
+        s->fast = true; s->fast_forced = forced > 0;
+        s->P_fast = P;
+        s->P_fast.kmax = best_k;
+        s->P_fast.pvmax = pv_for(best_k);
+        s->fast_group = bestf.group; s->fast_smem = bestf.smem; s->fast_grid = s->sm_count * bestf.occ;
+        s->P_fast.warp_bytes = (int)history_group_bytes(best_k, s->P_fast.pvmax, P.Ltot, bestf.group);
+    }
+    return 0;
+}
+
 // Device half of coalgpu_create: checks the device, uploads what prepare_host built, picks the launch geometry.
 // Everything goes into ONE stream-ordered allocation filled by asynchronous copies on `up`; nothing here waits for
 // kernels of other samplers. The caller orders its launches after `up` (stream wait or synchronize).
@@ -257,7 +326,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     const size_t o_grid = place(h.grid.size() * sizeof(GridConst)), o_lf = place(h.lfact.size() * sizeof(double));
     const size_t o_rcp = place(h.rcp.size() * sizeof(double)), o_toff = place(h.type_off.size() * sizeof(int));
     const size_t o_tw = place(h.type_w.size() * sizeof(unsigned long long)), o_tcg = place(h.type_cg.size() * sizeof(unsigned int));
-    const size_t o_cnt = place(8 * sizeof(unsigned long long));
+    const size_t o_cnt = place(kCounters * sizeof(unsigned long long));
     char* base = nullptr;
     {
         cudaError_t e = dev_alloc((void**)&base, off, up);
@@ -276,7 +345,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     put(o_toff, h.type_off.data(), h.type_off.size() * sizeof(int));
     put(o_tw, h.type_w.data(), h.type_w.size() * sizeof(unsigned long long));
     put(o_tcg, h.type_cg.data(), h.type_cg.size() * sizeof(unsigned int));
-    if (ue == cudaSuccess) ue = cudaMemsetAsync(base + o_cnt, 0, 8 * sizeof(unsigned long long), up);
+    if (ue == cudaSuccess) ue = cudaMemsetAsync(base + o_cnt, 0, kCounters * sizeof(unsigned long long), up);
     if (ue != cudaSuccess) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, std::string("upload: ") + cudaGetErrorString(ue)); }
     P.rows = (const double*)(base + o_rows); P.set_of_epoch = (const int*)(base + o_set); P.times = (const double*)(base + o_times);
     P.ep = (const EpochConst*)(base + o_ep); P.grid = (const GridConst*)(base + o_grid); P.lfact = (const double*)(base + o_lf);
@@ -284,68 +353,9 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     P.type_w = (const unsigned long long*)(base + o_tw); P.type_cg = (const unsigned int*)(base + o_tcg);
     s->d_counters = (unsigned long long*)(base + o_cnt);
 
-    // launch geometry: persistent CTAs of kCtaThreads threads = kCtaThreads/W groups of W lanes, one history per group.
-    // W = 16 when a batch of two-locus queries (Ltot + 1 of them for a C lineage) fits 16 lanes, else 32.
-    // The width that keeps more histories in flight per SM wins (shared memory per group grows with the
-    // lineage bound: 200 sequences need ~15 KB per group and W = 16 would leave one CTA per SM).
-    struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; };
-    auto geometry_for = [&](int kmax, int pvmax) -> Geometry {
-        Geometry best;
-        for (int W : {32, 16}) {
-            if (W == 16 && P.Ltot + 1 > 16) continue;
-            const size_t smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (kCtaThreads / W);
-            int occ = 0;
-            if (smem > 227 * 1024) continue;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)history_kernel_select(W, P.Ltot <= 32), kCtaThreads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
-            const int per_sm = occ * (kCtaThreads / W);
-            if (per_sm > best.per_sm) { best.group = W; best.occ = occ; best.per_sm = per_sm; best.smem = smem; }   // ties keep W = 32
-        }
-        if (const char* g = std::getenv("COALGPU_GROUP")) {
-            const int W = std::atoi(g);
-            if (W == 8 || W == 16 || W == 32) {
-                Geometry f; f.group = W; f.smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (kCtaThreads / W);
-                if (f.smem <= 227 * 1024 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f.occ, (const void*)history_kernel_select(W, P.Ltot <= 32), kCtaThreads, f.smem) == cudaSuccess) {
-                    f.per_sm = f.occ * (kCtaThreads / W);
-                    if (f.per_sm > 0) best = f;
-                } else cudaGetLastError();
-            }
-        }
-        return best;
-    };
-    const Geometry full = geometry_for(P.kmax, P.pvmax);
-    if (full.per_sm < 1) { coalgpu_destroy(s); return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA"); }
-    s->group = full.group; s->smem_bytes = full.smem; s->grid = sm_count * full.occ;
-    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
-    P.warp_bytes = s->warp_bytes;
-
-    // Two-pass capacity scheme. kmax is the worst case (every sampled two-locus lineage split by recombination and all
-    // types distinct); real histories hold far fewer distinct types. When a smaller type store lets more histories run
-    // per SM, the first pass uses it and defers the rare history that outgrows it to a second pass with the full store;
-    // a history's draws depend on (seed, index) only, so the results do not depend on the scheme.
-    {
-        int inj_max = 0;
-        for (int t = 0; t < h.T; t++) inj_max = std::max(inj_max, h.type_off[t + 1] - h.type_off[t]);
-        int forced = 0;
-        if (const char* e = std::getenv("COALGPU_KMAX_FAST")) forced = std::atoi(e);
-        Geometry bestf = full; int best_k = 0;
-        for (int kf : {256, 128, 64}) {       // descending: the largest store among those that reach an occupancy level
-            if (forced > 0) kf = ((forced + 7) / 8) * 8;          // tests force small stores so that histories ARE deferred
-            if (kf >= P.kmax || (forced <= 0 && kf < 2 * inj_max + 8)) { if (forced > 0) break; continue; }
-            int pvf = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + kf + 1); pvf = (pvf + 1) & ~1;
-            const Geometry g = geometry_for(kf, pvf);
-            if (g.per_sm > bestf.per_sm || (forced > 0 && g.per_sm > 0)) { bestf = g; best_k = kf; }
-            if (forced > 0) break;
-        }
-        if (best_k > 0 && forced >= 0) {
-            s->fast = true;
-            s->P_fast = P;
-            s->P_fast.kmax = best_k;
-            int pvf = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + best_k + 1); pvf = (pvf + 1) & ~1;
-            s->P_fast.pvmax = pvf;
-            s->fast_group = bestf.group; s->fast_smem = bestf.smem; s->fast_grid = sm_count * bestf.occ;
-            s->P_fast.warp_bytes = (int)history_group_bytes(best_k, pvf, P.Ltot, bestf.group);
-        }
-    }
+    for (int t = 0; t < h.T; t++) s->inj_max = std::max(s->inj_max, h.type_off[t + 1] - h.type_off[t]);
+    s->sm_count = sm_count;
+    if (int grc = choose_geometry(s, 0)) { coalgpu_destroy(s); return grc; }
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
     return 0;
@@ -387,6 +397,45 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
     return 0;
 }
 
+// One launch of K1. pass = 0: single pass with the full type store; 1: first pass with the reduced store, histories that
+// outgrow it go to d_defer (count in counters[6]); 2: the full store over the histories listed in d_defer.
+static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t first, uint64_t n, cudaStream_t st,
+                       double* d_weights, double* d_tmrca, double* d_lineages, uint32_t* d_nevents,
+                       coalgpu_event* d_events, uint32_t* d_event_counts, uint32_t n_trace, uint32_t max_events,
+                       unsigned long long* d_defer, uint64_t n_listed) {
+    SampleArgs a{};
+    a.seed = seed; a.first = first; a.n = n;
+    a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
+    a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
+    a.counters = s->d_counters;
+    const bool fast = pass == 1;
+    if (pass != 2) {
+        CU_OK(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st));
+        CU_OK(cudaMemsetAsync(s->d_counters + 6, 0, 2 * sizeof(unsigned long long), st));
+    }
+    if (pass == 1) a.defer_list = d_defer;
+    if (pass == 2) { a.list = d_defer; a.list_count = s->d_counters + 6; }
+    const DevProblem& P = fast ? s->P_fast : s->P;
+    const int group = fast ? s->fast_group : s->group;
+    const size_t smem = fast ? s->fast_smem : s->smem_bytes;
+    int grid = fast ? s->fast_grid : s->grid;
+    const int groups_per_cta = cta_threads(group) / group;
+    const unsigned long long todo = pass == 2 ? n_listed : n;
+    const unsigned long long ctas_needed = (todo + groups_per_cta - 1) / groups_per_cta;
+    if ((unsigned long long)grid > ctas_needed) grid = (int)std::max<unsigned long long>(ctas_needed, 1);
+    history_kernel_fn kfn = history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+    kfn<<<grid, cta_threads(group), smem, st>>>(P, a);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    return 0;
+}
+
+// The reduced-store first pass pays off when the launch can fill the device; a launch smaller than what the full-store
+// geometry keeps in flight is latency bound and runs single-pass with the wider groups.
+static bool use_two_pass(const coalgpu_sampler* s, uint64_t n) {
+    return s->fast && (s->fast_forced || n >= (uint64_t)s->grid * (cta_threads(s->group) / s->group));
+}
+
 int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
                    double* d_weights, double* d_tmrca, double* d_lineages, uint32_t* d_nevents,
                    coalgpu_event* d_events, uint32_t* d_event_counts, uint32_t n_trace, uint32_t max_events) {
@@ -394,35 +443,14 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
     if (n == 0) return 0;
     CU_OK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU_OK(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st));
-    CU_OK(cudaMemsetAsync(s->d_counters + 6, 0, 2 * sizeof(unsigned long long), st));
-    SampleArgs a{};
-    a.seed = seed; a.first = first; a.n = n;
-    a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
-    a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
-    a.counters = s->d_counters;
-    auto launch = [&](const DevProblem& P, const SampleArgs& args, int group, int full_grid, size_t smem) -> int {
-        const int groups_per_cta = kCtaThreads / group;
-        int grid = full_grid;
-        const unsigned long long ctas_needed = (n + groups_per_cta - 1) / groups_per_cta;
-        if ((unsigned long long)grid > ctas_needed) grid = (int)ctas_needed;
-        history_kernel_fn kfn = history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
-        kfn<<<grid, kCtaThreads, smem, st>>>(P, args);
-        g_launches++;
-        CU_OK(cudaGetLastError());
-        return 0;
-    };
-    if (!s->fast) return launch(s->P, a, s->group, s->grid, s->smem_bytes);
-    // first pass with the reduced type store, second pass (full store) over the histories it deferred: usually none,
-    // then its CTAs find the list empty and leave
+    if (!use_two_pass(s, n))
+        return sample_pass(s, 0, seed, first, n, st, d_weights, d_tmrca, d_lineages, d_nevents, d_events, d_event_counts, n_trace, max_events, nullptr, 0);
+    // Asynchronous contract: the host cannot look at the number of deferred histories, so the second pass is always
+    // launched, with the full grid; when the list is empty (the usual case) its CTAs leave after one load.
     unsigned long long* d_defer = nullptr;
     CU_OK(dev_alloc((void**)&d_defer, n * sizeof(unsigned long long), st));
-    SampleArgs a1 = a; a1.defer_list = d_defer;
-    int rc = launch(s->P_fast, a1, s->fast_group, s->fast_grid, s->fast_smem);
-    if (!rc) {
-        SampleArgs a2 = a; a2.list = d_defer; a2.list_count = s->d_counters + 6;
-        rc = launch(s->P, a2, s->group, s->grid, s->smem_bytes);
-    }
+    int rc = sample_pass(s, 1, seed, first, n, st, d_weights, d_tmrca, d_lineages, d_nevents, d_events, d_event_counts, n_trace, max_events, d_defer, 0);
+    if (!rc) rc = sample_pass(s, 2, seed, first, n, st, d_weights, d_tmrca, d_lineages, d_nevents, d_events, d_event_counts, n_trace, max_events, d_defer, n);
     cudaFreeAsync(d_defer, st);
     return rc;
 }
@@ -448,13 +476,28 @@ int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n
     return 0;
 }
 
-int coalgpu_deferred_count(coalgpu_sampler* s, uint64_t* n_deferred) {
-    if (!s || !n_deferred) return fail(COALGPU_EINVAL, "null argument");
+int coalgpu_capacity_stats(coalgpu_sampler* s, uint64_t* n_deferred, uint32_t* store_first_pass, uint32_t* store_full,
+                           uint32_t* peak_types, uint32_t* lanes_per_history) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
     CU_OK(cudaSetDevice(s->device));
-    unsigned long long h[8];
+    unsigned long long h[kCounters];
     CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    *n_deferred = s->fast ? h[6] : 0;
+    if (n_deferred) *n_deferred = s->fast ? h[6] : 0;
+    if (store_first_pass) *store_first_pass = (uint32_t)(s->fast ? s->P_fast.kmax : s->P.kmax);
+    if (store_full) *store_full = (uint32_t)s->P.kmax;
+    if (peak_types) *peak_types = (uint32_t)h[8];
+    if (lanes_per_history) *lanes_per_history = (uint32_t)(s->fast ? s->fast_group : s->group);
     return 0;
+}
+
+int coalgpu_tune(coalgpu_sampler* s) {
+    if (!s) return fail(COALGPU_EINVAL, "null sampler");
+    CU_OK(cudaSetDevice(s->device));
+    CU_OK(cudaDeviceSynchronize());                 // no launch of this sampler may be in flight while its geometry changes
+    unsigned long long h[kCounters];
+    CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    if (h[8] == 0) return 0;                        // nothing drawn yet
+    return choose_geometry(s, (int)h[8]);
 }
 
 int coalgpu_fp64_peak(int device, double* tflops) {
@@ -537,11 +580,12 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     // chunk the batch so that the per-history weight matrix stays below ~2 GiB
     uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n_samples, (2ull << 30) / ((size_t)(G + T + 1) * 8)));
     double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
+    unsigned long long* d_defer = nullptr; unsigned long long n_deferred_total = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<double> hp((size_t)nstat * G * 2), acc((size_t)nstat * G * 2);
     for (size_t i = 0; i < acc.size(); i += 2) { acc[i] = -INFINITY; acc[i + 1] = 0.0; }
     auto cleanup = [&]() {
-        dev_free(d_w); dev_free(d_t); dev_free(d_l); dev_free(d_p);
+        dev_free(d_w); dev_free(d_t); dev_free(d_l); dev_free(d_p); dev_free(d_defer);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
         coalgpu_destroy(s);
     };
@@ -552,9 +596,23 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     RS_OK(dev_alloc((void**)&d_p, hp.size() * sizeof(double)));
     RS_OK(cudaEventCreate(&e0)); RS_OK(cudaEventCreate(&e1));
     RS_OK(cudaEventRecord(e0, 0));
-    for (uint64_t first = 0; first < n_samples; first += chunk) {
-        const uint64_t n = std::min<uint64_t>(chunk, n_samples - first);
-        rc = coalgpu_sample(s, seed, first, n, nullptr, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0);
+    // A long run starts with a pilot chunk; the reduced type store and the geometry of the rest are sized from what the
+    // pilot histories needed (coalgpu_tune). Chunking never changes which histories are drawn.
+    // (The pilot drains the device once, about one history's latency: worth it from ~16x what the device holds in flight.)
+    const uint64_t pilot = n_samples >= 16 * (uint64_t)s->grid * (cta_threads(s->group) / s->group) ? 1024 : 0;
+    uint64_t n = 0;
+    for (uint64_t first = 0; first < n_samples; first += n) {
+        n = (first == 0 && pilot) ? pilot : std::min<uint64_t>(chunk, n_samples - first);
+        if (!use_two_pass(s, n)) {
+            rc = sample_pass(s, 0, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, nullptr, 0);
+        } else {       // blocking call: look at the deferred count and launch the second pass only when it has work
+            if (!d_defer) RS_OK(dev_alloc((void**)&d_defer, chunk * sizeof(unsigned long long)));
+            rc = sample_pass(s, 1, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, d_defer, 0);
+            unsigned long long n_def = 0;
+            if (!rc) RS_OK(cudaMemcpy(&n_def, s->d_counters + 6, sizeof n_def, cudaMemcpyDeviceToHost));
+            if (!rc && n_def) rc = sample_pass(s, 2, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, d_defer, n_def);
+            n_deferred_total += n_def;
+        }
         if (!rc) rc = coalgpu_partials(s, n, nullptr, d_w, d_t, d_l, d_p);
         if (rc) { std::string m = g_err; cleanup(); return fail(rc, m); }
         RS_OK(cudaMemcpy(hp.data(), d_p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -562,6 +620,10 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
             const double m1 = acc[i], m2 = hp[i], mm = std::max(m1, m2);
             if (mm > -INFINITY) acc[i + 1] = acc[i + 1] * std::exp(m1 - mm) + hp[i + 1] * std::exp(m2 - mm);
             acc[i] = mm;
+        }
+        if (first == 0 && pilot) {
+            rc = coalgpu_tune(s);
+            if (rc) { std::string m = g_err; cleanup(); return fail(rc, m); }
         }
     }
     RS_OK(cudaEventRecord(e1, 0));
@@ -576,10 +638,10 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
     std::string m = g_err;
     if (timing && s->fast) {
-        unsigned long long h[8] = {0};
+        unsigned long long h[kCounters] = {0};
         cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "coalgpu_run_sampler: first pass with a type store of %d (full %d), W = %d (full %d), %d CTAs; %llu histories of the last chunk deferred to the full store\n",
-                s->P_fast.kmax, s->P.kmax, s->fast_group, s->group, s->fast_grid, h[6]);
+        fprintf(stderr, "coalgpu_run_sampler: first pass with a type store of %d (full %d, most needed %llu), W = %d (full %d), %d CTAs; %llu histories deferred to the full store\n",
+                s->P_fast.kmax, s->P.kmax, h[8], s->fast_group, s->group, s->fast_grid, n_deferred_total);
     }
     const double t_fin = tick();
     cleanup();
@@ -614,6 +676,8 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         coalgpu_sampler* s = nullptr;
         double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
         double* h_p = nullptr;            // slot of the pinned slab: partials [nstat*G*2] then 8 counters
+        unsigned long long* d_defer = nullptr;
+        cudaStream_t st = nullptr;
         size_t np = 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr, eu = nullptr;
         int index = -1;
@@ -658,7 +722,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     int rc = 0; std::string err;
     std::vector<Job> window;
     auto release = [&](Job& j) {
-        dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p);
+        dev_free(j.d_w); dev_free(j.d_t); dev_free(j.d_l); dev_free(j.d_p); dev_free(j.d_defer);
         if (j.e0) cudaEventDestroy(j.e0); if (j.e1) cudaEventDestroy(j.e1); if (j.eu) cudaEventDestroy(j.eu);
         if (j.s) coalgpu_destroy(j.s);
         j = Job();
@@ -669,6 +733,20 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             WB_OK(cudaEventSynchronize(j.e1));
             float ms = 0;
             if (!rc) WB_OK(cudaEventElapsedTime(&ms, j.e0, j.e1));
+            if (!rc) {
+                coalgpu_result* r = results + j.index;
+                unsigned long long cnt[8];
+                std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
+                if (j.d_defer && cnt[6]) {       // histories outgrew the reduced store: second pass, reduce again
+                    rc = sample_pass(j.s, 2, seed, 0, n_samples, j.st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, j.d_defer, cnt[6]);
+                    if (!rc) rc = coalgpu_partials(j.s, n_samples, j.st, j.d_w, j.d_t, j.d_l, j.d_p);
+                    if (rc) err = g_err;
+                    WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, j.st));
+                    WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, j.st));
+                    WB_OK(cudaStreamSynchronize(j.st));
+                    std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
+                }
+            }
             if (!rc) {
                 coalgpu_result* r = results + j.index;
                 unsigned long long cnt[8];
@@ -739,7 +817,16 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         // Full grid per pair (one history per group when n_samples is small). Capping the grid so that every group pulls
         // several histories was measured 25 % slower: only ~8 kernels run side by side (hardware queues), so smaller grids
         // leave SMs empty (profiles/r1_batch_pipeline.md).
-        rc = coalgpu_sample(j.s, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0);
+        // The pairs of a batch fill the device together, so every pair with a reduced store runs its first pass with it;
+        // the rare pair that deferred histories gets its second pass when it is retired.
+        j.st = st;
+        if (j.s->fast) {
+            WB_OK(cudaMallocAsync((void**)&j.d_defer, n_samples * sizeof(unsigned long long), st));
+            if (rc) break;
+            rc = sample_pass(j.s, 1, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, j.d_defer, 0);
+        } else {
+            rc = sample_pass(j.s, 0, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, nullptr, 0);
+        }
         if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
         if (rc) { err = g_err; break; }
         WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));

@@ -63,7 +63,8 @@ struct SampleArgs {
     unsigned int* event_counts;
     unsigned int n_trace, max_events;
     unsigned long long* counters;   // [0] next history, [1] events, [2] pismc, [3] overflow, [4] two-locus queries, [5] their classes,
-                                    // [6] histories deferred by the reduced-capacity pass, [7] next entry of `list`
+                                    // [6] histories deferred by the reduced-capacity pass, [7] next entry of `list`,
+                                    // [8] most distinct types any completed history held (max over the sampler's life)
     // Two-pass capacity scheme (coal_api.cu): the first pass runs with a type store smaller than the worst case and
     // appends the indices of the histories that outgrow it to defer_list (count in counters[6]); the second pass
     // draws exactly those histories (list != nullptr, count read from list_count) with the full capacity.

@@ -67,6 +67,7 @@ struct HistScalars {
     EpochStats st;            // target-density statistics of the current epoch
     LogProd qprod, evprod;    // proposal density (product part), event constants of the epoch
     double qsum, consts, tsum;
+    int peak;                 // most slots the type store held during this history (capacity statistics)
 };
 
 #ifdef COAL_TMA_ROWS
@@ -511,7 +512,7 @@ __device__ __forceinline__ void run_group() {
             injecting = true; post = true;
             e = 0; tset = sP.set_of_epoch[0];
             if (sub == 0) {
-                hs->qsum = 0.0; hs->consts = 0.0; hs->tsum = 0.0;
+                hs->qsum = 0.0; hs->consts = 0.0; hs->tsum = 0.0; hs->peak = 0;
                 hs->qprod.clear(); hs->evprod.clear(); epoch_stats_clear(hs->st);
             }
             G::sync();
@@ -539,6 +540,7 @@ __device__ __forceinline__ void run_group() {
                 comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
                 if (sub == 0) hs->consts += comb;
             }
+            if (sub == 0 && s.nslots > hs->peak) hs->peak = s.nslots;
             injecting = false;
             end_now = s.overflow;
         }
@@ -806,6 +808,7 @@ __device__ __forceinline__ void run_group() {
                 if (ev_kind == 0) evc = after0;
                 else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
                 else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
+                const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
                 s.nslots = commit<W>(m, s.nslots);
                 if (tracing && sub == 0 && nev < sA.max_events) {
                     coalgpu_event& r = sA.events[(unsigned long long)h * sA.max_events + nev];
@@ -818,6 +821,7 @@ __device__ __forceinline__ void run_group() {
                 if (sub == 0) {
                     EpochStats& st = hs->st;
                     hs->tsum = tsum + wait;
+                    if (ns_event > hs->peak) hs->peak = ns_event;
                     hs->qsum += -rate * wait;
                     hs->qprod.mul(qfac);
                     hs->evprod.mul(evc);
@@ -849,6 +853,7 @@ __device__ __forceinline__ void run_group() {
                 if (sA.tmrca) sA.tmrca[h] = hs->tsum;
                 if (sA.nevents) sA.nevents[h] = nev;
                 if (tracing && sA.event_counts) sA.event_counts[h] = nev;
+                if (!s.overflow) atomicMax(sA.counters + 8, (unsigned long long)hs->peak);
                 if (s.overflow) {
                     if (sA.defer_list) sA.defer_list[atomicAdd(sA.counters + 6, 1ull)] = h;   // drawn again with the full capacity
                     else atomicAdd(sA.counters + 3, 1ull);
@@ -874,13 +879,19 @@ __device__ __forceinline__ void run_group() {
 #ifndef COAL_CTA_THREADS
 #define COAL_CTA_THREADS 128
 #endif
-constexpr int kCtaThreads = COAL_CTA_THREADS;   // threads per CTA of the history kernel
-template <int W, bool N32>
-#ifdef COAL_MAXNREG
-__global__ void __maxnreg__(COAL_MAXNREG) history_kernel(const DevProblem P, const SampleArgs A) {
-#else
-__global__ void __launch_bounds__(COAL_CTA_THREADS, COAL_MIN_CTAS) history_kernel(const DevProblem P, const SampleArgs A) {
+constexpr int kCtaThreads = COAL_CTA_THREADS;   // threads per CTA of the history kernel (W = 16, 32)
+// W = 8 packs four histories into a warp; its CTAs are smaller so that shared memory, not the CTA granularity,
+// decides how many histories fit an SM.
+#ifndef COAL_CTA_THREADS_W8
+#define COAL_CTA_THREADS_W8 64
 #endif
+#ifndef COAL_MIN_CTAS_W8
+#define COAL_MIN_CTAS_W8 5
+#endif
+__host__ __device__ constexpr int cta_threads(int W) { return W == 8 ? COAL_CTA_THREADS_W8 : COAL_CTA_THREADS; }
+template <int W, bool N32>
+__global__ void __launch_bounds__(W == 8 ? COAL_CTA_THREADS_W8 : COAL_CTA_THREADS, W == 8 ? COAL_MIN_CTAS_W8 : COAL_MIN_CTAS)
+history_kernel(const DevProblem P, const SampleArgs A) {
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
     run_group<W, N32>();

@@ -55,7 +55,7 @@ _lib = None
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
            "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
-           "coalgpu_deferred_count"]
+           "coalgpu_capacity_stats", "coalgpu_tune"]
 
 
 def load_library():
@@ -81,7 +81,8 @@ def load_library():
         L.coalgpu_tables.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
         L.coalgpu_pismc_classes.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8
         L.coalgpu_work_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        L.coalgpu_deferred_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.coalgpu_capacity_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)] + [C.POINTER(C.c_uint32)] * 4
+        L.coalgpu_tune.argtypes = [C.c_void_p]
         L.coalgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -255,9 +256,22 @@ class DeviceSampler:
         _check(self.L.coalgpu_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         d, e = C.c_uint64(), C.c_uint64()
         _check(self.L.coalgpu_work_counters(self._h, C.byref(d), C.byref(e)))
-        f = C.c_uint64()
-        _check(self.L.coalgpu_deferred_count(self._h, C.byref(f)))
-        return dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value, n_two_locus=d.value, n_classes=e.value, n_deferred=f.value)
+        out = dict(n_events=a.value, n_pismc=b.value, n_overflow=c.value, n_two_locus=d.value, n_classes=e.value)
+        out.update(self.capacity_stats())
+        return out
+
+    def capacity_stats(self):
+        """Two-pass capacity scheme: histories of the last sample() call deferred to the full type store, the two store
+        sizes, the most distinct types any history needed so far, lanes per history of the first pass."""
+        f = C.c_uint64(); k1, k2, pk, w = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(self.L.coalgpu_capacity_stats(self._h, C.byref(f), C.byref(k1), C.byref(k2), C.byref(pk), C.byref(w)))
+        return dict(n_deferred=f.value, store_first_pass=k1.value, store_full=k2.value, peak_types=pk.value, lanes_per_history=w.value)
+
+    def tune(self):
+        """Re-size the reduced type store / launch geometry from the histories drawn so far (blocking; results never
+        change, only occupancy). coalgpu_run_sampler does this itself after a pilot chunk."""
+        _check(self.L.coalgpu_tune(self._h))
+        return self.capacity_stats()
 
     def events(self, buf) -> List[np.ndarray]:
         """Traced event records per history (the integer history encoding)."""

@@ -128,9 +128,17 @@ int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, 
  * (the quantities the algorithmic FLOP model of DESIGN.md §5 is written in). */
 int coalgpu_work_counters(coalgpu_sampler* s, uint64_t* n_two_locus, uint64_t* n_classes);
 
-/* Histories of the LAST coalgpu_sample call that outgrew the reduced type store of the first pass and were drawn
- * again with the full one (two-pass capacity scheme); 0 when the sampler runs single-pass. */
-int coalgpu_deferred_count(coalgpu_sampler* s, uint64_t* n_deferred);
+/* Capacity statistics of the two-pass scheme: histories of the LAST coalgpu_sample call that outgrew the
+ * reduced type store of the first pass and were drawn again with the full one; the two store sizes (equal when the
+ * sampler runs single-pass); the most distinct types any history of this sampler has held; lanes per history of the
+ * first pass. Any output may be NULL. Blocking. */
+int coalgpu_capacity_stats(coalgpu_sampler* s, uint64_t* n_deferred, uint32_t* store_first_pass, uint32_t* store_full,
+                           uint32_t* peak_types, uint32_t* lanes_per_history);
+
+/* Re-size the reduced type store and the launch geometry from what the histories drawn so far needed (peak_types).
+ * Blocking (synchronises the device). Never changes results, only occupancy. coalgpu_run_sampler does this itself
+ * after a pilot chunk; callers of the staged API may call it after a first coalgpu_sample. */
+int coalgpu_tune(coalgpu_sampler* s);
 
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (dependent-FMA chains, best of 3): the roofline
  * denominator of this fp64-ALU-bound path (MEASURED_PEAKS.json only carries HBM and bf16 peaks). */

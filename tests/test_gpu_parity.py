@@ -431,3 +431,19 @@ def test_two_pass_capacity_scheme_defers_and_reproduces(oracle, cuda_lib, monkey
         assert np.array_equal(e2[h], ref["events"][h])
     np.testing.assert_allclose(w2[:64], ref["weights"], rtol=RTOL_WEIGHT)
     s1.close(); s2.close()
+    # the blocking entry points (second pass launched only when histories were deferred; in a batch, when the pair is
+    # retired) give the same grids as single-pass runs
+    import coalescenator_b200 as cb
+    smp = cb.ImportanceSampler()
+    probs = [load_golden(nm)[0] for nm in ("cfg2_pair0", "cfg1_pair0", "missing_pair3")]
+    monkeypatch.setenv("COALGPU_KMAX_FAST", "-1")
+    one = [smp.run_sampler(q, 500, seed=3) for q in probs]
+    monkeypatch.setenv("COALGPU_KMAX_FAST", "16")
+    two = [smp.run_sampler(q, 500, seed=3) for q in probs]
+    bat = smp.run_sampler_batch(probs, 500, seed=3)
+    monkeypatch.delenv("COALGPU_KMAX_FAST")
+    for a, b, c in zip(one, two, bat):
+        for x in (b, c):
+            np.testing.assert_array_equal(a.likelihood, x.likelihood)
+            np.testing.assert_array_equal(a.lineages_remaining, x.lineages_remaining)
+            assert a.n_events == x.n_events
