@@ -280,7 +280,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     if (forced < 0) return 0;                                       // single pass
     std::vector<int> cand; bool allow8 = false;
     if (forced > 0) cand.push_back(((forced + 7) / 8) * 8);          // tests force small stores so that histories ARE deferred
-    else if (peak > 0) { cand.push_back(std::max(32, ((peak + peak / 4 + 8 + 7) / 8) * 8)); allow8 = peak <= 44; }   // 25 % + 8 above what was ever needed
+    else if (peak > 0) { cand.push_back(std::max(32, ((peak + std::max(4, peak / 8) + 7) / 8) * 8)); allow8 = peak <= 44; }   // 1/8 (at least 4) above what was ever needed, in steps of 8: a history that needs more is deferred, not lost
     else for (int kf : {256, 128, 64}) if (kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // descending: the largest store per occupancy level
     Geometry bestf = full; int best_k = 0;
     for (int kf : cand) {
