@@ -4,6 +4,7 @@
 #include "coal_kernels.cu"
 #include "coal_tables.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -89,10 +90,17 @@ struct coalgpu_sampler {
     size_t smem_bytes = 0;
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
     int inj_max = 0, sm_count = 0;    // most input types of one sampling time; SMs of the device
+    int type_estimate = 0;            // HostPrep::type_estimate
     bool fast = false, fast_forced = false;   // forced: COALGPU_KMAX_FAST > 0 (tests), two passes whatever the launch size
     DevProblem P_fast{};
     int fast_grid = 0, fast_group = 32;
     size_t fast_smem = 0;
+    // the same without W = 8 (for launches that run side by side with other pairs' launches and cannot fill the
+    // larger capacity of W = 8 on their own: coalgpu_run_sampler_batch with few samples per pair)
+    bool wide = false;
+    DevProblem P_wide{};
+    int wide_grid = 0, wide_group = 32;
+    size_t wide_smem = 0;
     unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
     // K2 scratch smem
     size_t k2_smem = 0;
@@ -104,6 +112,7 @@ namespace {
 // next locus pairs on host threads while the GPU works on the current ones.
 struct HostPrep {
     int T = 0, LA = 0, LB = 0, G = 0;
+    int type_estimate = 0;    // distinct two-locus haplotypes + distinct A parts + distinct B parts of the input (see choose_geometry)
     DevProblem P{};
     HostTables tab;
     std::vector<int> type_off;
@@ -169,6 +178,17 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
             for (size_t i = start; i < type_w.size(); i++) if ((int)(type_cg[i] >> 30) == g) { const unsigned int c = type_cg[i] & 0x3fffffffu; tot += c; perm += std::lgamma((double)c + 1.0); }
             perm -= std::lgamma((double)tot + 1.0);
         }
+    }
+    {   // haplotype diversity of the input: what a history's type store has to hold is close to it (choose_geometry)
+        std::vector<unsigned long long> c, a, b;
+        for (size_t i = 0; i < type_w.size(); i++) {
+            const int g = (int)(type_cg[i] >> 30);
+            if (g == COALGPU_GAMMA_C) c.push_back(type_w[i]);
+            if (g != COALGPU_GAMMA_B) a.push_back(type_w[i] & maskA);
+            if (g != COALGPU_GAMMA_A) b.push_back(type_w[i] & maskB);
+        }
+        auto distinct = [](std::vector<unsigned long long>& v) { std::sort(v.begin(), v.end()); return (int)(std::unique(v.begin(), v.end()) - v.begin()); };
+        h.type_estimate = distinct(c) + distinct(a) + distinct(b);
     }
     if (type_off[1] == 0) return bad("first sampling time has no sequences");
     if (n_bound < 1 || n_bound > 60000) return bad("lineage bound out of range (1..60000)");
@@ -272,7 +292,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     s->group = full.group; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
     s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
     P.warp_bytes = s->warp_bytes;
-    s->fast = false; s->fast_forced = false;
+    s->fast = false; s->fast_forced = false; s->wide = false;
 
     auto pv_for = [&](int k) { int pv = std::max(P.Ltot + 4, std::max(P.LA, P.LB) + k + 1); return (pv + 1) & ~1; };
     int forced = 0;
@@ -280,22 +300,35 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     if (forced < 0) return 0;                                       // single pass
     std::vector<int> cand; bool allow8 = false;
     if (forced > 0) cand.push_back(((forced + 7) / 8) * 8);          // tests force small stores so that histories ARE deferred
-    else if (peak > 0) { cand.push_back(std::max(32, ((peak + std::max(4, peak / 8) + 7) / 8) * 8)); allow8 = peak <= 44; }   // 1/8 (at least 4) above what was ever needed, in steps of 8: a history that needs more is deferred, not lost
-    else for (int kf : {256, 128, 64}) if (kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // descending: the largest store per occupancy level
-    Geometry bestf = full; int best_k = 0;
-    for (int kf : cand) {
-        kf = std::min(kf, P.kmax);                                   // kf == kmax: same store, possibly narrower groups
-        const Geometry g = geometry_for(P, kf, pv_for(kf), allow8);
-        if (g.per_sm > bestf.per_sm || (forced > 0 && kf < P.kmax && g.per_sm > 0)) { bestf = g; best_k = kf; }
+    else {
+        // What the histories need: measured (coalgpu_tune: the most distinct types any history held so far) or, before
+        // anything was drawn, estimated from the input: distinct two-locus haplotypes + distinct A parts + distinct
+        // B parts, + 4. On cfg1/cfg2/cfg4 pairs the measured peak is between 0.64x and 1.1x of that sum and never
+        // more than 2 above it (profiles/r1_kernel_iterations.md). The store is 1/8 (at least 4) above, in steps of 8:
+        // a history that needs more is deferred to the full store, not lost.
+        const int need = peak > 0 ? peak : s->type_estimate + 4;
+        cand.push_back(std::max(32, ((need + std::max(4, need / 8) + 7) / 8) * 8));
+        allow8 = need <= 44;
+        for (int kf : {256, 128, 64}) if (kf > cand[0] && kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // larger stores that still raise the occupancy
     }
-    if (best_k > 0) {
-        s->fast = true; s->fast_forced = forced > 0;
-        s->P_fast = P;
-        s->P_fast.kmax = best_k;
-        s->P_fast.pvmax = pv_for(best_k);
-        s->fast_group = bestf.group; s->fast_smem = bestf.smem; s->fast_grid = s->sm_count * bestf.occ;
-        s->P_fast.warp_bytes = (int)history_group_bytes(best_k, s->P_fast.pvmax, P.Ltot, bestf.group);
-    }
+    auto pick = [&](bool with8, DevProblem& Pout, int& grid, int& group, size_t& smem) -> bool {
+        Geometry bestf = full; int best_k = 0;
+        for (int kf : cand) {
+            kf = std::min(kf, P.kmax);                               // kf == kmax: same store, possibly narrower groups
+            const Geometry g = geometry_for(P, kf, pv_for(kf), with8);
+            if (g.per_sm > bestf.per_sm || (forced > 0 && kf < P.kmax && g.per_sm > 0)) { bestf = g; best_k = kf; }
+        }
+        if (best_k == 0) return false;
+        Pout = P;
+        Pout.kmax = best_k;
+        Pout.pvmax = pv_for(best_k);
+        group = bestf.group; smem = bestf.smem; grid = s->sm_count * bestf.occ;
+        Pout.warp_bytes = (int)history_group_bytes(best_k, Pout.pvmax, P.Ltot, bestf.group);
+        return true;
+    };
+    s->fast = pick(allow8, s->P_fast, s->fast_grid, s->fast_group, s->fast_smem);
+    s->fast_forced = s->fast && forced > 0;
+    s->wide = pick(false, s->P_wide, s->wide_grid, s->wide_group, s->wide_smem);
     return 0;
 }
 
@@ -355,6 +388,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
 
     for (int t = 0; t < h.T; t++) s->inj_max = std::max(s->inj_max, h.type_off[t + 1] - h.type_off[t]);
     s->sm_count = sm_count;
+    s->type_estimate = h.type_estimate;
     if (int grc = choose_geometry(s, 0)) { coalgpu_destroy(s); return grc; }
     s->k2_smem = (size_t)4 * (P.Ltot + 2) * 32 * sizeof(unsigned int);
     *out = s;
@@ -398,7 +432,8 @@ int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sam
 }
 
 // One launch of K1. pass = 0: single pass with the full type store; 1: first pass with the reduced store, histories that
-// outgrow it go to d_defer (count in counters[6]); 2: the full store over the histories listed in d_defer.
+// outgrow it go to d_defer (count in counters[6]); 3: the same with the W >= 16 variant of the reduced-store geometry;
+// 2: the full store over the histories listed in d_defer.
 static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t first, uint64_t n, cudaStream_t st,
                        double* d_weights, double* d_tmrca, double* d_lineages, uint32_t* d_nevents,
                        coalgpu_event* d_events, uint32_t* d_event_counts, uint32_t n_trace, uint32_t max_events,
@@ -408,17 +443,17 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
     a.weights = d_weights; a.tmrca = d_tmrca; a.lineages = d_lineages; a.nevents = d_nevents;
     a.events = d_events; a.event_counts = d_event_counts; a.n_trace = d_events ? n_trace : 0; a.max_events = max_events;
     a.counters = s->d_counters;
-    const bool fast = pass == 1;
+    const bool fast = pass == 1, wide = pass == 3;
     if (pass != 2) {
         CU_OK(cudaMemsetAsync(s->d_counters, 0, sizeof(unsigned long long), st));
         CU_OK(cudaMemsetAsync(s->d_counters + 6, 0, 2 * sizeof(unsigned long long), st));
     }
-    if (pass == 1) a.defer_list = d_defer;
+    if (pass == 1 || pass == 3) a.defer_list = d_defer;
     if (pass == 2) { a.list = d_defer; a.list_count = s->d_counters + 6; }
-    const DevProblem& P = fast ? s->P_fast : s->P;
-    const int group = fast ? s->fast_group : s->group;
-    const size_t smem = fast ? s->fast_smem : s->smem_bytes;
-    int grid = fast ? s->fast_grid : s->grid;
+    const DevProblem& P = fast ? s->P_fast : wide ? s->P_wide : s->P;
+    const int group = fast ? s->fast_group : wide ? s->wide_group : s->group;
+    const size_t smem = fast ? s->fast_smem : wide ? s->wide_smem : s->smem_bytes;
+    int grid = fast ? s->fast_grid : wide ? s->wide_grid : s->grid;
     const int groups_per_cta = cta_threads(group) / group;
     const unsigned long long todo = pass == 2 ? n_listed : n;
     const unsigned long long ctas_needed = (todo + groups_per_cta - 1) / groups_per_cta;
@@ -597,8 +632,9 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     RS_OK(cudaEventCreate(&e0)); RS_OK(cudaEventCreate(&e1));
     RS_OK(cudaEventRecord(e0, 0));
     // A long run starts with a pilot chunk; the reduced type store and the geometry of the rest are sized from what the
-    // pilot histories needed (coalgpu_tune). Chunking never changes which histories are drawn.
-    // (The pilot drains the device once, about one history's latency: worth it from ~16x what the device holds in flight.)
+    // pilot histories needed (coalgpu_tune) instead of the input-based estimate. Chunking never changes which histories
+    // are drawn. The pilot drains the device once, about one history's latency: worth it from ~16x what the device holds
+    // in flight (cfg2, 98,304 samples: 413 k histories/s with the pilot, 400 k with the estimate alone).
     const uint64_t pilot = n_samples >= 16 * (uint64_t)s->grid * (cta_threads(s->group) / s->group) ? 1024 : 0;
     uint64_t n = 0;
     for (uint64_t first = 0; first < n_samples; first += n) {
@@ -817,13 +853,16 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         // Full grid per pair (one history per group when n_samples is small). Capping the grid so that every group pulls
         // several histories was measured 25 % slower: only ~8 kernels run side by side (hardware queues), so smaller grids
         // leave SMs empty (profiles/r1_batch_pipeline.md).
-        // The pairs of a batch fill the device together, so every pair with a reduced store runs its first pass with it;
+        // The pairs of a batch fill the device together, so every pair with a reduced store runs its first pass with it
+        // (W = 8 only when the pair could fill the device on its own: about 8 launches run side by side, and a
+        // thousand histories each cannot fill the larger capacity of W = 8 -- measured 227 k vs 288 k at cfg2);
         // the rare pair that deferred histories gets its second pass when it is retired.
         j.st = st;
-        if (j.s->fast) {
+        const int first_pass = use_two_pass(j.s, n_samples) ? 1 : (j.s->wide ? 3 : 0);
+        if (first_pass) {
             WB_OK(cudaMallocAsync((void**)&j.d_defer, n_samples * sizeof(unsigned long long), st));
             if (rc) break;
-            rc = sample_pass(j.s, 1, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, j.d_defer, 0);
+            rc = sample_pass(j.s, first_pass, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, j.d_defer, 0);
         } else {
             rc = sample_pass(j.s, 0, seed, 0, n_samples, st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, nullptr, 0);
         }

@@ -447,3 +447,45 @@ def test_two_pass_capacity_scheme_defers_and_reproduces(oracle, cuda_lib, monkey
             np.testing.assert_array_equal(a.likelihood, x.likelihood)
             np.testing.assert_array_equal(a.lineages_remaining, x.lineages_remaining)
             assert a.n_events == x.n_events
+
+
+@pytest.mark.parametrize("W", [8, 16, 32])
+def test_every_group_width_is_bit_exact(oracle, cuda_lib, monkeypatch, W):
+    """The history kernel is instantiated for W = 8, 16 and 32 lanes per history; which one runs depends on the launch
+    size and on what the sampler knows about its histories. Small launches always take the wide
+    single-pass geometry, so every width is forced here (COALGPU_GROUP is read when the sampler is created): event
+    encodings bit-identical to the oracle, weights to 1e-9, on goldens with missing data, a grid, five time points,
+    and on loci longer than one lane batch (wide haplotype words when LA + LB > 32)."""
+    from coalescenator_b200.problem import synth_alignment, tile_loci, locus_pairs, sub_problem
+    monkeypatch.setenv("COALGPU_GROUP", str(W))
+    for name, n, seed in (("cfg2_pair0", 48, 5), ("missing_pair3", 48, 6), ("grid_pair5", 24, 7), ("varV_req_n", 32, 8)):
+        p, _, _ = load_golden(name)
+        _compare_histories(oracle, p, n, seed=seed)
+    aln = synth_alignment(9, 2, 6, 400, 60)
+    loci = tile_loci(aln, 80)
+    pairs = locus_pairs(loci)
+    best = max(pairs, key=lambda t: (loci[t[0]][3] - loci[t[0]][2]) + (loci[t[1]][3] - loci[t[1]][2]))
+    _compare_histories(oracle, sub_problem(aln, loci, *best), 16, seed=9, max_events=16384)
+    aln = synth_alignment(11, 2, 5, 400, 100)
+    loci = tile_loci(aln, 80)
+    best = max(locus_pairs(loci), key=lambda t: (loci[t[0]][3] - loci[t[0]][2]) + (loci[t[1]][3] - loci[t[1]][2]))
+    p = sub_problem(aln, loci, *best)
+    assert 32 < p.LA + p.LB <= 64          # 64-bit haplotype words in the loops over stored types
+    _compare_histories(oracle, p, 12, seed=10, max_events=32768)
+    # and the tuned two-pass path at a launch size that takes it (reduced store from the measured peak)
+    import torch
+    p, _, _ = load_golden("cfg2_pair0")
+    s = _sampler(p)
+    n = 8192
+    buf = s.alloc(n, n_trace=64, max_events=4096)
+    s.sample(buf, 12, 0, n); torch.cuda.synchronize()
+    st = s.tune()
+    assert st["lanes_per_history"] == W and st["peak_types"] > 0
+    s.sample(buf, 12, 0, n); torch.cuda.synchronize()
+    ref = oracle.run(p, 64, 12, mode=oracle.MODE_CANONICAL, n_event_hist=64, max_events=4096)
+    ev = s.events(buf)
+    for h in range(64):
+        assert np.array_equal(ev[h], ref["events"][h])
+    np.testing.assert_allclose(buf["weights"].cpu().numpy()[:64], ref["weights"], rtol=RTOL_WEIGHT)
+    assert s.counters()["n_overflow"] == 0
+    s.close()
