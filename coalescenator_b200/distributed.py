@@ -1,4 +1,5 @@
-"""Multi-GPU sharding of one locus pair's importance samples.
+"""Multi-GPU sharding: the importance samples of one locus pair over the ranks
+(run_sampler_distributed), or the locus pairs of an analysis over the ranks (run_sampler_batch_distributed).
 
 Histories are i.i.d. given (data, driving values) and history h is a pure function of (seed, h)
 (Philox counter), so rank r simply draws the contiguous index range shard_range(n, r, R) on its own
@@ -86,3 +87,46 @@ def run_sampler_distributed(problem: Problem, num_iterations: int, seed: int = 0
         raise RuntimeError("a history outgrew the type-store capacity")
     s.close()
     return out
+
+
+def shard_pairs(n_pairs: int, rank: int, world: int):
+    """Indices of the locus pairs rank `rank` owns: round robin, so that neighbouring pairs (similar locus lengths,
+    similar cost) spread over the ranks."""
+    return list(range(int(rank), int(n_pairs), int(world)))
+
+
+def gather_pair_results(mine, n_pairs: int, group=None):
+    """mine: list of (pair index, result) of this rank -> list of all n_pairs results in pair order on every rank.
+    One collective (all_gather_object: the results are a few small arrays per pair)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+    out = [None] * n_pairs
+    for part in parts:
+        for k, r in part:
+            assert out[k] is None, "pair %d computed twice" % k
+            out[k] = r
+    assert all(r is not None for r in out)
+    return out
+
+
+def run_sampler_batch_distributed(problems, num_iterations: int, seed: int = 0, quadrature_points: int = 16,
+                                  device: Optional[int] = None, group=None, compute=None):
+    """The double loop of main.cpp:242-311 over all ranks: with at least as many locus pairs as GPUs the pairs are the
+    parallel axis -- rank r runs pairs r, r+R, ... through coalgpu_run_sampler_batch on its own GPU with no data-path
+    communication, and the per-pair results are gathered once at the end. Every rank returns the full list, identical
+    to single-GPU results (a pair's histories depend on (seed, index) only). `compute` replaces the GPU call in the
+    CPU tests of the sharding/gather logic."""
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    idx = shard_pairs(len(problems), rank, world)
+    if compute is None:
+        from .sampler import ImportanceSampler
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(device)
+        compute = lambda ps: ImportanceSampler().run_sampler_batch(ps, num_iterations, seed=seed, quadrature_points=quadrature_points, device=device)
+    res = compute([problems[k] for k in idx]) if idx else []
+    return gather_pair_results(list(zip(idx, res)), len(problems), group)

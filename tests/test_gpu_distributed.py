@@ -60,3 +60,40 @@ def test_two_gpus_nccl_equal_single_gpu(cuda_lib):
     np.testing.assert_allclose(got[0][0], one.likelihood, rtol=1e-13)
     np.testing.assert_allclose(got[0][1], one.likelihoodSq, rtol=1e-13)
     assert got[0][2] == one.n_events
+
+
+def _pair_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from coalescenator_b200.distributed import run_sampler_batch_distributed
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    probs = [load_golden(n)[0] for n in ("cfg1_pair0", "cfg2_pair0", "missing_pair3", "stat_grid", "varV_req_n")]
+    out = run_sampler_batch_distributed(probs, 400, seed=4, device=rank)
+    q.put((rank, [o.likelihood.copy() for o in out], [o.n_events for o in out]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pairs_over_two_gpus_equal_single_gpu_batch(cuda_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import coalescenator_b200 as cb
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pair_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = {r: (a, n) for r, a, n in (q.get(timeout=300) for _ in range(2))}
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    probs = [load_golden(n)[0] for n in ("cfg1_pair0", "cfg2_pair0", "missing_pair3", "stat_grid", "varV_req_n")]
+    one = cb.ImportanceSampler().run_sampler_batch(probs, 400, seed=4)
+    for k in range(len(probs)):
+        assert np.array_equal(got[0][0][k], got[1][0][k]) and np.array_equal(got[0][0][k], one[k].likelihood)
+        assert got[0][1][k] == one[k].n_events
