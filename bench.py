@@ -147,9 +147,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own messages (e.g. "NCCL version ...") go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: what NCCL / torch print while the communicator comes up
+        # ("NCCL version ..." under NCCL_DEBUG=VERSION) is sent to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     probs = bench_problems()
     npairs = len(probs)
