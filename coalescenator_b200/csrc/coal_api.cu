@@ -770,7 +770,6 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             float ms = 0;
             if (!rc) WB_OK(cudaEventElapsedTime(&ms, j.e0, j.e1));
             if (!rc) {
-                coalgpu_result* r = results + j.index;
                 unsigned long long cnt[8];
                 std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
                 if (j.d_defer && cnt[6]) {       // histories outgrew the reduced store: second pass, reduce again
@@ -780,7 +779,6 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
                     WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, j.st));
                     WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, j.st));
                     WB_OK(cudaStreamSynchronize(j.st));
-                    std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
                 }
             }
             if (!rc) {
