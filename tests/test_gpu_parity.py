@@ -303,9 +303,15 @@ def _random_problem(rng, k):
     return Problem(LA, LB, times, viral, float(rng.choice([1.0, 1.7])), 2.5e-5, 1000.0, 5e-5 * scale, grid[0], grid[1], grid[2], types, name="fuzz%d" % k)
 
 
-def test_random_problems_differential(oracle, cuda_lib):
+@pytest.mark.parametrize("mode", ["default", "W8 + two-pass store of 16"])
+def test_random_problems_differential(oracle, cuda_lib, monkeypatch, mode):
     """Differential fuzz: random small problems (1-4 sampling times, A/B/C initial types, unequal viral loads,
-    1-18 sites per locus incl. LA+LB > 32, 1- and 4-point grids); events bit-exact, weights 1e-9 vs the oracle."""
+    1-18 sites per locus incl. LA+LB > 32, 1- and 4-point grids); events bit-exact, weights 1e-9 vs the oracle.
+    Second run: W = 8 lanes per history and a first-pass type store of 16, so that many histories take the
+    deferral path (aborted mid-history, drawn again by the second pass)."""
+    if mode != "default":
+        monkeypatch.setenv("COALGPU_GROUP", "8")
+        monkeypatch.setenv("COALGPU_KMAX_FAST", "16")
     rng = np.random.default_rng(2026)
     for k in range(24):
         p = _random_problem(rng, k)
