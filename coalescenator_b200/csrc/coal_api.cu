@@ -23,6 +23,7 @@ namespace {
 
 constexpr int kCounters = 16;     // device counters per sampler (SampleArgs::counters)
 thread_local std::string g_err;
+std::atomic<int> g_emission_mode{kEmissionReference};
 std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -200,7 +201,7 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
         thetas[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_mu;
         rrates[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_rho;
     }
-    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, h.tab, table_threads)) return bad("table construction failed");
+    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, h.tab, table_threads, g_emission_mode.load())) return bad("table construction failed");
 
     h.ep.resize(T);
     for (int c = 0; c < T; c++) {
@@ -406,6 +407,12 @@ const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged tab
 const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
 #endif
 uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
+
+int coalgpu_set_emission_mode(int mode) {
+    if (mode != COALGPU_EMISSION_REFERENCE && mode != COALGPU_EMISSION_STABLE) return fail(COALGPU_EINVAL, "unknown emission mode");
+    g_emission_mode.store(mode == COALGPU_EMISSION_STABLE ? kEmissionStable : kEmissionReference);
+    return 0;
+}
 
 void coalgpu_destroy(coalgpu_sampler* s) {
     if (!s) return;

@@ -108,6 +108,46 @@ void emission_table(int Q, const double* t, const double* w, const std::vector<d
     }
 }
 
+// ---- stable emission mode ----------------------------------------------------------------
+// The double sum above is an alternating binomial sum. In double precision its absolute error is ~1e-17: entries above
+// ~1e-6 are good to 1e-10 even at 30 sites per locus, entries near and below 1e-13 are rounding noise or the clamp.
+// Summed in closed form it is
+//   sum_l sum_k C(L-d,k) C(d,l) (-1)^l e^{-(a(k+l)+1)t} = e^{-t} (1 + e^{-at})^{L-d} (1 - e^{-at})^d,   a = 2 theta / n,
+// a positive integrand, so E[i][d] = 1/(w_i 2^L) * integral over interval i of it -- evaluated here with 32-point
+// Gauss-Legendre on the finite intervals and 32-point Gauss-Laguerre on the last, [t_{Q-1}, inf): relative error
+// <= 1e-14 on every entry against 300-digit arithmetic for L up to 40 (tests/test_tables_and_math_host.py).
+// Opt-in (coalgpu_set_emission_mode): the default stays bit-identical to the reference.
+constexpr double kGLx[32] = {-0.9972638618494816, -0.9856115115452684, -0.9647622555875064, -0.9349060759377397, -0.8963211557660521, -0.84936761373257, -0.7944837959679424, -0.7321821187402897, -0.6630442669302152, -0.5877157572407623, -0.5068999089322294, -0.42135127613063533, -0.33186860228212767, -0.23928736225213706, -0.1444719615827965, -0.048307665687738324, 0.048307665687738324, 0.1444719615827965, 0.23928736225213706, 0.33186860228212767, 0.42135127613063533, 0.5068999089322294, 0.5877157572407623, 0.6630442669302152, 0.7321821187402897, 0.7944837959679424, 0.84936761373257, 0.8963211557660521, 0.9349060759377397, 0.9647622555875064, 0.9856115115452684, 0.9972638618494816};
+constexpr double kGLw[32] = {0.007018610009470506, 0.016274394730905743, 0.025392065309262024, 0.034273862913021765, 0.042835898022226836, 0.05099805926237609, 0.058684093478535565, 0.06582222277636168, 0.07234579410884834, 0.07819389578707023, 0.08331192422694671, 0.08765209300440378, 0.09117387869576378, 0.09384439908080451, 0.09563872007927471, 0.09654008851472766, 0.09654008851472766, 0.09563872007927471, 0.09384439908080451, 0.09117387869576378, 0.08765209300440378, 0.08331192422694671, 0.07819389578707023, 0.07234579410884834, 0.06582222277636168, 0.058684093478535565, 0.05099805926237609, 0.042835898022226836, 0.034273862913021765, 0.025392065309262024, 0.016274394730905743, 0.007018610009470506};
+constexpr double kLagx[32] = {0.04448936583326739, 0.23452610951961825, 0.5768846293018863, 1.072448753817818, 1.7224087764446456, 2.5283367064257942, 3.492213273021994, 4.616456769749767, 5.903958504174244, 7.358126733186241, 8.982940924212597, 10.78301863253997, 12.763697986742725, 14.931139755522558, 17.292454336715316, 19.855860940336054, 22.630889013196775, 25.628636022459247, 28.862101816323474, 32.346629153964734, 36.10049480575197, 40.14571977153944, 44.50920799575494, 49.22439498730864, 54.33372133339691, 59.89250916213402, 65.97537728793505, 72.68762809066271, 80.18744697791352, 88.7353404178924, 98.82954286828398, 111.7513980979377};
+constexpr double kLagw[32] = {0.10921834195242515, 0.2104431079387924, 0.23521322966984298, 0.19590333597287354, 0.1299837862860684, 0.07057862386571556, 0.03176091250917397, 0.011918214834838204, 0.003738816294611417, 0.0009808033066149246, 0.0002148649188013578, 3.920341967987801e-05, 5.934541612868448e-06, 7.41640457866734e-07, 7.604567879120552e-08, 6.350602226625618e-09, 4.281382971040738e-10, 2.305899491891237e-11, 9.799379288726772e-13, 3.2378016577291567e-14, 8.171823443420549e-16, 1.542133833393811e-17, 2.119792290163547e-19, 2.0544296737880036e-21, 1.3469825866373617e-23, 5.661294130397462e-26, 1.4185605454629684e-28, 1.9133754944539943e-31, 1.1922487600982012e-34, 2.6715112192396625e-38, 1.3386169421064243e-42, 4.5105361938987784e-48};
+
+inline double stable_integrand(double a, int L, int d, double t) {
+    const double x = std::exp(-a * t);
+    return std::exp((double)(L - d) * std::log1p(x) + (d > 0 ? (double)d * std::log1p(-x) : 0.0));
+}
+
+void emission_table_stable(int Q, const double* t, const double* w, double theta, unsigned n, int L, double* E /*[L+1][kEStride]*/) {
+    const double a = 2 * theta / n;
+    const double two_L = std::pow(2, (double)L);
+    for (int d = 0; d <= L; d++) {
+        for (int i = 0; i < Q; i++) {
+            double v = 0;
+            if (i + 1 < Q || t[Q] < 1e299) {
+                const double lo = t[i], hi = t[i + 1], h = 0.5 * (hi - lo), c = 0.5 * (hi + lo);
+                for (int q = 0; q < 32; q++) { const double tt = c + h * kGLx[q]; v += kGLw[q] * std::exp(-tt) * stable_integrand(a, L, d, tt); }
+                v *= h;
+            } else {
+                const double lo = t[i];
+                for (int q = 0; q < 32; q++) v += kLagw[q] * stable_integrand(a, L, d, lo + kLagx[q]);
+                v *= std::exp(-lo);
+            }
+            v /= (w[i] * two_L);
+            E[(size_t)d * kEStride + i] = std::max(v, std::numeric_limits<double>::epsilon());   // the reference's clamp (:221)
+        }
+    }
+}
+
 // ---- emission cache ---------------------------------------------------------------------------------------------
 // E depends on (quadrature, L, theta, n) only -- not on the locus pair: theta = 4 lambda V mu is the same for every pair
 // of a data set and the pairs of main.cpp:242-311 have a handful of distinct L. The blocks are therefore kept in a
@@ -120,17 +160,17 @@ struct EmissionBlock {
     std::vector<double> data;
 };
 struct EmissionKey {
-    int Q, L; uint64_t theta_bits;
-    bool operator<(const EmissionKey& o) const { return std::tie(Q, L, theta_bits) < std::tie(o.Q, o.L, o.theta_bits); }
+    int Q, L, mode; uint64_t theta_bits;
+    bool operator<(const EmissionKey& o) const { return std::tie(Q, L, mode, theta_bits) < std::tie(o.Q, o.L, o.mode, o.theta_bits); }
 };
 std::mutex g_cache_mutex;
 std::map<EmissionKey, std::shared_ptr<EmissionBlock>> g_cache;
 size_t g_cache_doubles = 0;
 constexpr size_t kCacheMaxDoubles = (size_t)1 << 26;   // 512 MiB; the cache is dropped when it grows past this
 
-std::shared_ptr<EmissionBlock> emission_block(int Q, int L, double theta, int n_max, const double* t, const double* w,
+std::shared_ptr<EmissionBlock> emission_block(int Q, int L, int mode, double theta, int n_max, const double* t, const double* w,
                                               const std::vector<double>& bin, int bw, int threads) {
-    EmissionKey key{Q, L, 0};
+    EmissionKey key{Q, L, mode, 0};
     std::memcpy(&key.theta_bits, &theta, sizeof(double));
     std::shared_ptr<EmissionBlock> b;
     {
@@ -152,7 +192,8 @@ std::shared_ptr<EmissionBlock> emission_block(int Q, int L, double theta, int n_
         auto fill = [&](int a, int e) {
             for (int n = a + 1; n <= e; n++) {
                 double* E = b->data.data() + (size_t)(n - 1) * b->stride;
-                emission_table(Q, t, w, bin, bw, theta, (unsigned)n, L, E);
+                if (mode == kEmissionStable) emission_table_stable(Q, t, w, theta, (unsigned)n, L, E);
+                else emission_table(Q, t, w, bin, bw, theta, (unsigned)n, L, E);
                 double* wE = E + (L + 1) * kEStride;
                 for (int d = 0; d <= L; d++) { double acc = 0; for (int i = 0; i < kQ; i++) acc += w[i] * E[d * kEStride + i]; wE[d] = acc; }
             }
@@ -183,7 +224,7 @@ void clear_table_cache() {
 }
 
 bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
-                  const std::vector<double>& r_rates, HostTables& out, int threads) {
+                  const std::vector<double>& r_rates, HostTables& out, int threads, int emission_mode) {
     if ((Q != 4 && Q != 8 && Q != kQ) || LA < 1 || LB < 1 || n_max < 1 || thetas.size() != r_rates.size()) return false;
     if (threads <= 0) { const unsigned hw = std::thread::hardware_concurrency(); threads = (int)std::min<unsigned>(hw ? hw : 1, 16); }
     out.lay.init(LA, LB);
@@ -221,8 +262,8 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
 
     for (int s = 0; s < out.n_sets; s++) {
         const double theta = thetas[rep[s]], r = r_rates[rep[s]];
-        const std::shared_ptr<EmissionBlock> bA = emission_block(Q, LA, theta, n_max, t, w, bin, bw, threads);
-        const std::shared_ptr<EmissionBlock> bB = (LB == LA) ? bA : emission_block(Q, LB, theta, n_max, t, w, bin, bw, threads);
+        const std::shared_ptr<EmissionBlock> bA = emission_block(Q, LA, emission_mode, theta, n_max, t, w, bin, bw, threads);
+        const std::shared_ptr<EmissionBlock> bB = (LB == LA) ? bA : emission_block(Q, LB, emission_mode, theta, n_max, t, w, bin, bw, threads);
         for (int n = 1; n <= n_max; n++) {
             const size_t idx = (size_t)s * n_max + (n - 1);
             double* row = out.rows.data() + idx * lay.row_doubles;

@@ -45,8 +45,11 @@ struct HostTables {
 // thetas[c] = 4*lambda_d*V[c]*mu_d, r_rates[c] = 4*lambda_d*V[c]*rho_d (ImportanceSampler.cpp:69-76)
 // Emission blocks are shared between calls through a process-wide cache keyed by (Q, L, theta) (coal_tables.cpp).
 // threads: host threads used for blocks that are not cached yet (0 = all hardware threads, at most 16).
+// emission_mode: kEmissionReference = the reference's double sum in its operation order (bit-identical tables, loses
+// accuracy beyond ~20-30 sites per locus); kEmissionStable = the same quantity by quadrature of its closed form.
+enum { kEmissionReference = 0, kEmissionStable = 1 };
 bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
-                  const std::vector<double>& r_rates, HostTables& out, int threads = 0);
+                  const std::vector<double>& r_rates, HostTables& out, int threads = 0, int emission_mode = kEmissionReference);
 void clear_table_cache();
 
 }  // namespace coalgpu

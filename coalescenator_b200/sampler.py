@@ -55,7 +55,7 @@ _lib = None
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
            "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
-           "coalgpu_capacity_stats", "coalgpu_tune"]
+           "coalgpu_capacity_stats", "coalgpu_tune", "coalgpu_set_emission_mode"]
 
 
 def load_library():
@@ -83,6 +83,7 @@ def load_library():
         L.coalgpu_work_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.coalgpu_capacity_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)] + [C.POINTER(C.c_uint32)] * 4
         L.coalgpu_tune.argtypes = [C.c_void_p]
+        L.coalgpu_set_emission_mode.argtypes = [C.c_int]
         L.coalgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -141,6 +142,12 @@ class SamplerOutput:
         reference prints (main.cpp:240,306): var(log mean w) ~ (sum w^2 / (sum w)^2 - 1/N)."""
         rel = np.exp(self.likelihoodSq - 2 * self.likelihood) - 1.0 / max(self.n_histories, 1)
         return np.sqrt(np.maximum(rel, 0.0))
+
+
+def set_emission_mode(mode: str) -> None:
+    """'reference' (default: tables bit-identical to the reference's) or 'stable' (closed form by quadrature, every
+    entry accurate at any locus length); applies to samplers created afterwards (coalgpu_set_emission_mode)."""
+    _check(load_library().coalgpu_set_emission_mode({"reference": 0, "stable": 1}[mode]))
 
 
 def _result_arrays(p: Problem):

@@ -96,6 +96,16 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
 int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples,
                               uint32_t quadrature_points, uint64_t seed, int device, coalgpu_result* results);
 
+/* Emission-table mode of the samplers created AFTER the call (process-wide, thread-safe):
+ *   COALGPU_EMISSION_REFERENCE (default): ConditionalSamplingHMM.cpp:184-226 in the reference's operation order --
+ *       tables bit-identical to the reference's; entries below ~1e-13 are rounding noise / the epsilon clamp.
+ *   COALGPU_EMISSION_STABLE: the same quantity from the closed form of the double sum, by quadrature (every entry to
+ *       1e-14 relative, any locus length). Agrees with the reference mode on every entry that is
+ *       large enough to matter; histories are then no longer bit-identical to the oracle's. */
+#define COALGPU_EMISSION_REFERENCE 0
+#define COALGPU_EMISSION_STABLE 1
+int coalgpu_set_emission_mode(int mode);
+
 /* ---- staged API --------------------------------------------------------------------------------*/
 /* Build the HMM tables on the host (ConditionalSamplingHMM.cpp:36-226, same operation order),
  * upload problem + tables to `device`. quadrature_points must be 4, 8 or 16 (ConditionalSamplingHMM.cpp:39-58). */

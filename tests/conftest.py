@@ -67,6 +67,8 @@ def host_shim():
     L.hs_build.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.hs_build_q.restype = C.c_void_p
     L.hs_build_q.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hs_build_mode.restype = C.c_void_p
+    L.hs_build_mode.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.hs_free.argtypes = [C.c_void_p]
     L.hs_tables.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
     L.hs_pismc.restype = C.c_double

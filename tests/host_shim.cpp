@@ -21,6 +21,12 @@ void* hs_build_q(int Q, int LA, int LB, int n_max, int T, const double* thetas, 
     if (!build_tables(Q, LA, LB, n_max, th, rr, h->tab)) { delete h; return nullptr; }
     return h;
 }
+void* hs_build_mode(int Q, int mode, int LA, int LB, int n_max, int T, const double* thetas, const double* rrates) {
+    hs_tables_t* h = new hs_tables_t;
+    std::vector<double> th(thetas, thetas + T), rr(rrates, rrates + T);
+    if (!build_tables(Q, LA, LB, n_max, th, rr, h->tab, 0, mode)) { delete h; return nullptr; }
+    return h;
+}
 void* hs_build(int LA, int LB, int n_max, int T, const double* thetas, const double* rrates) {
     hs_tables_t* h = new hs_tables_t;
     std::vector<double> th(thetas, thetas + T), rr(rrates, rrates + T);
