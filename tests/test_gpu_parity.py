@@ -533,3 +533,29 @@ def test_stable_emission_mode_on_the_device(oracle, cuda_lib):
     out_ref = cb.ImportanceSampler().run_sampler(p, 4000, seed=5)
     se = np.hypot(out_ref.standard_error(), out_stable.standard_error())
     assert np.all(np.abs(out_ref.likelihood - out_stable.likelihood) < 5 * se + 1e-9)
+
+
+@pytest.mark.parametrize("LA,LB", [(40, 24), (63, 1), (1, 63), (32, 32)])
+def test_maximum_haplotype_width_64_sites(oracle, cuda_lib, LA, LB):
+    """LA + LB = 64: the whole 64-bit haplotype word is in use (locus B starts at bit LA; masks, the A^B concatenation
+    and the C -> A/B splits of ProposalEngine.cpp:596-640 at their limits). Event encodings bit-identical to the oracle."""
+    from coalescenator_b200.problem import Problem
+    rng = np.random.default_rng(5 + LA)
+    fa = [int(rng.integers(0, 1 << min(LA, 62))) for _ in range(3)]
+    fb = [int(rng.integers(0, 1 << min(LB, 62))) for _ in range(3)]
+    types = []
+    for t in range(2):
+        cnt = {}
+        for _ in range(4):
+            f = int(rng.integers(0, 3))
+            a = fa[f] ^ ((1 << int(rng.integers(0, LA))) if rng.random() < 0.5 else 0)
+            b = fb[f] ^ ((1 << int(rng.integers(0, LB))) if rng.random() < 0.5 else 0)
+            u = rng.random()
+            key = (2, a | (b << LA)) if u < 0.6 else ((0, a) if u < 0.8 else (1, b << LA))
+            cnt[key] = cnt.get(key, 0) + 1
+        types.append([(g, w, c) for (g, w), c in cnt.items()])
+    if LA == 63:      # make sure the top bit of the word is set somewhere
+        g, w, c = types[0][0]
+        types[0][0] = (g, w | (1 << 63) if g != 0 else w | (1 << 62), c)
+    p = Problem(LA, LB, [0.0, 30.0], [100.0, 100.0], 1.0, 2.5e-5, 1000.0, 5e-5, [2.5e-5], [5e-5], [1000.0], types, name="max%d_%d" % (LA, LB))
+    _compare_histories(oracle, p, 12, seed=7, max_events=1 << 16)
