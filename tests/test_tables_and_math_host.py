@@ -197,3 +197,4 @@ def test_stable_emission_mode_against_300_digit_arithmetic(host_shim):
     assert worst_stable < 1e-12
     assert worst_ref_big < 1e-9
     assert worst_ref_tiny > 1e-3
+
