@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kCounters = 16;     // device counters per sampler (SampleArgs::counters)
 thread_local std::string g_err;
-std::atomic<int> g_emission_mode{kEmissionReference};
+std::atomic<int> g_emission_mode{COALGPU_EMISSION_REFERENCE};   // API value (coalgpu_set_emission_mode)
 std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -92,6 +92,7 @@ struct coalgpu_sampler {
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
     int inj_max = 0, sm_count = 0;    // most input types of one sampling time; SMs of the device
     int type_estimate = 0;            // HostPrep::type_estimate
+    bool rows_on_device_only = false; // emission parts were built on the device: coalgpu_tables fetches the rows first
     bool fast = false, fast_forced = false;   // forced: COALGPU_KMAX_FAST > 0 (tests), two passes whatever the launch size
     DevProblem P_fast{};
     int fast_grid = 0, fast_group = 32;
@@ -114,6 +115,8 @@ namespace {
 struct HostPrep {
     int T = 0, LA = 0, LB = 0, G = 0;
     int type_estimate = 0;    // distinct two-locus haplotypes + distinct A parts + distinct B parts of the input (see choose_geometry)
+    bool device_emission = false;     // emission parts of the rows are built by emission_stable_kernel after the upload
+    std::vector<double> thetas; int Q = 16;
     DevProblem P{};
     HostTables tab;
     std::vector<int> type_off;
@@ -201,7 +204,13 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
         thetas[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_mu;
         rrates[c] = 4 * p->driving_lambda * p->viral[c] * p->driving_rho;
     }
-    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, h.tab, table_threads, g_emission_mode.load())) return bad("table construction failed");
+    // emission tables: reference order (host, cached), stable on the host, or left empty for the device kernel (finish_device)
+    const int emode = g_emission_mode.load();
+    h.device_emission = emode == COALGPU_EMISSION_STABLE;
+    h.thetas = thetas; h.Q = (int)Q;
+    if (!build_tables((int)Q, LA, LB, n_max, thetas, rrates, h.tab, table_threads,
+                      emode == COALGPU_EMISSION_STABLE ? kEmissionNone : emode == COALGPU_EMISSION_STABLE_HOST ? kEmissionStable : kEmissionReference))
+        return bad("table construction failed");
 
     h.ep.resize(T);
     for (int c = 0; c < T; c++) {
@@ -380,6 +389,29 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     put(o_tw, h.type_w.data(), h.type_w.size() * sizeof(unsigned long long));
     put(o_tcg, h.type_cg.data(), h.type_cg.size() * sizeof(unsigned int));
     if (ue == cudaSuccess) ue = cudaMemsetAsync(base + o_cnt, 0, kCounters * sizeof(unsigned long long), up);
+    if (ue == cudaSuccess && h.device_emission) {
+        // stable emission mode: the table sets' thetas ride in the arena; K4 fills EA | EB | wEA | wEB of every row
+        std::vector<double> set_theta(s->tab.n_sets, 0.0);
+        for (int c = 0; c < h.T; c++) set_theta[s->tab.set_of_epoch[c]] = h.thetas[c];
+        double* d_theta = nullptr;
+        ue = dev_alloc((void**)&d_theta, set_theta.size() * sizeof(double), up);
+        if (ue == cudaSuccess) { s->allocs.push_back(d_theta); ue = cudaMemcpyAsync(d_theta, set_theta.data(), set_theta.size() * sizeof(double), cudaMemcpyHostToDevice, up); }
+        if (ue == cudaSuccess) {
+            const TableLayout& lay = s->tab.lay;
+            EmissionArgs ea{};
+            ea.rows = (double*)(base + o_rows); ea.thetas = d_theta;
+            ea.n_sets = s->tab.n_sets; ea.n_max = s->tab.n_max; ea.row_doubles = lay.row_doubles; ea.LA = h.LA; ea.LB = h.LB; ea.Q = h.Q;
+            ea.off_EA = lay.off_EA; ea.off_EB = lay.off_EB; ea.off_wEA = lay.off_wEA; ea.off_wEB = lay.off_wEB;
+            for (int i = 0; i <= kQ; i++) ea.t[i] = s->tab.quad[i];
+            for (int i = 0; i < kQ; i++) ea.w[i] = s->tab.w[i];
+            const long long total = (long long)ea.n_sets * ea.n_max * (h.LA + h.LB + 2);
+            const int blocks = (int)std::min<long long>((total + 127) / 128, (long long)sm_count * 16);
+            emission_stable_kernel<<<blocks, 128, 0, up>>>(ea);
+            g_launches++;
+            ue = cudaGetLastError();
+            s->rows_on_device_only = true;
+        }
+    }
     if (ue != cudaSuccess) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, std::string("upload: ") + cudaGetErrorString(ue)); }
     P.rows = (const double*)(base + o_rows); P.set_of_epoch = (const int*)(base + o_set); P.times = (const double*)(base + o_times);
     P.ep = (const EpochConst*)(base + o_ep); P.grid = (const GridConst*)(base + o_grid); P.lfact = (const double*)(base + o_lf);
@@ -409,8 +441,8 @@ const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
 uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
 
 int coalgpu_set_emission_mode(int mode) {
-    if (mode != COALGPU_EMISSION_REFERENCE && mode != COALGPU_EMISSION_STABLE) return fail(COALGPU_EINVAL, "unknown emission mode");
-    g_emission_mode.store(mode == COALGPU_EMISSION_STABLE ? kEmissionStable : kEmissionReference);
+    if (mode != COALGPU_EMISSION_REFERENCE && mode != COALGPU_EMISSION_STABLE && mode != COALGPU_EMISSION_STABLE_HOST) return fail(COALGPU_EINVAL, "unknown emission mode");
+    g_emission_mode.store(mode);
     return 0;
 }
 
@@ -899,6 +931,13 @@ int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* 
     if (time_idx < 0 || time_idx >= s->T || n_all < 1 || n_all > s->tab.n_max) return fail(COALGPU_EINVAL, "table index out of range");
     const TableLayout& lay = s->tab.lay;
     const int set = s->tab.set_of_epoch[time_idx];
+    if (s->rows_on_device_only) {       // emission parts live on the device only: fetch the rows once
+        if (s->tab.rows.empty()) return fail(COALGPU_EINVAL, "table rows were released (batch sampler)");
+        CU_OK(cudaSetDevice(s->device));
+        CU_OK(cudaDeviceSynchronize());
+        CU_OK(cudaMemcpy(s->tab.rows.data(), s->P.rows, s->tab.rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        s->rows_on_device_only = false;
+    }
     const double* row = s->tab.row(set, n_all);
     const double* yy = s->tab.y.data() + ((size_t)set * s->tab.n_max + (n_all - 1)) * kQ;
     if (w) std::memcpy(w, s->tab.w.data(), sizeof(double) * kQ);

@@ -1027,4 +1027,62 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 
 size_t history_group_bytes(int kmax, int pvmax, int Ltot, int W) { return group_mem_bytes(kmax, pvmax, Ltot, W); }
 
+// K4: emission tables of the stable mode on the device (the host version and the derivation are in
+// coal_tables.cpp: E[i][d] = 1/(w_i 2^L) * integral over interval i of e^-t (1+e^-at)^(L-d) (1-e^-at)^d dt, a = 2 theta/n,
+// 32-point Gauss-Legendre on the finite intervals, 32-point Gauss-Laguerre on the last). One thread per
+// (table set, lineage count n, locus, distance d): 16 intervals x 32 nodes, then the weighted sums wE[d].
+// On the host this costs seconds per data set (4 transcendentals per node); here it is a millisecond.
+__constant__ double c_GLx[32] = {-0.9972638618494816, -0.9856115115452684, -0.9647622555875064, -0.9349060759377397, -0.8963211557660521, -0.84936761373257, -0.7944837959679424, -0.7321821187402897, -0.6630442669302152, -0.5877157572407623, -0.5068999089322294, -0.42135127613063533, -0.33186860228212767, -0.23928736225213706, -0.1444719615827965, -0.048307665687738324, 0.048307665687738324, 0.1444719615827965, 0.23928736225213706, 0.33186860228212767, 0.42135127613063533, 0.5068999089322294, 0.5877157572407623, 0.6630442669302152, 0.7321821187402897, 0.7944837959679424, 0.84936761373257, 0.8963211557660521, 0.9349060759377397, 0.9647622555875064, 0.9856115115452684, 0.9972638618494816};
+__constant__ double c_GLw[32] = {0.007018610009470506, 0.016274394730905743, 0.025392065309262024, 0.034273862913021765, 0.042835898022226836, 0.05099805926237609, 0.058684093478535565, 0.06582222277636168, 0.07234579410884834, 0.07819389578707023, 0.08331192422694671, 0.08765209300440378, 0.09117387869576378, 0.09384439908080451, 0.09563872007927471, 0.09654008851472766, 0.09654008851472766, 0.09563872007927471, 0.09384439908080451, 0.09117387869576378, 0.08765209300440378, 0.08331192422694671, 0.07819389578707023, 0.07234579410884834, 0.06582222277636168, 0.058684093478535565, 0.05099805926237609, 0.042835898022226836, 0.034273862913021765, 0.025392065309262024, 0.016274394730905743, 0.007018610009470506};
+__constant__ double c_Lagx[32] = {0.04448936583326739, 0.23452610951961825, 0.5768846293018863, 1.072448753817818, 1.7224087764446456, 2.5283367064257942, 3.492213273021994, 4.616456769749767, 5.903958504174244, 7.358126733186241, 8.982940924212597, 10.78301863253997, 12.763697986742725, 14.931139755522558, 17.292454336715316, 19.855860940336054, 22.630889013196775, 25.628636022459247, 28.862101816323474, 32.346629153964734, 36.10049480575197, 40.14571977153944, 44.50920799575494, 49.22439498730864, 54.33372133339691, 59.89250916213402, 65.97537728793505, 72.68762809066271, 80.18744697791352, 88.7353404178924, 98.82954286828398, 111.7513980979377};
+__constant__ double c_Lagw[32] = {0.10921834195242515, 0.2104431079387924, 0.23521322966984298, 0.19590333597287354, 0.1299837862860684, 0.07057862386571556, 0.03176091250917397, 0.011918214834838204, 0.003738816294611417, 0.0009808033066149246, 0.0002148649188013578, 3.920341967987801e-05, 5.934541612868448e-06, 7.41640457866734e-07, 7.604567879120552e-08, 6.350602226625618e-09, 4.281382971040738e-10, 2.305899491891237e-11, 9.799379288726772e-13, 3.2378016577291567e-14, 8.171823443420549e-16, 1.542133833393811e-17, 2.119792290163547e-19, 2.0544296737880036e-21, 1.3469825866373617e-23, 5.661294130397462e-26, 1.4185605454629684e-28, 1.9133754944539943e-31, 1.1922487600982012e-34, 2.6715112192396625e-38, 1.3386169421064243e-42, 4.5105361938987784e-48};
+struct EmissionArgs {
+    double* rows;               // [n_sets][n_max][row_doubles]
+    const double* thetas;       // [n_sets]
+    int n_sets, n_max, row_doubles, LA, LB, Q;
+    int off_EA, off_EB, off_wEA, off_wEB;
+    double t[kQd + 1], w[kQd];
+};
+__global__ void __launch_bounds__(128) emission_stable_kernel(const EmissionArgs A) {
+    const int per_row = A.LA + 1 + A.LB + 1;
+    const long long total = (long long)A.n_sets * A.n_max * per_row;
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(id % per_row);
+        const long long rn = id / per_row;
+        const int n = (int)(rn % A.n_max) + 1, set = (int)(rn / A.n_max);
+        const bool locA = k <= A.LA;
+        const int L = locA ? A.LA : A.LB, d = locA ? k : k - A.LA - 1;
+        double* row = A.rows + (size_t)rn * A.row_doubles;
+        double* E = row + (locA ? A.off_EA : A.off_EB) + (size_t)d * kEStride;
+        const double a = 2 * A.thetas[set] / (double)n;
+        const double two_L = exp2((double)L);
+        double wE = 0.0;
+        for (int i = 0; i < kQd; i++) {
+            double e = 0.0;
+            if (i < A.Q) {
+                double v = 0.0;
+                const double lo = A.t[i];
+                if (i + 1 < A.Q) {
+                    const double hi = A.t[i + 1], h = 0.5 * (hi - lo), c = 0.5 * (hi + lo);
+                    for (int q = 0; q < 32; q++) {
+                        const double tt = c + h * c_GLx[q], x = exp(-a * tt);
+                        v += c_GLw[q] * exp(-tt + (double)(L - d) * log1p(x) + (d > 0 ? (double)d * log1p(-x) : 0.0));
+                    }
+                    v *= h;
+                } else {
+                    for (int q = 0; q < 32; q++) {
+                        const double x = exp(-a * (lo + c_Lagx[q]));
+                        v += c_Lagw[q] * exp((double)(L - d) * log1p(x) + (d > 0 ? (double)d * log1p(-x) : 0.0));
+                    }
+                    v *= exp(-lo);
+                }
+                e = fmax(v / (A.w[i] * two_L), 2.220446049250313e-16);      // the reference's clamp (ConditionalSamplingHMM.cpp:221)
+            }
+            E[i] = e;
+            wE += A.w[i] * e;
+        }
+        row[(locA ? A.off_wEA : A.off_wEB) + d] = wE;
+    }
+}
+
 }  // namespace coalgpu

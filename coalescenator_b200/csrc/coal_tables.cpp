@@ -262,14 +262,16 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
 
     for (int s = 0; s < out.n_sets; s++) {
         const double theta = thetas[rep[s]], r = r_rates[rep[s]];
-        const std::shared_ptr<EmissionBlock> bA = emission_block(Q, LA, emission_mode, theta, n_max, t, w, bin, bw, threads);
-        const std::shared_ptr<EmissionBlock> bB = (LB == LA) ? bA : emission_block(Q, LB, emission_mode, theta, n_max, t, w, bin, bw, threads);
+        const bool emit = emission_mode != kEmissionNone;
+        const std::shared_ptr<EmissionBlock> bA = emit ? emission_block(Q, LA, emission_mode, theta, n_max, t, w, bin, bw, threads) : nullptr;
+        const std::shared_ptr<EmissionBlock> bB = !emit ? nullptr : (LB == LA) ? bA : emission_block(Q, LB, emission_mode, theta, n_max, t, w, bin, bw, threads);
         for (int n = 1; n <= n_max; n++) {
             const size_t idx = (size_t)s * n_max + (n - 1);
             double* row = out.rows.data() + idx * lay.row_doubles;
             double* y = out.y.data() + idx * kQ;
             transition_row(Q, t, w, e0, r, (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
             for (int i = 0; i < kQ; i++) row[lay.off_yw + i] = y[i] * w[i];
+            if (!emit) continue;
             const double* a = bA->data.data() + (size_t)(n - 1) * bA->stride;
             const double* b = bB->data.data() + (size_t)(n - 1) * bB->stride;
             std::memcpy(row + lay.off_EA, a, sizeof(double) * (LA + 1) * kEStride);

@@ -47,7 +47,7 @@ struct HostTables {
 // threads: host threads used for blocks that are not cached yet (0 = all hardware threads, at most 16).
 // emission_mode: kEmissionReference = the reference's double sum in its operation order (bit-identical tables, loses
 // accuracy beyond ~20-30 sites per locus); kEmissionStable = the same quantity by quadrature of its closed form.
-enum { kEmissionReference = 0, kEmissionStable = 1 };
+enum { kEmissionReference = 0, kEmissionStable = 1, kEmissionNone = 2 };   // None: emission parts left zero (built on the device)
 bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& thetas,
                   const std::vector<double>& r_rates, HostTables& out, int threads = 0, int emission_mode = kEmissionReference);
 void clear_table_cache();

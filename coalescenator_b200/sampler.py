@@ -145,9 +145,10 @@ class SamplerOutput:
 
 
 def set_emission_mode(mode: str) -> None:
-    """'reference' (default: tables bit-identical to the reference's) or 'stable' (closed form by quadrature, every
-    entry accurate at any locus length); applies to samplers created afterwards (coalgpu_set_emission_mode)."""
-    _check(load_library().coalgpu_set_emission_mode({"reference": 0, "stable": 1}[mode]))
+    """'reference' (default: tables bit-identical to the reference's), 'stable' (closed form by quadrature, every
+    entry accurate at any locus length; built by a kernel on the device) or 'stable-host' (the same quadrature on the
+    host); applies to samplers created afterwards (coalgpu_set_emission_mode)."""
+    _check(load_library().coalgpu_set_emission_mode({"reference": 0, "stable": 1, "stable-host": 2}[mode]))
 
 
 def _result_arrays(p: Problem):

@@ -100,10 +100,14 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
  *   COALGPU_EMISSION_REFERENCE (default): ConditionalSamplingHMM.cpp:184-226 in the reference's operation order --
  *       tables bit-identical to the reference's; entries below ~1e-13 are rounding noise / the epsilon clamp.
  *   COALGPU_EMISSION_STABLE: the same quantity from the closed form of the double sum, by quadrature (every entry to
- *       1e-14 relative, any locus length). Agrees with the reference mode on every entry that is
- *       large enough to matter; histories are then no longer bit-identical to the oracle's. */
+ *       1e-14 relative, any locus length), built ON THE DEVICE by its own kernel. Agrees with the
+ *       reference mode on every entry that is large enough to matter; histories are then no longer bit-identical to
+ *       the oracle's.
+ *   COALGPU_EMISSION_STABLE_HOST: the same quadrature evaluated on the host (seconds per data set; the CPU-testable
+ *       statement of what the device kernel computes). */
 #define COALGPU_EMISSION_REFERENCE 0
 #define COALGPU_EMISSION_STABLE 1
+#define COALGPU_EMISSION_STABLE_HOST 2
 int coalgpu_set_emission_mode(int mode);
 
 /* ---- staged API --------------------------------------------------------------------------------*/

@@ -508,6 +508,23 @@ def test_stable_emission_mode_on_the_device(oracle, cuda_lib):
     p, _, _ = load_golden("cfg2_pair0")
     ref_tab = oracle.tables(p, 7, 1)
     try:
+        # the device kernel (K4) against the host statement of the same quadrature, incl. 8 quadrature intervals
+        import time
+        for Q in (16, 8):
+            tabs = {}
+            for mode in ("stable-host", "stable"):
+                cb.set_emission_mode(mode)
+                t0 = time.perf_counter()
+                sq = _sampler(p, Q)
+                tabs[mode] = [sq.tables(n, c) for n, c in ((1, 0), (7, 1), (40, 4))]
+                print("Q = %d, %s: sampler + tables in %.1f ms" % (Q, mode, 1e3 * (time.perf_counter() - t0)))
+                sq.close()
+            for a, b in zip(tabs["stable-host"], tabs["stable"]):
+                for key in ("EA", "EB"):
+                    assert a[key].shape == b[key].shape and (a[key][:Q] > 0).all()
+                    np.testing.assert_allclose(b[key], a[key], rtol=1e-12, atol=0)
+                for key in ("w", "y", "z"):
+                    assert np.array_equal(a[key], b[key])
         cb.set_emission_mode("stable")
         s = _sampler(p)
         tab = s.tables(7, 1)
