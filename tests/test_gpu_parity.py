@@ -577,3 +577,61 @@ def test_maximum_haplotype_width_64_sites(oracle, cuda_lib, LA, LB):
         types[0][0] = (g, w | (1 << 63) if g != 0 else w | (1 << 62), c)
     p = Problem(LA, LB, [0.0, 30.0], [100.0, 100.0], 1.0, 2.5e-5, 1000.0, 5e-5, [2.5e-5], [5e-5], [1000.0], types, name="max%d_%d" % (LA, LB))
     _compare_histories(oracle, p, 12, seed=7, max_events=1 << 16)
+
+
+def test_full_size_cfg2_pair_properties(oracle, cuda_lib):
+    """BASELINE config 2 at its full size (100,000 importance samples of one cfg2 locus pair; the launch takes the
+    tuned two-pass W = 8 path). The oracle needs minutes for that many histories, so the check is through
+    size-independent properties: (1) 96 histories picked at random from the full launch carry the log-weight, tmrca
+    and lineage counts the oracle computes for exactly those indices (a history is a function of (seed, index), whatever
+    the launch size or geometry); (2) the reduction of the whole equals the merge of the reductions of three unequal
+    parts; (3) counters are consistent (sum of per-history event counts, no overflow, every weight finite);
+    (4) the drop-in call (pilot chunk + tuned rest) returns the same estimates."""
+    import torch
+    import coalescenator_b200 as cb
+    from coalescenator_b200.distributed import merge_pairs
+    from coalescenator_b200.problem import make_config, sub_problem
+    aln, loci, pairs = make_config(2)
+    p = sub_problem(aln, loci, *pairs[40])
+    n, seed = 100_000, 42
+    s = _sampler(p)
+    buf = s.alloc(n)
+    s.sample(buf, seed, 0, 8192); torch.cuda.synchronize()
+    st = s.tune()
+    s.sample(buf, seed, 0, n); torch.cuda.synchronize()
+    cap = s.capacity_stats()
+    print("full size: first-pass store %d of %d, %d lanes per history, %d deferred" % (cap["store_first_pass"], cap["store_full"], cap["lanes_per_history"], cap["n_deferred"]))
+    assert cap["store_first_pass"] < cap["store_full"]            # the two-pass path is what ran
+    w = buf["weights"].cpu().numpy(); tm = buf["tmrca"].cpu().numpy(); lin = buf["lineages"].cpu().numpy(); nev = buf["nevents"].cpu().numpy()
+    assert np.isfinite(w).all() and (tm > 0).all() and (nev > 0).all()
+    # (1) random histories against the oracle at their own indices
+    rng = np.random.default_rng(3)
+    for h in rng.choice(n, size=96, replace=False):
+        ref = oracle.run(p, 1, seed, mode=oracle.MODE_CANONICAL, first=int(h))
+        np.testing.assert_allclose(w[h], ref["weights"][0], rtol=RTOL_WEIGHT)
+        np.testing.assert_allclose(tm[h], ref["tmrca"][0], rtol=1e-12)
+        assert np.array_equal(lin[h], ref["lineages"][0]) and nev[h] == ref["n_events"][0]
+    # (2) reduction of the whole == merge of the parts
+    whole = s.partials(buf, n).clone()
+    parts = []
+    for a, b in ((0, 7), (7, 33_341), (33_341, n)):
+        sub = dict(weights=buf["weights"][a:b].contiguous(), tmrca=buf["tmrca"][a:b].contiguous(), lineages=buf["lineages"][a:b].contiguous(),
+                   partials=torch.empty_like(buf["partials"]))
+        parts.append(s.partials(sub, b - a).clone())
+    merged = merge_pairs(torch.stack(parts))
+    lse = lambda t: (t[..., 0] + torch.log(t[..., 1])).cpu().numpy()
+    np.testing.assert_allclose(lse(merged), lse(whole), rtol=1e-13)
+    # (3) counters
+    c = s.counters()
+    assert c["n_overflow"] == 0
+    total_launched = 8192 + n
+    assert c["n_events"] == int(nev.sum()) + int(nev[:8192].sum())     # the warm-up launch drew histories 0..8191 as well
+    out_staged = s.finalize(whole.cpu().numpy(), n)
+    s.close()
+    # (4) the drop-in call
+    out = cb.ImportanceSampler().run_sampler(p, n, seed=seed)
+    np.testing.assert_allclose(out.likelihood, out_staged.likelihood, rtol=1e-12)
+    np.testing.assert_allclose(out.likelihoodSq, out_staged.likelihoodSq, rtol=1e-12)
+    np.testing.assert_allclose(out.tmrca, out_staged.tmrca, rtol=1e-10)
+    assert out.n_events == int(nev.sum())
+    print("full size: log sum w = %.6f, ESS = %.1f, %.1f events per history" % (out.likelihood.ravel()[0], out.ess.ravel()[0], nev.mean()))
