@@ -65,5 +65,20 @@ def main():
         print(name, "LA", p.LA, "LB", p.LB, "T", p.T, "n", p.n_lineages(), "G", p.G, os.path.getsize(tmp + ".gz"), "bytes")
 
 
+def big_statistical_fixture(n=60000, threads=8, seed=777):
+    """stat_grid.big_result.json: the reference's estimates for the stat_grid problem from 60,000 histories (8 threads),
+    so that the GPU's estimates can be held against the reference's with small Monte-Carlo error on both sides."""
+    from coalescenator_b200.problem import Problem
+    p = Problem.load(os.path.join(HERE, "stat_grid.coalprob"))
+    res = O.run_reference(p, n, seed, threads=threads)
+    res.pop("seconds", None)
+    with open(os.path.join(HERE, "stat_grid.big_result.json"), "w") as fh:
+        json.dump(res, fh, indent=0)
+    print("stat_grid.big_result.json", n, "histories")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["big"]:
+        big_statistical_fixture()
+        sys.exit(0)
     main()
