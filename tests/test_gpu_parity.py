@@ -671,3 +671,26 @@ def test_estimates_against_60000_reference_histories(cuda_lib):
     np.testing.assert_allclose(np.exp(out.tmrca.ravel()[big]), np.exp(np.array(ref["tmrca"])[big]), rtol=0.05)
     for l in range(p.T):
         np.testing.assert_allclose(np.exp(out.lineages_remaining[l].ravel()[big]), np.exp(np.array(ref["lineages_remaining"][str(l)])[big]), rtol=0.05)
+
+
+def test_one_driving_point_per_grid_point(cuda_lib):
+    """SURVEY.md section 8d.3, optional variant: every grid point proposes its own histories (an extra batch axis
+    through coalgpu_run_sampler_batch). Each entry equals run_sampler with driving = target = that point, and the
+    effective sample sizes no longer collapse away from a single driving point."""
+    import dataclasses
+    import coalescenator_b200 as cb
+    p, _, _ = load_golden("stat_grid")
+    smp = cb.ImportanceSampler()
+    n = 4000
+    out = smp.run_sampler_driving_grid(p, n, seed=8)
+    assert out.likelihood.shape == (len(p.target_mu), len(p.target_rho), len(p.target_lambda))
+    for (i, j, k) in ((0, 0, 0), (2, 1, 2), (1, 0, 2)):
+        q = dataclasses.replace(p, driving_mu=p.target_mu[i], driving_rho=p.target_rho[j], driving_lambda=p.target_lambda[k],
+                                target_mu=[p.target_mu[i]], target_rho=[p.target_rho[j]], target_lambda=[p.target_lambda[k]])
+        one = smp.run_sampler(q, n, seed=8)
+        assert out.likelihood[i, j, k] == one.likelihood.ravel()[0] and out.tmrca[i, j, k] == one.tmrca.ravel()[0]
+        assert np.array_equal(out.lineages_remaining[:, i, j, k], one.lineages_remaining.ravel())
+    single = smp.run_sampler(p, n, seed=8)
+    print("ESS with one driving point: min %.1f median %.1f; one driving point per grid point: min %.1f median %.1f"
+          % (single.ess.min(), np.median(single.ess), out.ess.min(), np.median(out.ess)))
+    assert np.median(out.ess) > np.median(single.ess)
