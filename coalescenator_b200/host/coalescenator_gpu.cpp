@@ -2,7 +2,8 @@
 // (/root/reference/src/main.cpp:48-354), calling the B200 path through the C ABI of include/coalgpu.h
 // where the reference calls ImportanceSampler::runSampler (main.cpp:281-283).
 //
-// Same options as the reference (main.cpp:54-88); additions: --device N, --dump-problems DIR (write one
+// Same options as the reference (main.cpp:54-88); additions: --device N, --gpus N (locus pairs dealt round robin to
+// devices device..device+N-1, one host thread per device, no exchange needed: pairs are independent), --dump-problems DIR (write one
 // .coalprob file per eligible locus pair and stop: needs no GPU), --ess (append an ESS column), --summary (side-car
 // <prefix>_summary.txt: the grid point that maximises the composite likelihood, per-pair work and ESS, throughput).
 #include <chrono>
@@ -18,6 +19,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/coalgpu.h"
@@ -35,7 +37,7 @@ struct Options {
     std::string rho_list = "1e-10,1e-9,1e-8,1e-7,1e-6,5e-6,1e-5,5e-5,1e-4,5e-4,1e-3";
     double generation_time = 0, mutation_driving = 2.5e-5, scale_driving = 1000, rho_driving = 5e-5;
     bool have_coords = false, have_generation_time = false, ess = false, summary = false;
-    int device = 0;
+    int device = 0, gpus = 1;
     std::string dump_dir;
 };
 
@@ -47,7 +49,7 @@ std::string now() {   // Utils.hpp:211-265: dd/mm/yyyy hh:mm:ss
 
 void usage() {
     std::cout << "\n#### Coalescenator (B200) ####\n"
-              << "  -h [ --help ]  -p [ --num-threads ] N (ignored)  -s [ --seed ] N  --output-file-prefix S  --device N\n"
+              << "  -h [ --help ]  -p [ --num-threads ] N (ignored)  -s [ --seed ] N  --output-file-prefix S  --device N  --gpus N\n"
               << "  -f [ --fasta-list ] a.fa,b.fa  -t [ --time-list ] t1,t2  -v [ --viral-list ] v1,v2  -g [ --generation-time ] X\n"
               << "  --coordinate-list [l-r],... | bp1,bp2   --loci-size N (1)\n"
               << "  -i [ --mc-samples ] N (500000)  --mutation-list L  --mutation-driving X (2.5e-5)  --scale-list L  --scale-driving X (1000)\n"
@@ -87,6 +89,7 @@ Options parse(int argc, char** argv) {
         else if (k == "--min-comp-dist") o.min_dist = (unsigned)std::stoul(v);
         else if (k == "--max-comp-dist") o.max_dist = (unsigned)std::stoul(v);
         else if (k == "--device") o.device = std::stoi(v);
+        else if (k == "--gpus") o.gpus = std::max(1, std::stoi(v));
         else if (k == "--dump-problems") o.dump_dir = v;
         else throw std::runtime_error("unrecognised option '" + k + "'");
     }
@@ -231,8 +234,30 @@ int main(int argc, char** argv) {
                 results[q] = coalgpu_result{j.like.data(), j.likesq.data(), j.tm.data(), j.lin.data(), j.ess.data(), 0, 0, 0, 0.0};
             }
             const auto tb0 = std::chrono::steady_clock::now();
-            const int rc = coalgpu_run_sampler_batch((int)probs.size(), probs.data(), o.mc_samples, 16, o.seed, o.device, results.data());   // replaces :281-283
-            if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+            if (o.gpus <= 1) {
+                const int rc = coalgpu_run_sampler_batch((int)probs.size(), probs.data(), o.mc_samples, 16, o.seed, o.device, results.data());   // replaces :281-283
+                if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+            } else {
+                // pairs are independent: device d takes pairs d, d+gpus, ... and runs its own batch; a pair's histories
+                // depend on (seed, index) only, so the output does not depend on the number of GPUs
+                std::vector<std::vector<coalgpu_problem>> dp(o.gpus);
+                std::vector<std::vector<coalgpu_result>> dr(o.gpus);
+                std::vector<std::vector<size_t>> di(o.gpus);
+                for (size_t q = 0; q < probs.size(); q++) { const int d = (int)(q % o.gpus); dp[d].push_back(probs[q]); dr[d].push_back(results[q]); di[d].push_back(q); }
+                std::vector<std::string> errs(o.gpus);
+                std::vector<std::thread> th;
+                for (int d = 0; d < o.gpus; d++)
+                    th.emplace_back([&, d]() {
+                        if (dp[d].empty()) return;
+                        if (coalgpu_run_sampler_batch((int)dp[d].size(), dp[d].data(), o.mc_samples, 16, o.seed, o.device + d, dr[d].data()))
+                            errs[d] = coalgpu_last_error();      // thread-local in the library: read on the thread that failed
+                    });
+                for (std::thread& t : th) t.join();
+                for (int d = 0; d < o.gpus; d++) {
+                    if (!errs[d].empty()) throw std::runtime_error("coalgpu (device " + std::to_string(o.device + d) + "): " + errs[d]);
+                    for (size_t k = 0; k < di[d].size(); k++) results[di[d][k]] = dr[d][k];
+                }
+            }
             sampling_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
             for (size_t q = 0; q < jobs.size(); q++) {
                 PairStat st;

@@ -177,3 +177,25 @@ def test_host_driver_end_to_end_outputs(tmp_path):
     best = max(comp[1:], key=lambda c: float(c[3]))
     assert (summ[0][2], summ[0][4], summ[0][6]) == (best[0], best[1], best[2])
     assert len(summ) == 3 + len(problems) and all(float(x[4]) >= 1.0 - 1e-9 for x in summ[3:])
+
+
+@pytest.mark.gpu
+def test_host_driver_two_gpus_same_files(tmp_path):
+    """--gpus 2: locus pairs dealt round robin to two devices (one host thread per device); the output files are
+    byte-identical to the single-GPU run (a pair's histories depend on (seed, index) only)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from coalescenator_b200 import build as B
+    B.build_cuda()
+    build_host()
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    common = ["-f", fl, "-t", tl, "-v", vl, "-g", "1.5", "--loci-size", "30", "--mutation-list", "1e-5,2.5e-5", "--scale-list", "1000",
+              "--rho-list", "5e-5,1e-4", "-s", "77", "-i", "800", "--max-comp-dist", "60"]
+    outs = []
+    for gpus in ("1", "2"):
+        prefix = str(tmp_path / ("run" + gpus))
+        r = subprocess.run([HOST] + common + ["--output-file-prefix", prefix, "--gpus", gpus], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs.append((open(prefix + "_pairwise_loglikelihood.txt").read(), open(prefix + "_composite_loglikelihood.txt").read()))
+    assert outs[0] == outs[1] and outs[0][0].count("\n") > 4
