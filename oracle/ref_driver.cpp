@@ -114,11 +114,26 @@ int main(int argc, char** argv) {
     coalref_trace_close();
 
 #ifdef COALREF_GPU_BINDING
+    // the batch method of the binding on three copies of the pair: every output must equal the single call's
+    bool batch_equal = true;
+    {
+        std::vector<Sample*> ss(3, &sample); std::vector<ModelParameters> ms(3, p.mp);
+        std::vector<SamplerOutput<double> > bo = sampler.runSamplerBatch(ss, ms, n_samples, 16, seed);
+        for (size_t b = 0; b < bo.size(); b++)
+            for (uint i = 0; i < res.likelihood().dim1(); i++) for (uint j = 0; j < res.likelihood().dim2(); j++) for (uint k = 0; k < res.likelihood().dim3(); k++)
+                batch_equal = batch_equal && bo[b].likelihood().getElement(i, j, k) == res.likelihood().getElement(i, j, k)
+                                          && bo[b].tmrca().getElement(i, j, k) == res.tmrca().getElement(i, j, k);
+        batch_equal = batch_equal && bo.size() == 3;
+    }
+    printf("{\n\"batch_equal\": %s,\n", batch_equal ? "true" : "false");
     const char* impl = "reference-binding-gpu";
 #else
     const char* impl = "reference";
 #endif
-    printf("{\n\"impl\": \"%s\", \"n_samples\": %u, \"n_threads\": %u, \"seed\": %u, \"seconds\": %.6f,\n", impl, n_samples, n_threads, seed, secs);
+#ifndef COALREF_GPU_BINDING
+    printf("{\n");
+#endif
+    printf("\"impl\": \"%s\", \"n_samples\": %u, \"n_threads\": %u, \"seed\": %u, \"seconds\": %.6f,\n", impl, n_samples, n_threads, seed, secs);
     printf("\"dims\": [%u, %u, %u], \"T\": %u,\n", res.likelihood().dim1(), res.likelihood().dim2(), res.likelihood().dim3(), p.T);
 #ifdef COALREF_GPU_BINDING
     {   // the order in which the binding walked the reference's unordered_maps (the sampler's draws depend on it)

@@ -347,6 +347,7 @@ def test_reference_side_binding_equals_python_mirror(cuda_lib):
         assert r.returncode == 0, r.stderr
         got = json.loads(r.stdout)
         assert got["impl"] == "reference-binding-gpu"
+        assert got["batch_equal"] is True          # GpuImportanceSampler::runSamplerBatch on three copies == the single call
         q = copy.deepcopy(p)
         q.types = [[("ABC".index(g), p.word("ABC".index(g), bits), c) for g, bits, c in tp] for tp in got["type_order"]]
         assert [sorted(tp) for tp in q.types] == [sorted(tp) for tp in p.types]
