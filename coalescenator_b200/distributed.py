@@ -76,6 +76,8 @@ def run_sampler_distributed(problem: Problem, num_iterations: int, seed: int = 0
         s.sample(buf, seed, first + done, n)
         part = s.partials(buf, n)
         acc = merge_pairs(torch.stack([acc, part]))
+        if done == 0 and count > n:
+            s.tune()          # size the first-pass type store / lanes per history from what the first chunk needed
         done += n
     total = combine_partials(acc, group)
     out = s.finalize(total.cpu().numpy(), num_iterations)
