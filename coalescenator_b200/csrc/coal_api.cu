@@ -87,7 +87,7 @@ struct coalgpu_sampler {
     unsigned long long* d_counters = nullptr;
     double* d_block_partials = nullptr;
     size_t block_partials_cap = 0;
-    int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history (16 or 32)
+    int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history of the full-store geometry (16 or 32; the reduced-store first pass may use 8)
     size_t smem_bytes = 0;
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
     int inj_max = 0, sm_count = 0;    // most input types of one sampling time; SMs of the device

@@ -1,6 +1,6 @@
 // Device-side data layout and kernels of the importance-sampling likelihood path (sm_100a).
 //
-// One GROUP of W lanes (W = 16: two histories per warp) draws one coalescent history
+// One GROUP of W lanes (W = 8, 16 or 32: four, two or one histories per warp) draws one coalescent history
 // (ProposalEngine::calculateLikelihood, /root/reference/src/ProposalEngine.cpp:643-861). The ancestral
 // configuration (TypeContainer, TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed
 // haplotypes; the candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:

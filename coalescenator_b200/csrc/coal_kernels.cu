@@ -89,7 +89,7 @@ __host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot,
     return (b + 15) & ~(size_t)15;
 }
 
-// A GROUP of W lanes (W = 16 or 32) draws one history; a warp carries 32/W independent groups. Every
+// A GROUP of W lanes (W = 8, 16 or 32) draws one history; a warp carries 32/W independent groups. Every
 // collective below names only the lanes of its own group (mask), so the groups of a warp never wait for each
 // other; where their control flow coincides the hardware issues one instruction for all of them.
 template <int W>
