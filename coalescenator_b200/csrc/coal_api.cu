@@ -55,7 +55,9 @@ cudaError_t dev_alloc(void** p, size_t bytes, cudaStream_t stream = 0) {
     }
     return cudaMallocAsync(p, std::max<size_t>(bytes, 16), stream);
 }
-void dev_free(void* p) { if (p) cudaFreeAsync(p, 0); }
+// Stream-ordered free: the release must be ordered after the last kernel that touches the buffer, i.e. issued on the
+// stream that ran it (the legacy default stream does not order against cudaStreamNonBlocking streams).
+void dev_free(void* p, cudaStream_t stream = 0) { if (p) cudaFreeAsync(p, stream); }
 
 // The dynamic shared memory limit is a property of the kernel function, not of a launch: raise it to the device's
 // opt-in maximum once per device for every instantiation. (Changing it per launch serialises against the launches of
@@ -87,6 +89,8 @@ struct coalgpu_sampler {
     unsigned long long* d_counters = nullptr;
     double* d_block_partials = nullptr;
     size_t block_partials_cap = 0;
+    double* d_full_rows = nullptr;    // reference-layout rows on the device (device table builder only; owned through allocs)
+    cudaStream_t last_stream = 0;     // stream of the most recent launch of this sampler: its buffers are freed in that stream's order
     int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history of the full-store geometry (16 or 32; the reduced-store first pass may use 8)
     size_t smem_bytes = 0;
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
@@ -104,6 +108,7 @@ struct coalgpu_sampler {
     int wide_grid = 0, wide_group = 32;
     size_t wide_smem = 0;
     unsigned long long tot_events = 0, tot_pismc = 0, tot_overflow = 0;
+    unsigned long long n_nan_seen = 0;   // NaN log-weights the reduction kernel skipped (counters[9]) as of the last coalgpu_counters
     // K2 scratch smem
     size_t k2_smem = 0;
 };
@@ -134,6 +139,15 @@ int validate_problem(const coalgpu_problem* p, uint32_t Q, std::string& err) {
     if (p->n_mu < 1 || p->n_rho < 1 || p->n_lambda < 1) return bad("empty target grid");
     if (!(p->tau > 0) || !(p->driving_mu > 0) || !(p->driving_lambda > 0) || !(p->driving_rho > 0)) return bad("driving values and tau must be positive (main.cpp:147-150)");
     for (int t = 1; t < p->T; t++) if (!(p->times[t] > p->times[t - 1])) return bad("sampling times must be strictly ascending");
+    if (!p->times || !p->viral || !p->mu || !p->rho || !p->lambda || !p->type_offsets) return bad("null array in the problem");
+    for (int t = 0; t < p->T; t++) if (!(p->viral[t] > 0)) return bad("viral loads must be positive");
+    // the target grid as main.cpp:165-182 asserts it: mu >= 0, rho >= 0, lambda > 0 (NaN fails every comparison)
+    for (int i = 0; i < p->n_mu; i++) if (!(p->mu[i] >= 0) || std::isinf(p->mu[i])) return bad("target mutation rates must be finite and >= 0 (main.cpp:169)");
+    for (int i = 0; i < p->n_rho; i++) if (!(p->rho[i] >= 0) || std::isinf(p->rho[i])) return bad("target recombination rates must be finite and >= 0 (main.cpp:181)");
+    for (int i = 0; i < p->n_lambda; i++) if (!(p->lambda[i] > 0) || std::isinf(p->lambda[i])) return bad("target scale values must be finite and > 0 (main.cpp:175)");
+    if (p->type_offsets[0] < 0) return bad("type_offsets must start at a non-negative index");
+    for (int t = 0; t < p->T; t++) if (p->type_offsets[t + 1] < p->type_offsets[t]) return bad("type_offsets must be non-decreasing");
+    if (p->type_offsets[p->T] > p->type_offsets[0] && (!p->type_gamma || !p->type_words || !p->type_counts)) return bad("null type arrays");
     return 0;
 }
 
@@ -250,15 +264,14 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
     P.kmax = ((n_max + 2 + 31) / 32) * 32;
     P.pvmax = std::max(LA + LB + 4, std::max(LA, LB) + P.kmax + 1);
     P.pvmax = (P.pvmax + 1) & ~1;
-    P.row_doubles = lay.row_doubles;
-    P.off_yw = lay.off_yw; P.off_zlow = lay.off_zlow; P.off_g = lay.off_g; P.off_zdiag = lay.off_zdiag;
-    P.off_EA = lay.off_EA; P.off_EB = lay.off_EB; P.off_wEA = lay.off_wEA; P.off_wEB = lay.off_wEB;
+    P.row_doubles = lay.dev_row_doubles;
+    P.SB = lay.dev_sb; P.off_wEA = lay.dev_off_wEA; P.off_wEB = lay.dev_off_wEB;
+    P.stage_doubles = (LA + LB <= 32) ? lay.dev_row_doubles : 0;    // matches kStaged in history_kernel: longer loci read their rows through L1
     P.maskA = maskA; P.maskB = maskB;
     P.perm_const = perm;
     P.pow2negLA = std::ldexp(1.0, -LA); P.pow2negLB = std::ldexp(1.0, -LB); P.pow2negL = std::ldexp(1.0, -(LA + LB));
     double wsum = 0; for (int i = 0; i < kQ; i++) wsum += h.tab.w[i];
     P.wsum = wsum;
-    for (int i = 0; i < kQ; i++) P.w[i] = h.tab.w[i];
     return 0;
 }
 
@@ -282,7 +295,7 @@ Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
     if (const char* g = std::getenv("COALGPU_GROUP")) { const int W = std::atoi(g); if (W == 8 || W == 16 || W == 32) forced_w = W; }
     auto eval = [&](int W) {
         Geometry g; g.group = W;
-        g.smem = history_group_bytes(kmax, pvmax, P.Ltot, W) * (cta_threads(W) / W);
+        g.smem = history_group_bytes(kmax, pvmax, P.Ltot, W, P.stage_doubles) * (cta_threads(W) / W);
         if (g.smem > 227 * 1024) return Geometry();
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_kernel_select(W, P.Ltot <= 32), cta_threads(W), g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
         g.per_sm = g.occ * (cta_threads(W) / W);
@@ -300,7 +313,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     const Geometry full = geometry_for(P, P.kmax, P.pvmax, false);
     if (full.per_sm < 1) return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA");
     s->group = full.group; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
-    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group);
+    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group, P.stage_doubles);
     P.warp_bytes = s->warp_bytes;
     s->fast = false; s->fast_forced = false; s->wide = false;
 
@@ -333,7 +346,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
         Pout.kmax = best_k;
         Pout.pvmax = pv_for(best_k);
         group = bestf.group; smem = bestf.smem; grid = s->sm_count * bestf.occ;
-        Pout.warp_bytes = (int)history_group_bytes(best_k, Pout.pvmax, P.Ltot, bestf.group);
+        Pout.warp_bytes = (int)history_group_bytes(best_k, Pout.pvmax, P.Ltot, bestf.group, P.stage_doubles);
         return true;
     };
     s->fast = pick(allow8, s->P_fast, s->fast_grid, s->fast_group, s->fast_smem);
@@ -364,7 +377,8 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     // arena layout (every part 256-byte aligned: the table rows are the source of bulk copies)
     size_t off = 0;
     auto place = [&off](size_t bytes) { const size_t o = off; off += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255; return o; };
-    const size_t o_rows = place(s->tab.rows.size() * sizeof(double)), o_set = place(s->tab.set_of_epoch.size() * sizeof(int));
+    const size_t dev_rows_doubles = (size_t)s->tab.n_sets * s->tab.n_max * s->tab.lay.dev_row_doubles;
+    const size_t o_rows = place(dev_rows_doubles * sizeof(double)), o_set = place(s->tab.set_of_epoch.size() * sizeof(int));
     const size_t o_times = place(h.times.size() * sizeof(double)), o_ep = place(h.ep.size() * sizeof(EpochConst));
     const size_t o_grid = place(h.grid.size() * sizeof(GridConst)), o_lf = place(h.lfact.size() * sizeof(double));
     const size_t o_rcp = place(h.rcp.size() * sizeof(double)), o_toff = place(h.type_off.size() * sizeof(int));
@@ -378,7 +392,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     s->allocs.push_back(base);
     cudaError_t ue = cudaSuccess;
     auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes && ue == cudaSuccess) ue = cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, up); };
-    put(o_rows, s->tab.rows.data(), s->tab.rows.size() * sizeof(double));
+    if (!h.device_emission) put(o_rows, s->tab.dev_rows.data(), dev_rows_doubles * sizeof(double));
     put(o_set, s->tab.set_of_epoch.data(), s->tab.set_of_epoch.size() * sizeof(int));
     put(o_times, h.times.data(), h.times.size() * sizeof(double));
     put(o_ep, h.ep.data(), h.ep.size() * sizeof(EpochConst));
@@ -390,16 +404,20 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     put(o_tcg, h.type_cg.data(), h.type_cg.size() * sizeof(unsigned int));
     if (ue == cudaSuccess) ue = cudaMemsetAsync(base + o_cnt, 0, kCounters * sizeof(unsigned long long), up);
     if (ue == cudaSuccess && h.device_emission) {
-        // stable emission mode: the table sets' thetas ride in the arena; K4 fills EA | EB | wEA | wEB of every row
+        // Stable emission mode, table builder on the device: the reference-layout rows arrive with the transition constants
+        // only (host), K4 fills their EA | EB | wEA | wEB from the table sets' thetas, K5 turns them into the rows the
+        // history kernel reads. The reference-layout copy stays on the device for coalgpu_tables.
         std::vector<double> set_theta(s->tab.n_sets, 0.0);
         for (int c = 0; c < h.T; c++) set_theta[s->tab.set_of_epoch[c]] = h.thetas[c];
         double* d_theta = nullptr;
         ue = dev_alloc((void**)&d_theta, set_theta.size() * sizeof(double), up);
         if (ue == cudaSuccess) { s->allocs.push_back(d_theta); ue = cudaMemcpyAsync(d_theta, set_theta.data(), set_theta.size() * sizeof(double), cudaMemcpyHostToDevice, up); }
+        if (ue == cudaSuccess) ue = dev_alloc((void**)&s->d_full_rows, s->tab.rows.size() * sizeof(double), up);
+        if (ue == cudaSuccess) { s->allocs.push_back(s->d_full_rows); ue = cudaMemcpyAsync(s->d_full_rows, s->tab.rows.data(), s->tab.rows.size() * sizeof(double), cudaMemcpyHostToDevice, up); }
         if (ue == cudaSuccess) {
             const TableLayout& lay = s->tab.lay;
             EmissionArgs ea{};
-            ea.rows = (double*)(base + o_rows); ea.thetas = d_theta;
+            ea.rows = s->d_full_rows; ea.thetas = d_theta;
             ea.n_sets = s->tab.n_sets; ea.n_max = s->tab.n_max; ea.row_doubles = lay.row_doubles; ea.LA = h.LA; ea.LB = h.LB; ea.Q = h.Q;
             ea.off_EA = lay.off_EA; ea.off_EB = lay.off_EB; ea.off_wEA = lay.off_wEA; ea.off_wEB = lay.off_wEB;
             for (int i = 0; i <= kQ; i++) ea.t[i] = s->tab.quad[i];
@@ -410,6 +428,22 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
             g_launches++;
             ue = cudaGetLastError();
             s->rows_on_device_only = true;
+        }
+        if (ue == cudaSuccess) {
+            const TableLayout& lay = s->tab.lay;
+            BilinearArgs ba{};
+            ba.full_rows = s->d_full_rows; ba.dev_rows = (double*)(base + o_rows);
+            ba.n_rows = (long long)s->tab.n_sets * s->tab.n_max;
+            ba.row_doubles = lay.row_doubles; ba.dev_row_doubles = lay.dev_row_doubles; ba.LA = h.LA; ba.LB = h.LB;
+            ba.off_yw = lay.off_yw; ba.off_zlow = lay.off_zlow; ba.off_g = lay.off_g; ba.off_zdiag = lay.off_zdiag;
+            ba.off_EA = lay.off_EA; ba.off_EB = lay.off_EB; ba.off_wEA = lay.off_wEA; ba.off_wEB = lay.off_wEB;
+            ba.dev_sb = lay.dev_sb; ba.dev_off_wEA = lay.dev_off_wEA; ba.dev_off_wEB = lay.dev_off_wEB;
+            for (int i = 0; i < kQ; i++) ba.w[i] = s->tab.w[i];
+            const long long total = ba.n_rows * (h.LA + 2);
+            const int blocks = (int)std::min<long long>((total + 127) / 128, (long long)sm_count * 16);
+            bilinear_rows_kernel<<<blocks, 128, 0, up>>>(ba);
+            g_launches++;
+            ue = cudaGetLastError();
         }
     }
     if (ue != cudaSuccess) { coalgpu_destroy(s); return fail(COALGPU_ECUDA, std::string("upload: ") + cudaGetErrorString(ue)); }
@@ -449,12 +483,13 @@ int coalgpu_set_emission_mode(int mode) {
 void coalgpu_destroy(coalgpu_sampler* s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    for (void* p : s->allocs) dev_free(p);
-    dev_free(s->d_block_partials);
+    // ordered after the sampler's last launch (the legacy default stream does not order against non-blocking streams)
+    for (void* p : s->allocs) dev_free(p, s->last_stream);
+    dev_free(s->d_block_partials, s->last_stream);
     delete s;
 }
 
-int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
+static int create_impl(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) {
     if (!p || !out) return fail(COALGPU_EINVAL, "null argument");
     *out = nullptr;
     HostPrep h; std::string err;
@@ -501,6 +536,7 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
     kfn<<<grid, cta_threads(group), smem, st>>>(P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
+    s->last_stream = st;
     return 0;
 }
 
@@ -532,8 +568,9 @@ int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n
 int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, uint64_t* n_overflow) {
     if (!s) return fail(COALGPU_EINVAL, "null sampler");
     CU_OK(cudaSetDevice(s->device));
-    unsigned long long h[8];
+    unsigned long long h[kCounters];
     CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    s->n_nan_seen = h[9];
     if (n_events) *n_events = h[1];
     if (n_pismc) *n_pismc = h[2];
     if (n_overflow) *n_overflow = h[3];
@@ -606,23 +643,28 @@ int coalgpu_partials(coalgpu_sampler* s, uint64_t n, void* stream, const double*
     CU_OK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int nstat = 3 + s->T;
-    int nb = (int)std::min<uint64_t>((n + 255) / 256, 64);
-    if (nb < 1) nb = 1;
+    // block = 256 threads = (256 / cols) history rows x cols grid columns, cols = the power of two >= min(G, 32)
+    int cols = 1;
+    while (cols < 32 && cols < s->G) cols *= 2;
+    const int rows = 256 / cols, col_tiles = (s->G + cols - 1) / cols;
+    int nb = (int)std::min<uint64_t>((n + (uint64_t)rows * 4 - 1) / ((uint64_t)rows * 4), (uint64_t)std::max(1, 4 * s->sm_count / col_tiles));
+    nb = std::max(1, std::min(nb, 1024));
     const size_t need = (size_t)nstat * s->G * nb * 2 * sizeof(double);
     if (need > s->block_partials_cap) {
-        dev_free(s->d_block_partials);
+        dev_free(s->d_block_partials, s->last_stream);      // its last reader ran on last_stream
         s->d_block_partials = nullptr; s->block_partials_cap = 0;
         CU_OK(dev_alloc((void**)&s->d_block_partials, need, st));
         s->block_partials_cap = need;
     }
-    dim3 grid(nb, s->G, nstat);
-    lse_partial_kernel<<<grid, 256, 0, st>>>(n, s->G, s->T, d_weights, d_tmrca, d_lineages, s->d_block_partials);
+    dim3 grid(nb, col_tiles, (s->T + kLseT - 1) / kLseT);
+    lse_partial_kernel<<<grid, 256, 0, st>>>(n, s->G, s->T, cols, d_weights, d_tmrca, d_lineages, s->d_block_partials, s->d_counters);
     g_launches++;
     CU_OK(cudaGetLastError());
     const int total = nstat * s->G;
     lse_combine_kernel<<<(total + 127) / 128, 128, 0, st>>>(nb, total, s->d_block_partials, d_partials);
     g_launches++;
     CU_OK(cudaGetLastError());
+    s->last_stream = st;
     return 0;
 }
 
@@ -640,7 +682,7 @@ int coalgpu_finalize(int32_t G, int32_t T, const double* hp, coalgpu_result* r) 
     return 0;
 }
 
-int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
+static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
     if (!problem || !result) return fail(COALGPU_EINVAL, "null argument");
     if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
     const bool timing = std::getenv("COALGPU_TIMING") != nullptr;
@@ -708,6 +750,7 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
     const double t_sampled = tick();
     uint64_t nev = 0, npi = 0, nov = 0;
     rc = coalgpu_counters(s, &nev, &npi, &nov);
+    const unsigned long long n_nan = s->n_nan_seen;
     const double t_cnt = tick();
     if (!rc) rc = coalgpu_finalize(G, T, acc.data(), result);
     result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
@@ -724,6 +767,7 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
                         1e3 * (t_created - t_begin), 1e3 * (t_sampled - t_created), (double)ms, 1e3 * (t_cnt - t_sampled), 1e3 * (t_fin - t_cnt), 1e3 * (tick() - t_fin));
     if (rc) return fail(rc, m);
     if (nov) return fail(COALGPU_EOVERFLOW, "a history outgrew the type-store capacity");
+    if (n_nan) return fail(COALGPU_ENAN, "a history weight is not a number (target grid / driving values out of range?)");
     return 0;
 }
 
@@ -733,8 +777,8 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
 // GPU samples the current ones, every pair runs on one of 16 streams, at most 32 pairs are in flight, and the only
 // host<-device transfer per pair is one pinned copy of its (max, sum) partials and counters.
 // Results are identical to n_problems calls of coalgpu_run_sampler.
-int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples, uint32_t Q,
-                              uint64_t seed, int device, coalgpu_result* results) {
+static int run_sampler_batch_impl(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples, uint32_t Q,
+                                  uint64_t seed, int device, coalgpu_result* results) {
     if (n_problems < 0 || (n_problems > 0 && (!problems || !results))) return fail(COALGPU_EINVAL, "null argument");
     if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
     if (n_problems == 0) return 0;
@@ -785,9 +829,12 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             // one table thread per pair: the pairs are the parallel axis here
             auto work = [p, Q, device, up]() {
                 std::unique_ptr<Prep> r(new Prep);
-                HostPrep h;
-                r->rc = prepare_host(p, Q, 1, h, r->err);
-                if (!r->rc) { r->rc = finish_device(h, device, up, &r->s); if (r->rc) r->err = g_err; }
+                try {
+                    HostPrep h;
+                    r->rc = prepare_host(p, Q, 1, h, r->err);
+                    if (!r->rc) { r->rc = finish_device(h, device, up, &r->s); if (r->rc) r->err = g_err; }
+                } catch (const std::bad_alloc&) { r->rc = COALGPU_ENOMEM; r->err = "out of host memory while preparing a locus pair"; }
+                catch (const std::exception& e) { r->rc = COALGPU_EINVAL; r->err = std::string("preparing a locus pair: ") + e.what(); }
                 return r;
             };
             try { preps[next_prep] = std::async(std::launch::async, work); }
@@ -809,25 +856,27 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
             float ms = 0;
             if (!rc) WB_OK(cudaEventElapsedTime(&ms, j.e0, j.e1));
             if (!rc) {
-                unsigned long long cnt[8];
+                unsigned long long cnt[kCounters];
                 std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
                 if (j.d_defer && cnt[6]) {       // histories outgrew the reduced store: second pass, reduce again
                     rc = sample_pass(j.s, 2, seed, 0, n_samples, j.st, j.d_w, j.d_t, j.d_l, nullptr, nullptr, nullptr, 0, 0, j.d_defer, cnt[6]);
+                    WB_OK(cudaMemsetAsync(j.s->d_counters + 9, 0, sizeof(unsigned long long), j.st));   // the first reduction saw the deferred histories' NaN placeholders
                     if (!rc) rc = coalgpu_partials(j.s, n_samples, j.st, j.d_w, j.d_t, j.d_l, j.d_p);
                     if (rc) err = g_err;
-                    WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, j.st));
-                    WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, j.st));
+                    WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, kCounters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, j.st));
+                    WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + kCounters) * sizeof(double), cudaMemcpyDeviceToHost, j.st));
                     WB_OK(cudaStreamSynchronize(j.st));
                 }
             }
             if (!rc) {
                 coalgpu_result* r = results + j.index;
-                unsigned long long cnt[8];
+                unsigned long long cnt[kCounters];
                 std::memcpy(cnt, j.h_p + j.np, sizeof cnt);
                 rc = coalgpu_finalize(j.s->G, j.s->T, j.h_p, r);
                 if (rc) err = g_err;
                 r->n_histories = n_samples; r->n_events = cnt[1]; r->n_pismc = cnt[2]; r->seconds_device = ms * 1e-3;
                 if (!rc && cnt[3]) { rc = COALGPU_EOVERFLOW; err = "a history outgrew the type-store capacity"; }
+                if (!rc && cnt[9]) { rc = COALGPU_ENAN; err = "a history weight is not a number (target grid / driving values out of range?)"; }
             }
         }
         release(j);
@@ -835,7 +884,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     // one pinned slab for the partials of the pairs in flight (pinned allocations synchronise the device: once per call)
     size_t slot_doubles = 0;
     for (int k = 0; k < n_problems; k++)
-        if (!is_big(problems + k)) slot_doubles = std::max(slot_doubles, (size_t)(3 + problems[k].T) * problems[k].n_mu * problems[k].n_rho * problems[k].n_lambda * 2 + 8);
+        if (!is_big(problems + k)) slot_doubles = std::max(slot_doubles, (size_t)(3 + problems[k].T) * problems[k].n_mu * problems[k].n_rho * problems[k].n_lambda * 2 + kCounters);
     double* slab = nullptr;
     if (slot_doubles) {
         cudaError_t e = cudaSetDevice(device);
@@ -854,7 +903,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     for (int k = 0; k < n_problems && !rc; k++) {
         const coalgpu_problem* p = problems + k;
         if (is_big(p)) {                   // sequential, chunked
-            rc = coalgpu_run_sampler(p, n_samples, Q, seed, device, results + k);
+            rc = run_sampler_impl(p, n_samples, Q, seed, device, results + k);
             if (rc) err = g_err;
             schedule(k + 1 + lookahead);
             continue;
@@ -881,7 +930,7 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         WB_OK(cudaMallocAsync((void**)&j.d_w, n_samples * G * sizeof(double), st));
         WB_OK(cudaMallocAsync((void**)&j.d_t, n_samples * sizeof(double), st));
         WB_OK(cudaMallocAsync((void**)&j.d_l, n_samples * T * sizeof(double), st));
-        WB_OK(cudaMallocAsync((void**)&j.d_p, (j.np + 8) * sizeof(double), st));
+        WB_OK(cudaMallocAsync((void**)&j.d_p, (j.np + kCounters) * sizeof(double), st));
         j.h_p = slab + (size_t)(launched++ % kWindow) * slot_doubles;   // free again: its previous user was retired above
         WB_OK(cudaEventCreate(&j.e0)); WB_OK(cudaEventCreate(&j.e1));
         if (rc) break;
@@ -905,8 +954,8 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
         }
         if (!rc) rc = coalgpu_partials(j.s, n_samples, st, j.d_w, j.d_t, j.d_l, j.d_p);
         if (rc) { err = g_err; break; }
-        WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-        WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + 8) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, kCounters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + kCounters) * sizeof(double), cudaMemcpyDeviceToHost, st));
         WB_OK(cudaEventRecord(j.e1, st));
         t_launch += tick() - t0;
     }
@@ -926,6 +975,22 @@ int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problem
     return 0;
 }
 
+// No C++ exception crosses the C ABI (std::bad_alloc from the table vectors, std::system_error from std::thread /
+// std::async): they become return codes like every other failure.
+#define COALGPU_GUARD(call)                                                                                         \
+    try { return call; }                                                                                            \
+    catch (const std::bad_alloc&) { return fail(COALGPU_ENOMEM, "out of host memory"); }                           \
+    catch (const std::exception& e) { return fail(COALGPU_EINVAL, std::string("internal error: ") + e.what()); }   \
+    catch (...) { return fail(COALGPU_EINVAL, "internal error"); }
+int coalgpu_create(const coalgpu_problem* p, uint32_t Q, int device, coalgpu_sampler** out) { COALGPU_GUARD(create_impl(p, Q, device, out)) }
+int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
+    COALGPU_GUARD(run_sampler_impl(problem, n_samples, Q, seed, device, result))
+}
+int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples, uint32_t Q,
+                              uint64_t seed, int device, coalgpu_result* results) {
+    COALGPU_GUARD(run_sampler_batch_impl(n_problems, problems, n_samples, Q, seed, device, results))
+}
+
 int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* w, double* y, double* z, double* EA, double* EB) {
     if (!s) return fail(COALGPU_EINVAL, "null sampler");
     if (time_idx < 0 || time_idx >= s->T || n_all < 1 || n_all > s->tab.n_max) return fail(COALGPU_EINVAL, "table index out of range");
@@ -935,7 +1000,7 @@ int coalgpu_tables(coalgpu_sampler* s, int32_t n_all, int32_t time_idx, double* 
         if (s->tab.rows.empty()) return fail(COALGPU_EINVAL, "table rows were released (batch sampler)");
         CU_OK(cudaSetDevice(s->device));
         CU_OK(cudaDeviceSynchronize());
-        CU_OK(cudaMemcpy(s->tab.rows.data(), s->P.rows, s->tab.rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CU_OK(cudaMemcpy(s->tab.rows.data(), s->d_full_rows, s->tab.rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
         s->rows_on_device_only = false;
     }
     const double* row = s->tab.row(set, n_all);

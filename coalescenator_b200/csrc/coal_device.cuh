@@ -6,9 +6,9 @@
 // haplotypes; the candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:
 //  * marginal (one-locus) conditional sampling probabilities collapse to a dot product of a distance
 //    histogram with a precomputed weight vector (ConditionalSamplingHMM.cpp:332-370),
-//  * two-locus ones run the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) with the
-//    interval axis split over a power-of-two lane sub-group and the structured transition matrix folded
-//    into running prefix sums exchanged by warp shuffles,
+//  * two-locus ones (the 16-interval forward pass, ConditionalSamplingHMM.cpp:372-424) are bilinear forms over the
+//    class distances with two small per-row matrices in which the interval axis is already summed out (coal_math.h),
+//    one query per lane,
 //  * the table rows an event reads are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier).
 // fp64 throughout; no tensor cores (the recursion is a diagonal + rank-1 update, not a contraction).
 #pragma once
@@ -36,11 +36,11 @@ struct GridConst {
 struct DevProblem {
     int T, LA, LB, Ltot, G;
     int n_max, kmax, row_doubles, pvmax, warp_bytes;
-    int off_yw, off_zlow, off_g, off_zdiag, off_EA, off_EB, off_wEA, off_wEB;
+    int SB, off_wEA, off_wEB;     // device row (coal_tables.h): MY[(LA+2)][SB = LB+2][2] | wEA[LA+1] | wEB[LB+1], row_doubles in all
+    int stage_doubles;            // doubles of a row staged into shared memory per event by TMA (row_doubles, or 0: rows too large, read through L1)
     unsigned long long maskA, maskB;
     double perm_const;        // sum_t probabilitySamplePermutation (ProposalEngine.cpp:88-118,822-828)
     double pow2negLA, pow2negLB, pow2negL, wsum;
-    double w[kQd];            // interval weights (ConditionalSamplingHMM.cpp:63-71); per sampler: they depend on quadrature_points
     const double* rows;       // [n_sets][n_max][row_doubles]
     const int* set_of_epoch;  // [T]
     const double* times;      // [T]
@@ -93,19 +93,21 @@ __device__ __noinline__ uint4 philox_block(unsigned long long seed, unsigned lon
     }
     return make_uint4(c0, c1, c2, c3);
 }
-__device__ __forceinline__ double u53(unsigned int lo, unsigned int hi) {
-    const unsigned long long bits = (((unsigned long long)hi << 32) | lo) >> 11;
-    return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+// 52 random bits -> (0,1): (bits + 0.5) * 2^-52 has at most 53 significant bits, so it is exact, at least 2^-53 and at
+// most 1 - 2^-53 (with 53 bits the +0.5 would round and the largest draw would be exactly 1: a zero waiting time).
+__device__ __forceinline__ double u52(unsigned int lo, unsigned int hi) {
+    const unsigned long long bits = (((unsigned long long)hi << 32) | lo) >> 12;
+    return ((double)bits + 0.5) * (1.0 / 4503599627370496.0);
 }
-// Sequential draws of one history: draw k lives in block k >> 1, half k & 1; -> (0,1), 53 bits.
+// Sequential draws of one history: draw k lives in block k >> 1, half k & 1; -> (0,1), 52 bits.
 struct PhiloxStream {
     unsigned long long seed, hist, k;
     uint4 blk;
     __device__ __forceinline__ void init(unsigned long long s, unsigned long long h) { seed = s; hist = h; k = 0; blk = make_uint4(0, 0, 0, 0); }
     __device__ __forceinline__ double next() {
         double u;
-        if ((k & 1) == 0) { blk = philox_block(seed, hist, k >> 1); u = u53(blk.x, blk.y); }
-        else u = u53(blk.z, blk.w);
+        if ((k & 1) == 0) { blk = philox_block(seed, hist, k >> 1); u = u52(blk.x, blk.y); }
+        else u = u52(blk.z, blk.w);
         k++;
         return u;
     }

@@ -17,9 +17,6 @@ constexpr int kAppended = 0x40000000;
 #if !defined(COAL_NO_TMA) && !defined(COAL_TMA_ROWS)
 #define COAL_TMA_ROWS 1     // table rows staged into shared memory by cp.async.bulk (+5 % over ld.global.nc, profiles/r1_kernel_iterations.md)
 #endif
-#ifndef COAL_PER
-#define COAL_PER 4          // intervals per forward-pass block (and the minimum per lane)
-#endif
 #ifndef COAL_SLOT_UNROLL
 #define COAL_SLOT_UNROLL 1
 #endif
@@ -44,7 +41,7 @@ struct WarpMem {
     double* sd;                  // [4]     scalar results of the out-of-line helpers
     struct HistScalars* hs;      //         per-history scalars that are touched once per event (kept out of registers)
 #ifdef COAL_TMA_ROWS
-    double* rowbuf;              // [row_doubles] table row of the event's two-locus queries, staged by cp.async.bulk
+    double* rowbuf;              // [stage_doubles] table row of the event's two-locus queries, staged by cp.async.bulk
     double* wbuf;                // [2][wlen]     wEA|wEB tails of the two rows the one-locus queries read
     unsigned long long* mbar;    // mbarrier the bulk copies complete on
 #endif
@@ -72,12 +69,11 @@ struct HistScalars {
 
 #ifdef COAL_TMA_ROWS
 __host__ __device__ inline int tma_wlen(int Ltot) { return (Ltot + 2 + 1) & ~1; }           // doubles, 16-byte multiple
-__host__ __device__ inline int tma_row_doubles(int Ltot) { return ((4 * 16 + kEStride * (Ltot + 2) + (Ltot + 2)) + 1) & ~1; }
 #endif
-__host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W) {
+__host__ __device__ inline size_t group_mem_bytes(int kmax, int pvmax, int Ltot, int W, int stage_doubles) {
     size_t b = 0;
 #ifdef COAL_TMA_ROWS
-    b += (size_t)tma_row_doubles(Ltot) * 8 + 2 * (size_t)tma_wlen(Ltot) * 8 + 16;   // rowbuf, wbuf, mbarrier
+    b += (size_t)stage_doubles * 8 + 2 * (size_t)tma_wlen(Ltot) * 8 + 16;   // rowbuf, wbuf, mbarrier
 #endif
     b += (size_t)kmax * 8;                 // words
     b += (size_t)pvmax * 8;                // pv
@@ -123,7 +119,7 @@ __device__ __forceinline__ WarpMem wm() {
     const int kmax = sP.kmax, pvmax = sP.pvmax;
     WarpMem m;
 #ifdef COAL_TMA_ROWS
-    m.rowbuf = reinterpret_cast<double*>(base); base += (size_t)sP.row_doubles * 8;          // 16-byte aligned: first in the block
+    m.rowbuf = reinterpret_cast<double*>(base); base += (size_t)sP.stage_doubles * 8;        // 16-byte aligned: first in the block
     m.wbuf = reinterpret_cast<double*>(base); base += 2 * (size_t)tma_wlen(sP.Ltot) * 8;
     m.mbar = reinterpret_cast<unsigned long long*>(base); base += 16;
 #endif
@@ -419,42 +415,18 @@ __device__ __forceinline__ void build_classes(const WarpMem& m, int ns, int nqb,
     nH_out = nH; tot_out = tot;
 }
 
-// Two-locus queries, phase 2: the 16-interval forward pass (ConditionalSamplingHMM.cpp:372-424) of one query
-// per sub-group of p lanes (p a power of two), lane r of it taking the intervals [r*16/p, (r+1)*16/p).
-template <int W>
-__device__ __forceinline__ double forward_pass(const unsigned int* cls, int nH, ClassTotals tot, int p,
-                                               const double* __restrict__ row, unsigned int n_cond) {
-    const unsigned int gm = Grp<W>::mask();
-    const bool empty = (n_cond == 0 || nH == 0);     // empty configuration, ConditionalSamplingHMM.cpp:277-298
-    const int r = Grp<W>::sub() & (p - 1);
-    const int per = kQd / p;
-    const int i0 = r * per;
-    auto ld = [row](int off) { return tab_ld(row + off); };
-    ChunkPartial cp = {0, 0, 0, 0, 0, 0};
-    const double inv_n = __ldg(sP.rcp + tot.n);
-    if (!empty) {
-#define COAL_FWD(PER) chunk_forward<PER>(ld, sP.w, sP.off_yw, sP.off_zlow, sP.off_g, sP.off_zdiag, sP.off_EA, sP.off_EB, \
-                                          cls, 1, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB), sP.pow2negLA, sP.pow2negLB, i0, i0 + per)
-        cp = COAL_FWD(COAL_PER);   // one instantiation: a smaller event body beats fuller lanes at per < 4 (profiles/r1_kernel_iterations.md)
-#undef COAL_FWD
-    }
-    // exclusive prefixes of (pre, preB) over the lanes of the sub-group
-    double ipre = cp.pre, ipreB = cp.preB;
-#pragma unroll 1
-    for (int o = 1; o < p; o <<= 1) {
-        const double t1 = __shfl_up_sync(gm, ipre, o, p);
-        const double t2 = __shfl_up_sync(gm, ipreB, o, p);
-        if (r >= o) { ipre += t1; ipreB += t2; }
-    }
-    double epre = __shfl_up_sync(gm, ipre, 1, p), epreB = __shfl_up_sync(gm, ipreB, 1, p);
-    if (r == 0) { epre = 0.0; epreB = 0.0; }
-    double acc = chunk_finish(cp, epre, epreB), acc2 = cp.acc2;
-#pragma unroll 1
-    for (int o = 1; o < p; o <<= 1) {
-        acc += __shfl_xor_sync(gm, acc, o, p);
-        acc2 += __shfl_xor_sync(gm, acc2, o, p);
-    }
-    return empty ? sP.pow2negL : (acc * inv_n + acc2) * inv_n;
+// Two-locus queries, phase 2: pi_SMC of the query whose class list the lane has just built (the forward pass of
+// ConditionalSamplingHMM.cpp:372-424 as a bilinear form, coal_math.h). STAGED: the row sits in the group's shared
+// memory (one 16-byte load per (M, Y) pair); otherwise it is read through L1 from the sampler's table in HBM / L2.
+template <bool STAGED>
+__device__ __forceinline__ double two_locus_pi(const unsigned int* cls, int nH, ClassTotals tot, const double* __restrict__ row, unsigned int n_cond) {
+    if (n_cond == 0 || nH == 0) return sP.pow2negL;      // empty configuration, ConditionalSamplingHMM.cpp:277-298
+    auto ldmy = [row](int k) {
+        const double2 v = STAGED ? *reinterpret_cast<const double2*>(row + 2 * k) : __ldg(reinterpret_cast<const double2*>(row + 2 * k));
+        MYPair e; e.m = v.x; e.y = v.y; return e;
+    };
+    return pismc_bilinear(ldmy, sP.SB, sP.LA, sP.LB, cls, 1, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB),
+                          __ldg(sP.rcp + tot.n), sP.pow2negLA, sP.pow2negLB);
 }
 
 __device__ __forceinline__ const double* row_ptr(int set, int n_all) {
@@ -612,10 +584,10 @@ __device__ __forceinline__ void run_group() {
                     const bool c_chosen = (xg == GC);
                     const double* g_m1 = row_ptr(tset, n - 1);
                     const double* g_alt = row_ptr(tset, c_chosen ? n : n - 2);
-                    const unsigned int rb = (unsigned int)sP.row_doubles * 8u, wb = (unsigned int)(sP.row_doubles - sP.off_wEA) * 8u;
+                    const unsigned int rb = (unsigned int)sP.stage_doubles * 8u, wb = (unsigned int)(sP.row_doubles - sP.off_wEA) * 8u;
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_expect(m.mbar, rb + 2u * wb);
-                    bulk_g2s(m.rowbuf, c_chosen ? g_m1 : g_alt, rb, m.mbar);
+                    if (rb) bulk_g2s(m.rowbuf, c_chosen ? g_m1 : g_alt, rb, m.mbar);
                     bulk_g2s(m.wbuf, g_m1 + sP.off_wEA, wb, m.mbar);
                     bulk_g2s(m.wbuf + tma_wlen(Ltot), g_alt + sP.off_wEA, wb, m.mbar);
                 }
@@ -712,11 +684,13 @@ __device__ __forceinline__ void run_group() {
                 //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
                 //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
                 const int nq = isC ? Ltot + 1 : np;
+                constexpr bool kStaged =
 #ifdef COAL_TMA_ROWS
-                const double* crow = m.rowbuf;
+                    N32;        // rows of up to 32 sites fit the staging buffer; longer loci read their (quadratically larger) rows through L1
 #else
-                const double* crow = isC ? row_m1 : row_alt;
+                    false;
 #endif
+                const double* crow = kStaged ? m.rowbuf : (isC ? row_ptr(tset, n - 1) : row_ptr(tset, n - 2));
                 const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
                 const int hstride = (Ltot + 2) | 1;
 #pragma unroll 1
@@ -725,22 +699,9 @@ __device__ __forceinline__ void run_group() {
                     int my_nH; ClassTotals my_tot;
                     build_classes<W, N32>(m, ns, nqb, qb, isC, xw, pg, my_nH, my_tot);
                     nh_lane += (unsigned int)my_nH; ncq += (unsigned int)nqb;
-                    // one pass: sub-groups of p lanes per query, p the largest power of two with nqb * p <= W (<= 4).
-                    // (Splitting the batch into several always-full passes costs more in per-pass set-up than the
-                    // idle lanes cost here, profiles/r1_kernel_iterations.md.)
-                    int p = 1;
-                    while (p < 16 / COAL_PER && nqb * (p * 2) <= W) p *= 2;
-                    const int ql = sub / p;
-                    const bool valid = ql < nqb;
-                    const int qloc = valid ? ql : 0;
-                    const int nH = G::shfl(my_nH, qloc);
-                    ClassTotals tot;
-                    tot.n = G::shfl(my_tot.n, qloc);
-                    tot.ncompA = G::shfl(my_tot.ncompA, qloc);
-                    tot.ncompB = G::shfl(my_tot.ncompB, qloc);
-                    const double pi = forward_pass<W>(m.hist + qloc * hstride, nH, tot, p, crow, cn);
-                    if (valid && (sub & (p - 1)) == 0) {
-                        const int qi = qb + qloc;
+                    if (sub < nqb) {       // one query per lane: the lane that built the class list evaluates it
+                        const double pi = two_locus_pi<kStaged>(m.hist + sub * hstride, my_nH, my_tot, crow, cn);
+                        const int qi = qb + sub;
                         if (isC) { if (qi == 0) m.sd[2] = pi; else m.pv[qi - 1] = pi; }
                         else {
                             const int pslot = (int)m.plist[qi];
@@ -749,7 +710,6 @@ __device__ __forceinline__ void run_group() {
                     }
                     G::sync();
                 }
-                G::sync();
 
                 int ncand;
                 if (isC) pi0 = m.sd[2];
@@ -904,32 +864,27 @@ history_kernel_fn history_kernel_select(int W, bool narrow) {
     return W == 8 ? history_kernel<8, false> : W == 16 ? history_kernel<16, false> : history_kernel<32, false>;
 }
 
-// K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC).
-// One group of 16 lanes per query; classes are staged into the group's shared-memory column.
+// K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC): one query per thread, through
+// the same table rows and the same arithmetic (coal_math.h) as the history kernel. The class list of a thread sits in
+// its own shared-memory column.
 __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long long nq, const unsigned char* __restrict__ gamma,
                                                             const int* __restrict__ n_all, const int* __restrict__ tidx,
                                                             const long long* __restrict__ offs, const int* __restrict__ cnt,
                                                             const int* __restrict__ dA, const int* __restrict__ dB,
                                                             double* __restrict__ out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int* hist = reinterpret_cast<unsigned int*>(smem_dyn) + (size_t)warp * (P.Ltot + 2) * 32;
-    const int p = 16, r = lane & 15;
-    const long long qbase = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 2;
-    for (long long q0 = qbase; q0 < nq; q0 += (long long)gridDim.x * (blockDim.x >> 5) * 2) {
-        const long long qi = q0 + (lane >> 4);
-        const bool valid = qi < nq;
-        const long long lo = valid ? offs[qi] : 0, hi = valid ? offs[qi + 1] : 0;
+    unsigned int* col = reinterpret_cast<unsigned int*>(smem_dyn) + threadIdx.x;
+    const int cs = blockDim.x;
+    for (long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x; qi < nq; qi += (long long)gridDim.x * blockDim.x) {
+        const long long lo = offs[qi], hi = offs[qi + 1];
         const int nH = (int)(hi - lo);
-        const int g = valid ? gamma[qi] : GC;
-        const unsigned int n = valid ? (unsigned int)n_all[qi] : 1u;
-        const int set = valid ? P.set_of_epoch[tidx[qi]] : 0;
-        const double* row = P.rows + ((size_t)set * P.n_max + (n - 1)) * P.row_doubles;
-        unsigned int* col = hist + lane;
+        const int g = gamma[qi];
+        const unsigned int n = (unsigned int)n_all[qi];
+        const double* row = P.rows + ((size_t)P.set_of_epoch[tidx[qi]] * P.n_max + (n - 1)) * P.row_doubles;
         ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
         double num = 0.0; unsigned int ncomp = 0;
         for (int k = 0; k < nH; k++) {
             const int c = cnt[lo + k], a = dA[lo + k], b = dB[lo + k];
-            col[k * 32] = pack_class((unsigned int)c, a, b);
+            col[k * cs] = pack_class((unsigned int)c, a, b);
             tot.n += (unsigned int)c;
             if (a >= 0) tot.ncompA += (unsigned int)c;
             if (b >= 0) tot.ncompB += (unsigned int)c;
@@ -937,65 +892,108 @@ __global__ void __launch_bounds__(128) pismc_classes_kernel(DevProblem P, long l
             if (g == GB && b >= 0) { num += (double)c * __ldg(row + P.off_wEB + b); ncomp += (unsigned int)c; }
         }
         double pi;
-        {
-            ChunkPartial cp = {0, 0, 0, 0, 0, 0};
-            auto ld = [row](int off) { return __ldg(row + off); };
-            if (g == GC && nH > 0) cp = chunk_forward<1>(ld, P.w, P.off_yw, P.off_zlow, P.off_g, P.off_zdiag, P.off_EA, P.off_EB,
-                                                         col, 32, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0, tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0,
-                                                         P.pow2negLA, P.pow2negLB, r, r + 1);
-            double ipre = cp.pre, ipreB = cp.preB;
-            for (int o = 1; o < p; o <<= 1) {
-                const double t1 = __shfl_up_sync(kFull, ipre, o, p), t2 = __shfl_up_sync(kFull, ipreB, o, p);
-                if (r >= o) { ipre += t1; ipreB += t2; }
-            }
-            double epre = __shfl_up_sync(kFull, ipre, 1, p), epreB = __shfl_up_sync(kFull, ipreB, 1, p);
-            if (r == 0) { epre = 0.0; epreB = 0.0; }
-            double acc = chunk_finish(cp, epre, epreB), acc2 = cp.acc2;
-            for (int o = 1; o < p; o <<= 1) { acc += __shfl_xor_sync(kFull, acc, o); acc2 += __shfl_xor_sync(kFull, acc2, o); }
-            if (g == GC) pi = nH > 0 ? pismc_finish(acc, acc2, tot.n) : P.pow2negL;
-            else pi = marginal_finish(num, ncomp, nH > 0 ? n : 0u, g == GA ? P.pow2negLA : P.pow2negLB, P.wsum);
+        if (g == GC) {
+            auto ldmy = [row](int k) { const double2 v = __ldg(reinterpret_cast<const double2*>(row + 2 * k)); MYPair e; e.m = v.x; e.y = v.y; return e; };
+            pi = nH > 0 ? pismc_bilinear(ldmy, P.SB, P.LA, P.LB, col, cs, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0,
+                                         tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, 1.0 / (double)tot.n, P.pow2negLA, P.pow2negLB)
+                        : P.pow2negL;
+        } else {
+            pi = marginal_finish(num, ncomp, nH > 0 ? n : 0u, g == GA ? P.pow2negLA : P.pow2negLB, P.wsum);
         }
-        if (valid && r == 0) out[qi] = pi;
-        __syncwarp();
+        out[qi] = pi;
     }
 }
 
-// K3: per-block partial log-sum-exp of the (3+T) weighted statistics of SamplerOutput::addSample
-// (SamplerOutput.cpp:76-93). grid = (blocks over histories, G, 3+T); block partials [stat][g][block][2].
-__global__ void __launch_bounds__(256) lse_partial_kernel(unsigned long long n, int G, int T, const double* __restrict__ weights,
-                                                          const double* __restrict__ tmrca, const double* __restrict__ lineages,
-                                                          double* __restrict__ block_partials) {
-    const int g = blockIdx.y, stat = blockIdx.z;
-    double mx = -INFINITY, sm = 0.0;
-    for (unsigned long long h = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < n; h += (unsigned long long)gridDim.x * blockDim.x) {
-        const double w = weights[h * (unsigned long long)G + g];
-        double x;
-        if (stat == 0) x = w;
-        else if (stat == 1) x = 2.0 * w;
-        else if (stat == 2) x = w + log(tmrca[h]);
-        else x = w + log(lineages[h * (unsigned long long)T + (stat - 3)]);
-        if (x == x) {   // histories that overflowed carry NaN and are counted separately
-            if (x > mx) { sm = sm * exp(mx - x) + 1.0; mx = x; } else { sm += exp(x - mx); }
+// K3: per-block partial log-sum-exp of the (3+T) weighted statistics of SamplerOutput::addSample (SamplerOutput.cpp:76-93)
+// in ONE pass over the weights: with m the running maximum of the log-weights w of a grid point and e_h = exp(w_h - m),
+//   log sum w = m + log sum e,   log sum w^2 = 2m + log sum e^2,   log sum w t = m + log sum t e,   log sum w n_l = m + log sum n_l e,
+// so every history costs one exp per grid point for all statistics (the reference inserts 3+T values per history and
+// grid point into multisets and log-adds them in sorted order). Thread (r, c) of a block owns grid column c of its
+// column tile and every kLseRows-th history; rows are combined with warp shuffles (columns narrower than a warp) and
+// through shared memory. Weights of -inf (a target value of 0) count as 0; NaN weights are the histories that overflowed
+// the type store (counted by K1) or a numerical failure: they are skipped and counted in counters[9].
+// grid = (blocks over histories, column tiles, ceil(T / kLseT)); block partials [stat][g][block][2].
+constexpr int kLseT = 8;          // lineage statistics per pass (blockIdx.z selects l0 = z * kLseT; z > 0 skips the first three)
+struct LseAcc {
+    double m, s[3 + kLseT];
+    __device__ __forceinline__ void clear() { m = -INFINITY; for (int i = 0; i < 3 + kLseT; i++) s[i] = 0.0; }
+    // this <- this (+) o
+    __device__ __forceinline__ void merge(const LseAcc& o) {
+        const double mm = fmax(m, o.m);
+        if (mm == -INFINITY) return;
+        const double f1 = exp(m - mm), f2 = exp(o.m - mm);          // exp(-inf) = 0: an empty side vanishes
+        s[1] = s[1] * (f1 * f1) + o.s[1] * (f2 * f2);
+        s[0] = s[0] * f1 + o.s[0] * f2; s[2] = s[2] * f1 + o.s[2] * f2;
+#pragma unroll
+        for (int i = 3; i < 3 + kLseT; i++) s[i] = s[i] * f1 + o.s[i] * f2;
+        m = mm;
+    }
+};
+__global__ void __launch_bounds__(256) lse_partial_kernel(unsigned long long n, int G, int T, int cols /* power of two <= 32 */,
+                                                          const double* __restrict__ weights, const double* __restrict__ tmrca,
+                                                          const double* __restrict__ lineages, double* __restrict__ block_partials,
+                                                          unsigned long long* __restrict__ counters) {
+    const int c = threadIdx.x & (cols - 1), r = threadIdx.x / cols, rows = blockDim.x / cols;
+    const int g = blockIdx.y * cols + c;
+    const int l0 = blockIdx.z * kLseT, nl = min(kLseT, T - l0);
+    LseAcc a; a.clear();
+    unsigned int n_nan = 0;
+    if (g < G) {
+        for (unsigned long long h = (unsigned long long)blockIdx.x * rows + r; h < n; h += (unsigned long long)gridDim.x * rows) {
+            const double w = weights[h * (unsigned long long)G + g];
+            if (w != w) { n_nan++; continue; }
+            if (w == -INFINITY) continue;
+            double e = 1.0;
+            if (w > a.m) {
+                const double f = exp(a.m - w);                       // a.m = -inf: 0
+                a.s[0] *= f; a.s[1] *= f * f; a.s[2] *= f;
+#pragma unroll
+                for (int i = 3; i < 3 + kLseT; i++) a.s[i] *= f;
+                a.m = w;
+            } else {
+                e = exp(w - a.m);
+            }
+            a.s[0] += e; a.s[1] += e * e; a.s[2] += tmrca[h] * e;
+            const double* ln = lineages + h * (unsigned long long)T + l0;
+#pragma unroll
+            for (int i = 0; i < kLseT; i++) if (i < nl) a.s[3 + i] += ln[i] * e;
         }
     }
-    __shared__ double smx[256], ssm[256];
-    smx[threadIdx.x] = mx; ssm[threadIdx.x] = sm;
+    // rows of one warp that share a column: xor shuffles over the row bits of the lane index
+    for (int o = cols; o < 32; o <<= 1) {
+        LseAcc b;
+        b.m = __shfl_xor_sync(kFull, a.m, o);
+#pragma unroll
+        for (int i = 0; i < 3 + kLseT; i++) b.s[i] = __shfl_xor_sync(kFull, a.s[i], o);
+        a.merge(b);
+    }
+    n_nan = warp_sum_u(n_nan);
+    // one accumulator per (warp, column) through shared memory, combined by the threads of warp 0
+    __shared__ double sh[8][32][4 + kLseT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < cols) {
+        sh[warp][lane][0] = a.m;
+#pragma unroll
+        for (int i = 0; i < 3 + kLseT; i++) sh[warp][lane][1 + i] = a.s[i];
+    }
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            const double m1 = smx[threadIdx.x], m2 = smx[threadIdx.x + o];
-            const double s1 = ssm[threadIdx.x], s2 = ssm[threadIdx.x + o];
-            const double mm = fmax(m1, m2);
-            double ss = 0.0;
-            if (mm > -INFINITY) ss = s1 * exp(m1 - mm) + s2 * exp(m2 - mm);
-            smx[threadIdx.x] = mm; ssm[threadIdx.x] = ss;
+    if (warp == 0 && lane < cols) {
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) {
+            LseAcc b; b.m = sh[w2][lane][0];
+#pragma unroll
+            for (int i = 0; i < 3 + kLseT; i++) b.s[i] = sh[w2][lane][1 + i];
+            a.merge(b);
         }
-        __syncthreads();
+        if (g < G) {
+            auto put = [&](int stat, double mx, double sm) {
+                double* o = block_partials + (((size_t)stat * G + g) * gridDim.x + blockIdx.x) * 2;
+                o[0] = mx; o[1] = sm;
+            };
+            if (blockIdx.z == 0) { put(0, a.m, a.s[0]); put(1, 2.0 * a.m, a.s[1]); put(2, a.m, a.s[2]); }
+            for (int i = 0; i < nl; i++) put(3 + l0 + i, a.m, a.s[3 + i]);
+        }
     }
-    if (threadIdx.x == 0) {
-        double* o = block_partials + (((size_t)stat * G + g) * gridDim.x + blockIdx.x) * 2;
-        o[0] = smx[0]; o[1] = ssm[0];
-    }
+    if (lane == 0 && n_nan && blockIdx.z == 0) atomicAdd(counters + 9, (unsigned long long)n_nan);
 }
 
 // K3b: combine block partials -> partials[stat][g][2]
@@ -1004,9 +1002,9 @@ __global__ void lse_combine_kernel(int nblocks, int total, const double* __restr
     if (i >= total) return;
     const double* p = block_partials + (size_t)i * nblocks * 2;
     double mx = -INFINITY;
-    for (int b = 0; b < nblocks; b++) mx = fmax(mx, p[2 * b]);
+    for (int b = 0; b < nblocks; b++) if (p[2 * b + 1] > 0.0) mx = fmax(mx, p[2 * b]);
     double sm = 0.0;
-    if (mx > -INFINITY) for (int b = 0; b < nblocks; b++) sm += p[2 * b + 1] * exp(p[2 * b] - mx);
+    if (mx > -INFINITY) for (int b = 0; b < nblocks; b++) if (p[2 * b + 1] > 0.0) sm += p[2 * b + 1] * exp(p[2 * b] - mx);
     partials[2 * i] = mx; partials[2 * i + 1] = sm;
 }
 
@@ -1025,7 +1023,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-size_t history_group_bytes(int kmax, int pvmax, int Ltot, int W) { return group_mem_bytes(kmax, pvmax, Ltot, W); }
+size_t history_group_bytes(int kmax, int pvmax, int Ltot, int W, int stage_doubles) { return group_mem_bytes(kmax, pvmax, Ltot, W, stage_doubles); }
 
 // K4: emission tables of the stable mode on the device (the host version and the derivation are in
 // coal_tables.cpp: E[i][d] = 1/(w_i 2^L) * integral over interval i of e^-t (1+e^-at)^(L-d) (1-e^-at)^d dt, a = 2 theta/n,
@@ -1037,7 +1035,7 @@ __constant__ double c_GLw[32] = {0.007018610009470506, 0.016274394730905743, 0.0
 __constant__ double c_Lagx[32] = {0.04448936583326739, 0.23452610951961825, 0.5768846293018863, 1.072448753817818, 1.7224087764446456, 2.5283367064257942, 3.492213273021994, 4.616456769749767, 5.903958504174244, 7.358126733186241, 8.982940924212597, 10.78301863253997, 12.763697986742725, 14.931139755522558, 17.292454336715316, 19.855860940336054, 22.630889013196775, 25.628636022459247, 28.862101816323474, 32.346629153964734, 36.10049480575197, 40.14571977153944, 44.50920799575494, 49.22439498730864, 54.33372133339691, 59.89250916213402, 65.97537728793505, 72.68762809066271, 80.18744697791352, 88.7353404178924, 98.82954286828398, 111.7513980979377};
 __constant__ double c_Lagw[32] = {0.10921834195242515, 0.2104431079387924, 0.23521322966984298, 0.19590333597287354, 0.1299837862860684, 0.07057862386571556, 0.03176091250917397, 0.011918214834838204, 0.003738816294611417, 0.0009808033066149246, 0.0002148649188013578, 3.920341967987801e-05, 5.934541612868448e-06, 7.41640457866734e-07, 7.604567879120552e-08, 6.350602226625618e-09, 4.281382971040738e-10, 2.305899491891237e-11, 9.799379288726772e-13, 3.2378016577291567e-14, 8.171823443420549e-16, 1.542133833393811e-17, 2.119792290163547e-19, 2.0544296737880036e-21, 1.3469825866373617e-23, 5.661294130397462e-26, 1.4185605454629684e-28, 1.9133754944539943e-31, 1.1922487600982012e-34, 2.6715112192396625e-38, 1.3386169421064243e-42, 4.5105361938987784e-48};
 struct EmissionArgs {
-    double* rows;               // [n_sets][n_max][row_doubles]
+    double* rows;               // [n_sets][n_max][row_doubles], reference layout (coal_tables.h): the kernel fills EA | EB | wEA | wEB
     const double* thetas;       // [n_sets]
     int n_sets, n_max, row_doubles, LA, LB, Q;
     int off_EA, off_EB, off_wEA, off_wEB;
@@ -1082,6 +1080,31 @@ __global__ void __launch_bounds__(128) emission_stable_kernel(const EmissionArgs
             wE += A.w[i] * e;
         }
         row[(locA ? A.off_wEA : A.off_wEB) + d] = wE;
+    }
+}
+
+// K5: device rows (bilinear tables M, Y + one-locus weight vectors, coal_tables.h) from reference-layout rows that live
+// on the device -- the second half of the device table builder: the stable-mode emission tables never visit the host.
+// One thread per (row, dA) for the MY part, the first LA + LB + 2 threads of a row's range copy the weight vectors.
+struct BilinearArgs {
+    const double* full_rows;    // [n_rows][row_doubles]
+    double* dev_rows;           // [n_rows][dev_row_doubles]
+    long long n_rows;
+    int row_doubles, dev_row_doubles, LA, LB;
+    int off_yw, off_zlow, off_g, off_zdiag, off_EA, off_EB, off_wEA, off_wEB, dev_sb, dev_off_wEA, dev_off_wEB;
+    double w[kQd];
+};
+__global__ void __launch_bounds__(128) bilinear_rows_kernel(const BilinearArgs A) {
+    const int per_row = A.LA + 2;
+    const long long total = A.n_rows * per_row;
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int dA = (int)(id % per_row);
+        const long long rn = id / per_row;
+        const double* row = A.full_rows + (size_t)rn * A.row_doubles;
+        double* drow = A.dev_rows + (size_t)rn * A.dev_row_doubles;
+        bilinear_row(row, A.w, A.off_yw, A.off_zlow, A.off_g, A.off_zdiag, A.off_EA, A.off_EB, A.LA, A.LB, dA, drow + (size_t)2 * dA * A.dev_sb);
+        if (dA <= A.LA) drow[A.dev_off_wEA + dA] = row[A.off_wEA + dA];
+        for (int d = dA; d <= A.LB; d += per_row) drow[A.dev_off_wEB + d] = row[A.off_wEB + d];
     }
 }
 

@@ -1,18 +1,29 @@
 // Arithmetic cores shared by the kernels (device) and the host unit-test shim (tests/ compile this
 // header with g++ and compare against the oracle on the CPU box, where no GPU exists).
 //
-// pi_SMC(h | H) for a two-locus query, ConditionalSamplingHMM.cpp:372-424 of the reference, restated so
-// that one lane group can split the Q = 16 absorption-time intervals:
+// pi_SMC(h | H) for a two-locus query, ConditionalSamplingHMM.cpp:372-424 of the reference. With the classes k of
+// TypeContainer::getDifferences (count c_k, distances dA_k, dB_k; -1 = locus not ancestral) the reference computes, per
+// absorption-time interval i,
 //   A_i  = sum_k c_k eA(i,k)   B_i = sum_k c_k eB(i,k)   X_i = sum_k c_k eA(i,k) eB(i,k)
 //   eA(i,k) = EA[i][dA_k] if class k is ancestral at locus A, else the count-weighted mean PA_i of the
 //             complete classes (ConditionalSamplingHMM.cpp:234-263), or 2^-LA if there is none
 //   b_i  = w_i A_i                                  (n * base_sum_vector(i), :385-391)
-//   S_j  = zlow_j sum_{i>j} b_i + w_j sum_{i<j} b_i g_i + zdiag_j b_j     (n * the i-loop at :404-407)
+//   S_j  = sum_i b_i z(i,j)                         (n * the i-loop at :404-407)
 //   pi   = ( sum_j S_j B_j / n + sum_j y_j w_j X_j ) / n                  (:409-419)
-// sum_j S_j B_j is accumulated in ONE forward sweep with two running prefixes,
-//   Pre_j = sum_{i<j} b_i g_i,   PreB_j = sum_{i<j} B_i zlow_i,
-//   sum_j S_j B_j = sum_j [ B_j (w_j Pre_j + zdiag_j b_j) + b_j PreB_j ],
-// so a chunk of intervals only needs the two prefixes of the chunks before it.
+// Every term is linear in the emission vectors of locus A and of locus B, and the interval axis is summed out. So the
+// 16-interval forward pass collapses into a BILINEAR FORM over distances with two small matrices that depend on the
+// table row (epoch, lineage count) only and are built once per sampler:
+//   M[dA][dB] = sum_ij EA[dA][i] w_i z(i,j) EB[dB][j]        Y[dA][dB] = sum_j y_j w_j EA[dA][j] EB[dB][j]
+// (index LA+1 / LB+1 = the all-ones emission vector, standing for "no class ancestral at this locus"). With
+// CA / CB = the classes ancestral at A / at B, ncompA / ncompB their lineage totals:
+//   pi = T1 / (ncompA ncompB) + ( T2 + T3 / ncompB + T4 / ncompA ) / n
+//   T1 = sum_{k in CA, k' in CB} c_k c_k' M[dA_k][dB_k']         (b^T Z B:   A_i = n/ncompA * sum_{CA} c_k EA[dA_k][i])
+//   T2 = sum_{k in CA and CB}    c_k Y[dA_k][dB_k]               (classes ancestral at both loci)
+//   T3 = sum_{k in CA \ CB, k' in CB} c_k c_k' Y[dA_k][dB_k']   (A-only classes take the mean B emission of CB)
+//   T4 = sum_{k' in CB \ CA, k in CA} c_k c_k' Y[dA_k][dB_k']   (B-only classes likewise)
+// about nH^2 fused multiply-adds per query instead of 16 intervals x nH classes x 7 + the interval chain. All terms
+// are non-negative, so the regrouping changes the result at the 1e-15 level only (tests: <= 1e-13 relative against
+// the values the compiled reference recorded).
 #pragma once
 #include <cstdint>
 
@@ -24,8 +35,8 @@
 
 namespace coalgpu {
 
-// Stride (in doubles) between the emission-table rows of consecutive distances (must be even: rows are copied with
-// 16-byte granularity). Padding to 18 removes shared-memory bank conflicts but was 0.7 % slower (larger copies).
+// Stride (in doubles) between the emission-table rows of consecutive distances in the reference-layout rows
+// (coal_tables.h; the kernels read the bilinear rows, not these).
 #ifndef COAL_ESTRIDE
 #define COAL_ESTRIDE 16
 #endif
@@ -34,81 +45,95 @@ constexpr int kEStride = COAL_ESTRIDE;
 // packed class: count | (dA+1) << 16 | (dB+1) << 24   (dA/dB = -1 when the locus is not ancestral)
 COAL_HD uint32_t pack_class(uint32_t count, int dA, int dB) { return count | ((uint32_t)(dA + 1) << 16) | ((uint32_t)(dB + 1) << 24); }
 
-struct ChunkPartial {
-    double acc;      // sum over the chunk of B_j (w_j Pre'_j + zdiag_j b_j) + b_j PreB'_j with chunk-local prefixes
-    double acc2;     // sum over the chunk of yw_j X_j
-    double pre;      // sum over the chunk of b_i g_i
-    double preB;     // sum over the chunk of B_i zlow_i
-    double sBw;      // sum over the chunk of B_j w_j
-    double sb;       // sum over the chunk of b_j
-};
-
 struct ClassTotals {
     uint32_t n;       // all lineages in the conditioning configuration
     uint32_t ncompA;  // lineages in classes ancestral at A
     uint32_t ncompB;
 };
 
-// Forward sweep over intervals [i0, i1) for one query, in blocks of PER intervals (PER divides i1 - i0).
-// The loop nest is class-outer / interval-inner so that the class word is decoded once per block and the
-// PER table reads of a class are independent loads. Emission tables are stored distance-major
-// (E[d*kEStride + i], see coal_tables.h), i.e. the intervals of one class are contiguous.
-// `cls` is read with stride `cstride` (32 on the device: one shared-memory column per query).
-template <int PER, class LoadF>
-COAL_HD ChunkPartial chunk_forward(LoadF ld, const double* w, int off_yw, int off_zlow, int off_g, int off_zdiag,
-                                   int off_EA, int off_EB, const uint32_t* cls, int cstride, int nH,
-                                   ClassTotals tot, double invA, double invB, double pow2negLA, double pow2negLB, int i0, int i1) {
-    // invA = 1/ncompA, invB = 1/ncompB (0 when the count is 0): the device reads them from a table
-    ChunkPartial p = {0, 0, 0, 0, 0, 0};
-    const double npartA = (double)(tot.n - tot.ncompA), npartB = (double)(tot.n - tot.ncompB);
-    for (int ib = i0; ib < i1; ib += PER) {
-        double aAll[PER], bAll[PER], x[PER], aAo[PER], bBo[PER];
-#pragma unroll
-        for (int ii = 0; ii < PER; ii++) { aAll[ii] = 0; bAll[ii] = 0; x[ii] = 0; aAo[ii] = 0; bBo[ii] = 0; }
+struct MYPair { double m, y; };
+
+// One dA row of the bilinear tables from a reference-layout row (yw | zlow | g | zdiag | EA | EB, coal_tables.h):
+// out[2*dB] = M[dA][dB], out[2*dB+1] = Y[dA][dB] for dB = 0..LB+1. z(i,j) = zlow[j] (i > j), w[j] g[i] (i < j),
+// zdiag[i] (i == j) (ConditionalSamplingHMM.cpp:110-173), so U_j = sum_i EA[dA][i] w_i z(i,j) needs one prefix and
+// one suffix sum. Shared by the host table builder and the device table builder (stable emission mode).
+COAL_HD void bilinear_row(const double* row, const double* w, int off_yw, int off_zlow, int off_g, int off_zdiag,
+                          int off_EA, int off_EB, int LA, int LB, int dA, double* out) {
+    constexpr int Q = 16;
+    double aw[Q], U[Q];
+    for (int i = 0; i < Q; i++) aw[i] = (dA <= LA ? row[off_EA + dA * kEStride + i] : 1.0) * w[i];
+    double suf[Q + 1];
+    suf[Q] = 0.0;
+    for (int i = Q - 1; i >= 0; i--) suf[i] = suf[i + 1] + aw[i];       // suf[i] = sum_{i' >= i} aw
+    double pre = 0.0;                                                    // sum_{i < j} aw_i g_i
+    for (int j = 0; j < Q; j++) {
+        U[j] = w[j] * pre + aw[j] * row[off_zdiag + j] + row[off_zlow + j] * suf[j + 1];
+        pre += aw[j] * row[off_g + j];
+    }
+    for (int dB = 0; dB <= LB + 1; dB++) {
+        double m = 0.0, y = 0.0;
+        for (int j = 0; j < Q; j++) {
+            const double eb = dB <= LB ? row[off_EB + dB * kEStride + j] : 1.0;
+            const double ea = dA <= LA ? row[off_EA + dA * kEStride + j] : 1.0;
+            m += U[j] * eb;
+            y += row[off_yw + j] * ea * eb;
+        }
+        out[2 * dB] = m; out[2 * dB + 1] = y;
+    }
+}
+
+// pi_SMC of one two-locus query from its class list (see the header comment). `cls` is read with stride `cstride`;
+// ldmy(k) returns the (M, Y) pair number k of the row (k = dA * SB + dB, SB = LB + 2). invA = 1/ncompA, invB = 1/ncompB
+// (0 when the count is 0: the device reads reciprocals from a table), inv_n = 1/tot.n. nH >= 1.
+template <class LoadMY>
+COAL_HD double pismc_bilinear(LoadMY ldmy, int SB, int LA, int LB, const uint32_t* cls, int cstride, int nH,
+                              ClassTotals tot, double invA, double invB, double inv_n, double pow2negLA, double pow2negLB) {
+    if (tot.ncompA != 0 && tot.ncompB != 0) {
+        double t1 = 0.0, ty = 0.0;
         for (int k = 0; k < nH; k++) {
             const uint32_t v = cls[k * cstride];
+            const int dA = (int)((v >> 16) & 0xffu) - 1;
+            if (dA < 0) continue;                                   // B-only class: enters through the k2 loop of the others
             const double c = (double)(v & 0xffffu);
-            const int dA = (int)((v >> 16) & 0xffu) - 1, dB = (int)(v >> 24) - 1;
-            const int ea_base = off_EA + (dA < 0 ? 0 : dA) * kEStride + ib, eb_base = off_EB + (dB < 0 ? 0 : dB) * kEStride + ib;
-            const double ca0 = dA >= 0 ? c : 0.0, cb0 = dB >= 0 ? c : 0.0;
-#pragma unroll
-            for (int ii = 0; ii < PER; ii++) {
-                const double eb = ld(eb_base + ii);
-                const double ca = ca0 * ld(ea_base + ii), cb = cb0 * eb;
-                aAll[ii] += ca; bAll[ii] += cb; x[ii] += ca * (dB >= 0 ? eb : 0.0);
-                if (dB < 0) aAo[ii] += ca;
-                if (dA < 0) bBo[ii] += cb;
+            const double fk = (v >> 24) == 0 ? invB : 0.0;          // A-only class: mean B emission of CB (T3)
+            const int rowoff = dA * SB;
+            double sm = 0.0, sy = 0.0;
+            for (int k2 = 0; k2 < nH; k2++) {
+                const uint32_t v2 = cls[k2 * cstride];
+                const int dB2 = (int)(v2 >> 24) - 1;
+                if (dB2 < 0) continue;
+                const double c2 = (double)(v2 & 0xffffu);
+                const MYPair e = ldmy(rowoff + dB2);
+                sm += c2 * e.m;
+                const double f = fk + (((v2 >> 16) & 0xffu) == 0 ? invA : 0.0);   // B-only partner: mean A emission of CA (T4)
+                sy += (k2 == k ? 1.0 : c2 * f) * e.y;               // k2 == k: the class itself, ancestral at both loci (T2)
             }
+            t1 += c * sm; ty += c * sy;
         }
-#pragma unroll
-        for (int ii = 0; ii < PER; ii++) {
-            const int i = ib + ii;
-            const double PA = tot.ncompA ? aAll[ii] * invA : pow2negLA;
-            const double PB = tot.ncompB ? bAll[ii] * invB : pow2negLB;
-            const double Ai = aAll[ii] + npartA * PA, Bi = bAll[ii] + npartB * PB;
-            const double Xi = x[ii] + PB * aAo[ii] + PA * bBo[ii];
-            const double wi = w[i];
-            const double bi = wi * Ai;
-            p.acc += Bi * (wi * p.pre + ld(off_zdiag + i) * bi) + bi * p.preB;
-            p.acc2 += ld(off_yw + i) * Xi;
-            p.sBw += Bi * wi;
-            p.sb += bi;
-            p.pre += bi * ld(off_g + i);
-            p.preB += Bi * ld(off_zlow + i);
-        }
+        return t1 * invA * invB + ty * inv_n;
     }
-    return p;
-}
-
-// Contribution of a chunk once the prefixes of all earlier chunks are known.
-COAL_HD double chunk_finish(const ChunkPartial& p, double pre_before, double preB_before) {
-    return p.acc + pre_before * p.sBw + preB_before * p.sb;
-}
-
-// pi from the sums over all chunks
-COAL_HD double pismc_finish(double sum_acc, double sum_acc2, uint32_t n) {
-    const double inv_n = 1.0 / (double)n;
-    return (sum_acc * inv_n + sum_acc2) * inv_n;
+    // nothing ancestral at one of the loci: its emission is the constant 2^-L (ConditionalSamplingHMM.cpp:249-252)
+    double sm = 0.0, sy = 0.0;
+    if (tot.ncompA == 0) {
+        for (int k2 = 0; k2 < nH; k2++) {
+            const uint32_t v2 = cls[k2 * cstride];
+            const int dB2 = (int)(v2 >> 24) - 1;
+            if (dB2 < 0) continue;
+            const double c2 = (double)(v2 & 0xffffu);
+            const MYPair e = ldmy((LA + 1) * SB + dB2);
+            sm += c2 * e.m; sy += c2 * e.y;
+        }
+        return pow2negLA * (sm * invB + sy * inv_n);
+    }
+    for (int k = 0; k < nH; k++) {
+        const uint32_t v = cls[k * cstride];
+        const int dA = (int)((v >> 16) & 0xffu) - 1;
+        if (dA < 0) continue;
+        const double c = (double)(v & 0xffffu);
+        const MYPair e = ldmy(dA * SB + LB + 1);
+        sm += c * e.m; sy += c * e.y;
+    }
+    return pow2negLB * (sm * invA + sy * inv_n);
 }
 
 // One-locus query (ConditionalSamplingHMM.cpp:332-370): with hist[d] = lineages at distance d among the
@@ -149,7 +174,9 @@ COAL_HD void epoch_stats_clear(EpochStats& s) {
 template <class LogF>
 COAL_HD double epoch_log_density(const EpochStats& s, double theta, double rho, double inv2Ntau, double log_theta,
                                  double log_rho, double log_2Ntau, LogF lg) {
-    double v = s.slog + s.n_mut * log_theta + s.n_rec * log_rho - s.n_rate * log_2Ntau
+    // A target value mu = 0 or rho = 0 (main.cpp:169,181 accept them) has log = -inf: a history without such an event keeps
+    // a finite weight there (0 * -inf must not turn into NaN), one with such an event gets weight -inf = probability 0.
+    double v = s.slog + (s.n_mut ? s.n_mut * log_theta : 0.0) + (s.n_rec ? s.n_rec * log_rho : 0.0) - s.n_rate * log_2Ntau
              - (s.s_nn + theta * s.s_a + rho * s.s_c) * inv2Ntau;
     if (s.has_post) v -= lg(s.post_nn + s.post_a * theta + s.post_c * rho);
     if (s.has_bnd) v += lg(s.bnd_nn + s.bnd_a * theta + s.bnd_c * rho);

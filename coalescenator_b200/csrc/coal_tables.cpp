@@ -153,11 +153,18 @@ void emission_table_stable(int Q, const double* t, const double* w, double theta
 // of a data set and the pairs of main.cpp:242-311 have a handful of distinct L. The blocks are therefore kept in a
 // process-wide cache, so that a batch of pairs builds each of them once (the host table
 // builder is the serial section that shows once sampling is fast). Values are the same doubles either way.
+// Readers never look at a buffer that can move: a block that has to grow is rebuilt into a NEW vector (old rows copied,
+// new rows computed) which is then published under the block's mutex; a reader holds the shared_ptr of the snapshot it
+// was given for as long as it copies rows out of it (build_tables), whatever later callers with a larger n_max do.
 struct EmissionBlock {
     std::mutex m;
-    int n_built = 0;                 // blocks for n = 1..n_built are valid
     int stride = 0;                  // doubles per n: (L+1)*kEStride table + (L+1) weighted sums
-    std::vector<double> data;
+    std::shared_ptr<const std::vector<double>> data;   // rows for n = 1..data->size()/stride
+};
+struct EmissionRows {                // an immutable snapshot of a block that covers n = 1..n_max of the request
+    std::shared_ptr<const std::vector<double>> data;
+    int stride = 0;
+    const double* row(int n) const { return data->data() + (size_t)(n - 1) * stride; }
 };
 struct EmissionKey {
     int Q, L, mode; uint64_t theta_bits;
@@ -168,8 +175,8 @@ std::map<EmissionKey, std::shared_ptr<EmissionBlock>> g_cache;
 size_t g_cache_doubles = 0;
 constexpr size_t kCacheMaxDoubles = (size_t)1 << 26;   // 512 MiB; the cache is dropped when it grows past this
 
-std::shared_ptr<EmissionBlock> emission_block(int Q, int L, int mode, double theta, int n_max, const double* t, const double* w,
-                                              const std::vector<double>& bin, int bw, int threads) {
+EmissionRows emission_block(int Q, int L, int mode, double theta, int n_max, const double* t, const double* w,
+                            const std::vector<double>& bin, int bw, int threads) {
     EmissionKey key{Q, L, mode, 0};
     std::memcpy(&key.theta_bits, &theta, sizeof(double));
     std::shared_ptr<EmissionBlock> b;
@@ -186,12 +193,16 @@ std::shared_ptr<EmissionBlock> emission_block(int Q, int L, int mode, double the
         }
     }
     std::lock_guard<std::mutex> lk(b->m);
-    if (b->n_built < n_max) {
-        const int lo = b->n_built;
-        b->data.resize((size_t)n_max * b->stride, 0.0);
+    const int n_built = b->data ? (int)(b->data->size() / (size_t)b->stride) : 0;
+    if (n_built < n_max) {
+        const int lo = n_built;
+        auto grown = std::make_shared<std::vector<double>>((size_t)n_max * b->stride, 0.0);
+        if (lo) std::memcpy(grown->data(), b->data->data(), sizeof(double) * (size_t)lo * b->stride);
+        double* const base = grown->data();
+        const int stride = b->stride;
         auto fill = [&](int a, int e) {
             for (int n = a + 1; n <= e; n++) {
-                double* E = b->data.data() + (size_t)(n - 1) * b->stride;
+                double* E = base + (size_t)(n - 1) * stride;
                 if (mode == kEmissionStable) emission_table_stable(Q, t, w, theta, (unsigned)n, L, E);
                 else emission_table(Q, t, w, bin, bw, theta, (unsigned)n, L, E);
                 double* wE = E + (L + 1) * kEStride;
@@ -211,9 +222,9 @@ std::shared_ptr<EmissionBlock> emission_block(int Q, int L, int mode, double the
             std::lock_guard<std::mutex> lk2(g_cache_mutex);
             g_cache_doubles += (size_t)total * b->stride;
         }
-        b->n_built = n_max;
+        b->data = std::move(grown);
     }
-    return b;
+    return EmissionRows{b->data, b->stride};
 }
 
 }  // namespace
@@ -263,8 +274,8 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
     for (int s = 0; s < out.n_sets; s++) {
         const double theta = thetas[rep[s]], r = r_rates[rep[s]];
         const bool emit = emission_mode != kEmissionNone;
-        const std::shared_ptr<EmissionBlock> bA = emit ? emission_block(Q, LA, emission_mode, theta, n_max, t, w, bin, bw, threads) : nullptr;
-        const std::shared_ptr<EmissionBlock> bB = !emit ? nullptr : (LB == LA) ? bA : emission_block(Q, LB, emission_mode, theta, n_max, t, w, bin, bw, threads);
+        const EmissionRows bA = emit ? emission_block(Q, LA, emission_mode, theta, n_max, t, w, bin, bw, threads) : EmissionRows();
+        const EmissionRows bB = !emit ? EmissionRows() : (LB == LA) ? bA : emission_block(Q, LB, emission_mode, theta, n_max, t, w, bin, bw, threads);
         for (int n = 1; n <= n_max; n++) {
             const size_t idx = (size_t)s * n_max + (n - 1);
             double* row = out.rows.data() + idx * lay.row_doubles;
@@ -272,12 +283,25 @@ bool build_tables(int Q, int LA, int LB, int n_max, const std::vector<double>& t
             transition_row(Q, t, w, e0, r, (unsigned)n, y, row + lay.off_zlow, row + lay.off_g, row + lay.off_zdiag);
             for (int i = 0; i < kQ; i++) row[lay.off_yw + i] = y[i] * w[i];
             if (!emit) continue;
-            const double* a = bA->data.data() + (size_t)(n - 1) * bA->stride;
-            const double* b = bB->data.data() + (size_t)(n - 1) * bB->stride;
+            const double* a = bA.row(n);
+            const double* b = bB.row(n);
             std::memcpy(row + lay.off_EA, a, sizeof(double) * (LA + 1) * kEStride);
             std::memcpy(row + lay.off_EB, b, sizeof(double) * (LB + 1) * kEStride);
             std::memcpy(row + lay.off_wEA, a + (LA + 1) * kEStride, sizeof(double) * (LA + 1));
             std::memcpy(row + lay.off_wEB, b + (LB + 1) * kEStride, sizeof(double) * (LB + 1));
+        }
+    }
+    // device rows: the bilinear form of the two-locus forward pass (coal_math.h) + the one-locus weight vectors
+    out.dev_rows.clear();
+    if (emission_mode != kEmissionNone) {
+        out.dev_rows.assign((size_t)out.n_sets * n_max * lay.dev_row_doubles, 0.0);
+        for (size_t idx = 0; idx < (size_t)out.n_sets * n_max; idx++) {
+            const double* row = out.rows.data() + idx * lay.row_doubles;
+            double* drow = out.dev_rows.data() + idx * lay.dev_row_doubles;
+            for (int dA = 0; dA <= LA + 1; dA++)
+                bilinear_row(row, w, lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB, LA, LB, dA, drow + (size_t)2 * dA * lay.dev_sb);
+            std::memcpy(drow + lay.dev_off_wEA, row + lay.off_wEA, sizeof(double) * (LA + 1));
+            std::memcpy(drow + lay.dev_off_wEB, row + lay.off_wEB, sizeof(double) * (LB + 1));
         }
     }
     return true;

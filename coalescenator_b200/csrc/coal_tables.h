@@ -18,7 +18,13 @@ struct TableLayout {
     int LA = 0, LB = 0;
     int off_yw = 0, off_zlow = kQ, off_g = 2 * kQ, off_zdiag = 3 * kQ;
     int off_EA = 4 * kQ, off_EB = 0, off_wEA = 0, off_wEB = 0;   // EA: [(LA+1)][kEStride], EB: [(LB+1)][kEStride] (distance-major, padded)
-    int row_doubles = 0;   // multiple of 2 (16-byte rows for bulk copies)
+    int row_doubles = 0;   // multiple of 2
+    // What the history kernel reads (coal_math.h "bilinear form"): per (table set, lineage count) one DEVICE row
+    //   MY[(LA+2)][(LB+2)][2] | wEA[LA+1] | wEB[LB+1]
+    // M[dA][dB] = sum_ij EA[dA][i] w_i z(i,j) EB[dB][j] and Y[dA][dB] = sum_j y_j w_j EA[dA][j] EB[dB][j], interleaved; index
+    // LA+1 / LB+1 stands for "no lineage ancestral at this locus" (emission 1 at every interval).
+    int dev_sb = 0;        // LB + 2: entries per dA row of MY
+    int dev_off_wEA = 0, dev_off_wEB = 0, dev_row_doubles = 0;   // dev_row_doubles: multiple of 2 (16-byte rows for bulk copies)
     void init(int la, int lb) {
         LA = la; LB = lb;
         off_EB = off_EA + kEStride * (LA + 1);
@@ -26,6 +32,10 @@ struct TableLayout {
         off_wEB = off_wEA + (LA + 1);
         row_doubles = off_wEB + (LB + 1);
         row_doubles = (row_doubles + 1) & ~1;
+        dev_sb = LB + 2;
+        dev_off_wEA = 2 * (LA + 2) * (LB + 2);
+        dev_off_wEB = dev_off_wEA + (LA + 1);
+        dev_row_doubles = (dev_off_wEB + (LB + 1) + 1) & ~1;
     }
 };
 
@@ -37,9 +47,11 @@ struct HostTables {
     std::vector<int> set_of_epoch; // [T]
     std::vector<double> w;         // [kQ] interval weights
     std::vector<double> quad;      // [kQ+1]
-    std::vector<double> rows;      // [n_sets][n_max][row_doubles]
+    std::vector<double> rows;      // [n_sets][n_max][row_doubles]: the reference's constants (coalgpu_tables, device table builder input)
+    std::vector<double> dev_rows;  // [n_sets][n_max][dev_row_doubles]: what the kernels read; empty when the emission tables are built on the device
     std::vector<double> y;         // [n_sets][n_max][kQ] plain y (for coalgpu_tables)
     const double* row(int set, int n_all) const { return rows.data() + ((size_t)set * n_max + (n_all - 1)) * lay.row_doubles; }
+    const double* dev_row(int set, int n_all) const { return dev_rows.data() + ((size_t)set * n_max + (n_all - 1)) * lay.dev_row_doubles; }
 };
 
 // thetas[c] = 4*lambda_d*V[c]*mu_d, r_rates[c] = 4*lambda_d*V[c]*rho_d (ImportanceSampler.cpp:69-76)

@@ -28,6 +28,7 @@ extern "C" {
 #define COALGPU_ECUDA    (-3)   /* CUDA runtime error (see coalgpu_last_error)       */
 #define COALGPU_ENOMEM   (-4)
 #define COALGPU_EOVERFLOW (-5)  /* a history outgrew the per-history state capacity  */
+#define COALGPU_ENAN     (-6)   /* a history weight came out as NaN (never dropped silently) */
 
 #define COALGPU_GAMMA_A 0       /* lineage ancestral at locus A only  (i,*) */
 #define COALGPU_GAMMA_B 1       /* lineage ancestral at locus B only  (*,j) */

@@ -78,13 +78,14 @@ struct Philox {
         }
         for (int i = 0; i < 4; i++) out[i] = c[i];
     }
-    // draw k of history hist: 53 bits -> (0,1)
+    // draw k of history hist: 52 bits -> (0,1). (bits + 0.5) needs 53 significant bits, so every value is exact,
+    // the smallest is 2^-53 and the largest 1 - 2^-53: never 0 and never 1 (the reference asserts a positive waiting time).
     static double uniform(uint64_t seed, uint64_t hist, uint64_t k) {
         uint32_t o[4];
         block(seed, hist, k >> 1, o);
         const uint32_t lo = o[(k & 1) * 2], hi = o[(k & 1) * 2 + 1];
-        const uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
-        return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+        const uint64_t bits = (((uint64_t)hi << 32) | lo) >> 12;
+        return ((double)bits + 0.5) * (1.0 / 4503599627370496.0);
     }
 };
 

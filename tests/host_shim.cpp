@@ -1,7 +1,7 @@
 // CPU-side harness around the product's host code and the arithmetic cores its kernels use
 // (coalescenator_b200/csrc/coal_tables.cpp, coal_math.h), so they can be checked against the oracle
-// where no GPU exists. The lane-group split of the forward pass is emulated by evaluating the chunks
-// one after another and passing the prefixes along, exactly as the warp shuffles do.
+// where no GPU exists: the table builder (reference-layout rows and the bilinear device rows) and the
+// bilinear evaluation of pi_SMC that every lane of the history kernel runs.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -53,37 +53,30 @@ int hs_tables(void* hp, int n_all, int time_idx, double* w, double* y, double* z
 double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int32_t* cnt, const int32_t* dA, const int32_t* dB, int p) {
     const HostTables& t = ((hs_tables_t*)hp)->tab;
     const TableLayout& lay = t.lay;
-    const double* row = t.row(t.set_of_epoch[time_idx], n_all);
+    (void)lay;
     const double p2A = 1.0 / (double)(1ull << lay.LA), p2B = 1.0 / (double)(1ull << lay.LB);
     double wsum = 0; for (int i = 0; i < kQ; i++) wsum += t.w[i];
     if (gamma != 2) {
         double num = 0; uint32_t ncomp = 0;
+        const double* dr = t.dev_row(t.set_of_epoch[time_idx], n_all);   // the one-locus weight vectors as the kernels read them
         for (int k = 0; k < nH; k++) {
             const int d = gamma == 0 ? dA[k] : dB[k];
-            if (d >= 0) { num += (double)cnt[k] * row[(gamma == 0 ? lay.off_wEA : lay.off_wEB) + d]; ncomp += cnt[k]; }
+            if (d >= 0) { num += (double)cnt[k] * dr[(gamma == 0 ? lay.dev_off_wEA : lay.dev_off_wEB) + d]; ncomp += cnt[k]; }
         }
         return marginal_finish(num, ncomp, nH > 0 ? (uint32_t)n_all : 0u, gamma == 0 ? p2A : p2B, wsum);
     }
     if (nH == 0) return p2A * p2B;
+    (void)p;   // the interval axis is summed out of the bilinear form: nothing left to split over lanes
     std::vector<uint32_t> cls(nH);
     ClassTotals tot{0, 0, 0};
     for (int k = 0; k < nH; k++) {
         cls[k] = pack_class((uint32_t)cnt[k], dA[k], dB[k]);
         tot.n += cnt[k]; if (dA[k] >= 0) tot.ncompA += cnt[k]; if (dB[k] >= 0) tot.ncompB += cnt[k];
     }
-    auto ld = [row](int off) { return row[off]; };
-    const int per = kQ / p;
-    double pre = 0, preB = 0, acc = 0, acc2 = 0;
-    for (int r = 0; r < p; r++) {
-        ChunkPartial cp;
-#define HS_CALL(PER) chunk_forward<PER>(ld, t.w.data(), lay.off_yw, lay.off_zlow, lay.off_g, lay.off_zdiag, lay.off_EA, lay.off_EB, \
-                                        cls.data(), 1, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0, tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, p2A, p2B, r * per, r * per + per)
-        if (per == 1) cp = HS_CALL(1); else if (per == 2) cp = HS_CALL(2); else cp = HS_CALL(4);
-#undef HS_CALL
-        acc += chunk_finish(cp, pre, preB); acc2 += cp.acc2;
-        pre += cp.pre; preB += cp.preB;
-    }
-    return pismc_finish(acc, acc2, tot.n);
+    const double* drow = t.dev_row(t.set_of_epoch[time_idx], n_all);
+    auto ldmy = [drow](int k) { MYPair e; e.m = drow[2 * k]; e.y = drow[2 * k + 1]; return e; };
+    return pismc_bilinear(ldmy, lay.dev_sb, lay.LA, lay.LB, cls.data(), 1, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0,
+                          tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, 1.0 / (double)tot.n, p2A, p2B);
 }
 
 }  // extern "C"

@@ -72,7 +72,9 @@ def test_philox_known_answer(oracle):
     # counter = key = 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
     u0 = oracle.uniform(0, 0, 0)
     lo, hi = 0x6627e8d5, 0xe169c58d
-    assert u0 == (((hi << 32 | lo) >> 11) + 0.5) / 2 ** 53
+    # 52 bits per draw: (bits + 0.5) / 2^52 is exact in double, never 0 and never 1 (53 bits + 0.5 rounds to 1.0)
+    assert u0 == (((hi << 32 | lo) >> 12) + 0.5) / 2 ** 52
     u1 = oracle.uniform(0, 0, 1)
     lo, hi = 0xbc57ac4c, 0x9b00dbd8
-    assert u1 == (((hi << 32 | lo) >> 11) + 0.5) / 2 ** 53
+    assert u1 == (((hi << 32 | lo) >> 12) + 0.5) / 2 ** 52
+    assert (2 ** 52 - 1 + 0.5) / 2 ** 52 < 1.0 and 0.5 / 2 ** 52 > 0.0
