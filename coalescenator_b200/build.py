@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("COALGPU_LIB") or os.path.join(HERE, "libcoalgpu.so")   # COALGPU_LIB: tuning variants only
 SOURCES = ["coal_api.cu", "coal_tables.cpp"]
-DEPS = SOURCES + ["coal_kernels.cu", "coal_device.cuh", "coal_math.h", "coal_tables.h", os.path.join("..", "..", "include", "coalgpu.h")]
+DEPS = SOURCES + ["coal_kernels.cu", "coal_multi.cu", "coal_device.cuh", "coal_math.h", "coal_tables.h", os.path.join("..", "..", "include", "coalgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -682,30 +682,29 @@ int coalgpu_finalize(int32_t G, int32_t T, const double* hp, coalgpu_result* r) 
     return 0;
 }
 
-static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
-    if (!problem || !result) return fail(COALGPU_EINVAL, "null argument");
-    if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
-    const bool timing = std::getenv("COALGPU_TIMING") != nullptr;
-    auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_begin = tick();
-    coalgpu_sampler* s = nullptr;
-    int rc = coalgpu_create(problem, Q, device, &s);
-    if (rc) return rc;
-    const double t_created = tick();
+// Histories [first0, first0 + count) of sampler s on the CURRENT device's default stream, chunked, reduced chunk by chunk
+// into the (max, sum) pairs acc[(3+T)*G*2] on the host. Shared by coalgpu_run_sampler (the whole batch on one device) and
+// coalgpu_run_sampler_comm (one index range per device). Chunking never changes which histories are drawn.
+static int sample_range(coalgpu_sampler* s, uint64_t seed, uint64_t first0, uint64_t count, std::vector<double>& acc,
+                        double* seconds_device, unsigned long long* n_deferred_out) {
     const int G = s->G, T = s->T, nstat = 3 + T;
+    acc.assign((size_t)nstat * G * 2, 0.0);
+    for (size_t i = 0; i < acc.size(); i += 2) acc[i] = -INFINITY;
+    if (seconds_device) *seconds_device = 0.0;
+    if (n_deferred_out) *n_deferred_out = 0;
+    if (count == 0) return 0;
     // chunk the batch so that the per-history weight matrix stays below ~2 GiB
-    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n_samples, (2ull << 30) / ((size_t)(G + T + 1) * 8)));
+    uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(count, (2ull << 30) / ((size_t)(G + T + 1) * 8)));
     double *d_w = nullptr, *d_t = nullptr, *d_l = nullptr, *d_p = nullptr;
     unsigned long long* d_defer = nullptr; unsigned long long n_deferred_total = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    std::vector<double> hp((size_t)nstat * G * 2), acc((size_t)nstat * G * 2);
-    for (size_t i = 0; i < acc.size(); i += 2) { acc[i] = -INFINITY; acc[i + 1] = 0.0; }
+    std::vector<double> hp((size_t)nstat * G * 2);
+    int rc = 0;
     auto cleanup = [&]() {
         dev_free(d_w); dev_free(d_t); dev_free(d_l); dev_free(d_p); dev_free(d_defer);
         if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
-        coalgpu_destroy(s);
     };
-#define RS_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return fail(COALGPU_ECUDA, m); } } while (0)
+#define RS_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); cleanup(); return fail(_e == cudaErrorMemoryAllocation ? COALGPU_ENOMEM : COALGPU_ECUDA, m); } } while (0)
     RS_OK(dev_alloc((void**)&d_w, chunk * G * sizeof(double)));
     RS_OK(dev_alloc((void**)&d_t, chunk * sizeof(double)));
     RS_OK(dev_alloc((void**)&d_l, chunk * T * sizeof(double)));
@@ -713,13 +712,13 @@ static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, 
     RS_OK(cudaEventCreate(&e0)); RS_OK(cudaEventCreate(&e1));
     RS_OK(cudaEventRecord(e0, 0));
     // A long run starts with a pilot chunk; the reduced type store and the geometry of the rest are sized from what the
-    // pilot histories needed (coalgpu_tune) instead of the input-based estimate. Chunking never changes which histories
-    // are drawn. The pilot drains the device once, about one history's latency: worth it from ~16x what the device holds
-    // in flight (cfg2, 98,304 samples: 413 k histories/s with the pilot, 400 k with the estimate alone).
-    const uint64_t pilot = n_samples >= 16 * (uint64_t)s->grid * (cta_threads(s->group) / s->group) ? 1024 : 0;
+    // pilot histories needed (coalgpu_tune) instead of the input-based estimate. The pilot drains the device once, about
+    // one history's latency: worth it from ~16x what the device holds in flight.
+    const uint64_t pilot = count >= 16 * (uint64_t)s->grid * (cta_threads(s->group) / s->group) ? 1024 : 0;
     uint64_t n = 0;
-    for (uint64_t first = 0; first < n_samples; first += n) {
-        n = (first == 0 && pilot) ? pilot : std::min<uint64_t>(chunk, n_samples - first);
+    for (uint64_t done = 0; done < count; done += n) {
+        const uint64_t first = first0 + done;
+        n = (done == 0 && pilot) ? pilot : std::min<uint64_t>(chunk, count - done);
         if (!use_two_pass(s, n)) {
             rc = sample_pass(s, 0, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, nullptr, 0);
         } else {       // blocking call: look at the deferred count and launch the second pass only when it has work
@@ -738,7 +737,7 @@ static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, 
             if (mm > -INFINITY) acc[i + 1] = acc[i + 1] * std::exp(m1 - mm) + hp[i + 1] * std::exp(m2 - mm);
             acc[i] = mm;
         }
-        if (first == 0 && pilot) {
+        if (done == 0 && pilot) {
             rc = coalgpu_tune(s);
             if (rc) { std::string m = g_err; cleanup(); return fail(rc, m); }
         }
@@ -747,13 +746,33 @@ static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, 
     RS_OK(cudaEventSynchronize(e1));
     float ms = 0; RS_OK(cudaEventElapsedTime(&ms, e0, e1));
 #undef RS_OK
+    if (seconds_device) *seconds_device = ms * 1e-3;
+    if (n_deferred_out) *n_deferred_out = n_deferred_total;
+    cleanup();
+    return 0;
+}
+
+static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, uint32_t Q, uint64_t seed, int device, coalgpu_result* result) {
+    if (!problem || !result) return fail(COALGPU_EINVAL, "null argument");
+    if (n_samples == 0) return fail(COALGPU_EINVAL, "n_samples must be positive");
+    const bool timing = std::getenv("COALGPU_TIMING") != nullptr;
+    auto tick = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = tick();
+    coalgpu_sampler* s = nullptr;
+    int rc = create_impl(problem, Q, device, &s);
+    if (rc) return rc;
+    const double t_created = tick();
+    std::vector<double> acc;
+    double sec = 0; unsigned long long n_deferred_total = 0;
+    rc = sample_range(s, seed, 0, n_samples, acc, &sec, &n_deferred_total);
+    if (rc) { std::string m = g_err; coalgpu_destroy(s); return fail(rc, m); }
     const double t_sampled = tick();
     uint64_t nev = 0, npi = 0, nov = 0;
     rc = coalgpu_counters(s, &nev, &npi, &nov);
     const unsigned long long n_nan = s->n_nan_seen;
     const double t_cnt = tick();
-    if (!rc) rc = coalgpu_finalize(G, T, acc.data(), result);
-    result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = ms * 1e-3;
+    if (!rc) rc = coalgpu_finalize(s->G, s->T, acc.data(), result);
+    result->n_histories = n_samples; result->n_events = nev; result->n_pismc = npi; result->seconds_device = sec;
     std::string m = g_err;
     if (timing && s->fast) {
         unsigned long long h[kCounters] = {0};
@@ -762,9 +781,9 @@ static int run_sampler_impl(const coalgpu_problem* problem, uint64_t n_samples, 
                 s->P_fast.kmax, s->P.kmax, h[8], s->fast_group, s->group, s->fast_grid, n_deferred_total);
     }
     const double t_fin = tick();
-    cleanup();
+    coalgpu_destroy(s);
     if (timing) fprintf(stderr, "coalgpu_run_sampler: create %.2f ms, alloc+sample+reduce %.2f ms (device %.2f ms), counters %.2f ms, finalize %.2f ms, free %.2f ms\n",
-                        1e3 * (t_created - t_begin), 1e3 * (t_sampled - t_created), (double)ms, 1e3 * (t_cnt - t_sampled), 1e3 * (t_fin - t_cnt), 1e3 * (tick() - t_fin));
+                        1e3 * (t_created - t_begin), 1e3 * (t_sampled - t_created), 1e3 * sec, 1e3 * (t_cnt - t_sampled), 1e3 * (t_fin - t_cnt), 1e3 * (tick() - t_fin));
     if (rc) return fail(rc, m);
     if (nov) return fail(COALGPU_EOVERFLOW, "a history outgrew the type-store capacity");
     if (n_nan) return fail(COALGPU_ENAN, "a history weight is not a number (target grid / driving values out of range?)");
@@ -1044,3 +1063,5 @@ int coalgpu_pismc_classes(coalgpu_sampler* s, int64_t nq, const uint8_t* gamma, 
 }
 
 }  // extern "C"
+
+#include "coal_multi.cu"

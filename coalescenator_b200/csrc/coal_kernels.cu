@@ -1108,4 +1108,12 @@ __global__ void __launch_bounds__(128) bilinear_rows_kernel(const BilinearArgs A
     }
 }
 
+// Multi-GPU combine (coal_multi.cu), between the two NCCL allreduces: sums of one device to the common maximum: sm[i] *= exp(mx[i] - gmx[i]) (0 for a device without samples)
+__global__ void lse_rescale_kernel(int n, const double* __restrict__ mx, const double* __restrict__ gmx, double* __restrict__ sm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = mx[i], g = gmx[i];
+    sm[i] = (m == -INFINITY || g == -INFINITY) ? 0.0 : sm[i] * exp(m - g);
+}
+
 }  // namespace coalgpu

@@ -38,6 +38,7 @@ struct Options {
     double generation_time = 0, mutation_driving = 2.5e-5, scale_driving = 1000, rho_driving = 5e-5;
     bool have_coords = false, have_generation_time = false, ess = false, summary = false;
     int device = 0, gpus = 1;
+    bool shard_samples = false;   // --shard-samples: with --gpus N, split the importance samples of every pair over the GPUs (NCCL combine)
     std::string dump_dir;
 };
 
@@ -54,7 +55,7 @@ void usage() {
               << "  --coordinate-list [l-r],... | bp1,bp2   --loci-size N (1)\n"
               << "  -i [ --mc-samples ] N (500000)  --mutation-list L  --mutation-driving X (2.5e-5)  --scale-list L  --scale-driving X (1000)\n"
               << "  --rho-list L  --rho-driving X (5e-5)  --min-comp-dist N (1)  --max-comp-dist N (400)\n"
-              << "  --dump-problems DIR  --ess  --summary\n";
+              << "  --dump-problems DIR  --ess  --summary  --shard-samples (with --gpus N: every pair's samples over all GPUs, NCCL combine)\n";
 }
 
 Options parse(int argc, char** argv) {
@@ -69,6 +70,7 @@ Options parse(int argc, char** argv) {
         if (k == "--help") { usage(); exit(1); }
         if (k == "--ess") { o.ess = true; continue; }
         if (k == "--summary") { o.summary = true; continue; }
+        if (k == "--shard-samples") { o.shard_samples = true; continue; }
         if (v.empty() && eq == std::string::npos) { if (i + 1 >= argc) throw std::runtime_error("the required argument for option '" + k + "' is missing"); v = argv[++i]; }
         if (k == "--num-threads") o.num_threads = (unsigned)std::stoul(v);
         else if (k == "--seed") o.seed = (unsigned)std::stoul(v);
@@ -162,6 +164,10 @@ int main(int argc, char** argv) {
             throw std::runtime_error("driving values and generation time must be positive");   // :147-150
 
         const std::vector<double> mu_list = number_list(o.mutation_list), lambda_list = number_list(o.scale_list), rho_list = number_list(o.rho_list);
+        // the reference asserts mu >= 0, lambda > 0, rho >= 0 (main.cpp:169,175,181)
+        for (double v : mu_list) if (!(v >= 0)) throw std::runtime_error("--mutation-list: values must be >= 0");
+        for (double v : lambda_list) if (!(v > 0)) throw std::runtime_error("--scale-list: values must be > 0");
+        for (double v : rho_list) if (!(v >= 0)) throw std::runtime_error("--rho-list: values must be >= 0");
         if (loci.size() == 1) { std::cout << "\n[" << now() << "] Only a single loci left no remcobination estimation possible - exiting!" << std::endl; return 0; }   // :202-207
 
         struct Pair { size_t i, j; unsigned dist; };
@@ -237,6 +243,18 @@ int main(int argc, char** argv) {
             if (o.gpus <= 1) {
                 const int rc = coalgpu_run_sampler_batch((int)probs.size(), probs.data(), o.mc_samples, 16, o.seed, o.device, results.data());   // replaces :281-283
                 if (rc) throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+            } else if (probs.size() < (size_t)o.gpus || o.shard_samples || (double)o.mc_samples * (double)(G + probs[0].T + 1) * 8.0 > 256.0 * 1048576.0) {
+                // Fewer pairs than GPUs, or so many importance samples per pair that one pair fills a GPU for a long time
+                // (the reference's default is 500,000, main.cpp:75): the SAMPLES of each pair are sharded over the GPUs --
+                // the thread fan-out of ImportanceSampler.cpp:125-139 with GPUs in the place of threads, one NCCL
+                // allreduce of the (max, sum) pairs per locus pair (coalgpu_run_sampler_multi). Same histories as one
+                // GPU would draw, so the files agree with the single-GPU run up to the rounding of the merge.
+                std::vector<int> devs;
+                for (int d = 0; d < o.gpus; d++) devs.push_back(o.device + d);
+                for (size_t q = 0; q < probs.size(); q++)
+                    if (coalgpu_run_sampler_multi(&probs[q], o.mc_samples, 16, o.seed, o.gpus, devs.data(), &results[q]))
+                        throw std::runtime_error(std::string("coalgpu: ") + coalgpu_last_error());
+                coalgpu_multi_shutdown();
             } else {
                 // pairs are independent: device d takes pairs d, d+gpus, ... and runs its own batch; a pair's histories
                 // depend on (seed, index) only, so the output does not depend on the number of GPUs

@@ -55,7 +55,9 @@ _lib = None
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
            "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
-           "coalgpu_capacity_stats", "coalgpu_tune", "coalgpu_set_emission_mode"]
+           "coalgpu_capacity_stats", "coalgpu_tune", "coalgpu_set_emission_mode",
+           "coalgpu_comm_init", "coalgpu_comm_finalize", "coalgpu_comm_size", "coalgpu_run_sampler_comm",
+           "coalgpu_run_sampler_multi", "coalgpu_multi_shutdown", "coalgpu_nccl_calls"]
 
 
 def load_library():
@@ -85,6 +87,14 @@ def load_library():
         L.coalgpu_tune.argtypes = [C.c_void_p]
         L.coalgpu_set_emission_mode.argtypes = [C.c_int]
         L.coalgpu_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.coalgpu_comm_init.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.coalgpu_comm_finalize.argtypes = [C.c_void_p]
+        L.coalgpu_comm_finalize.restype = None
+        L.coalgpu_comm_size.argtypes = [C.c_void_p]
+        L.coalgpu_run_sampler_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p]
+        L.coalgpu_run_sampler_multi.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
+        L.coalgpu_multi_shutdown.restype = None
+        L.coalgpu_nccl_calls.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -194,6 +204,25 @@ class ImportanceSampler:
         _check(L.coalgpu_run_sampler_batch(n, probs, int(num_iterations), int(quadrature_points), int(seed), int(device), ress))
         return [_to_output(p, a, r) for p, a, r in zip(samples, arrs, ress)]
 
+
+    def run_sampler_multi(self, sample: Problem, num_iterations: int, devices=None, quadrature_points: int = 16,
+                          seed: int = 0) -> SamplerOutput:
+        """runSampler with the importance samples of ONE locus pair sharded over several GPUs of this process
+        (coalgpu_run_sampler_multi: one host thread per device, NCCL allreduce of the (max, sum) pairs inside the
+        library). `devices`: list of CUDA device indices (default: all visible). Same histories, hence the same
+        estimates up to merge rounding, as run_sampler(num_iterations, seed) on one device -- the thread fan-out and
+        merge of ImportanceSampler.cpp:110-145 with GPUs in the place of threads."""
+        L = load_library()
+        if devices is None:
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        dv = np.asarray(list(devices), dtype=np.int32)
+        pk = _PackedProblem(sample)
+        arrs = _result_arrays(sample)
+        res = _CResult(_dp(arrs[0]), _dp(arrs[1]), _dp(arrs[2]), _dp(arrs[3]), _dp(arrs[4]), 0, 0, 0, 0.0)
+        _check(L.coalgpu_run_sampler_multi(C.byref(pk.struct), int(num_iterations), int(quadrature_points), int(seed),
+                                           len(dv), dv.ctypes.data_as(C.c_void_p), C.byref(res)))
+        return _to_output(sample, arrs, res)
 
     def run_sampler_driving_grid(self, sample: Problem, num_iterations: int, quadrature_points: int = 16, seed: int = 0,
                                  device: int = 0) -> SamplerOutput:
@@ -347,3 +376,8 @@ def fp64_peak_tflops(device: int = 0) -> float:
 
 def launch_count() -> int:
     return int(load_library().coalgpu_launch_count())
+
+
+def nccl_calls() -> int:
+    """NCCL collectives issued by libcoalgpu.so itself (coalgpu_run_sampler_multi / _comm) in this process."""
+    return int(load_library().coalgpu_nccl_calls())

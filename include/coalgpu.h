@@ -7,7 +7,8 @@
  *      locus pair at main.cpp:281-283, results read at main.cpp:285-306)
  * `coalgpu_run_sampler` replaces exactly that call. Everything else here is the same work split
  * into stages so a caller can keep histories on the device, shard them over GPUs and combine the
- * per-GPU partial sums itself (coalescenator_b200/distributed.py does it with one NCCL exchange).
+ * per-GPU partial sums itself (coalescenator_b200/distributed.py does it with one NCCL exchange between
+ * processes; coalgpu_run_sampler_multi does it inside this library for the GPUs of one process).
  *
  * Plain C types only. All functions return 0 on success or a negative COALGPU_E* code and never
  * abort; coalgpu_last_error() describes the last failure on the calling thread. The library is
@@ -29,6 +30,7 @@ extern "C" {
 #define COALGPU_ENOMEM   (-4)
 #define COALGPU_EOVERFLOW (-5)  /* a history outgrew the per-history state capacity  */
 #define COALGPU_ENAN     (-6)   /* a history weight came out as NaN (never dropped silently) */
+#define COALGPU_ENCCL    (-7)   /* NCCL missing or an NCCL call failed (multi-GPU entry points only) */
 
 #define COALGPU_GAMMA_A 0       /* lineage ancestral at locus A only  (i,*) */
 #define COALGPU_GAMMA_B 1       /* lineage ancestral at locus B only  (*,j) */
@@ -97,6 +99,31 @@ int coalgpu_run_sampler(const coalgpu_problem* problem, uint64_t n_samples, uint
 int coalgpu_run_sampler_batch(int32_t n_problems, const coalgpu_problem* problems, uint64_t n_samples,
                               uint32_t quadrature_points, uint64_t seed, int device, coalgpu_result* results);
 
+/* ---- one locus pair over several GPUs of one box (sample sharding) --------------------------------
+ * The reference fans num_iterations out over std::threads and merges their SamplerOutputs (ImportanceSampler.cpp:
+ * 110-145, SamplerOutput.cpp:97-133). Here every device draws the contiguous index range
+ *     first_r = r*floor(n/R) + min(r, n mod R),  count_r = floor(n/R) + (r < n mod R)
+ * of the SAME histories coalgpu_run_sampler(n_samples, seed) would draw on one device (a history is a pure function
+ * of (seed, index)), reduces it on its device, and the per-device (max, sum) pairs are combined over NVLink with NCCL:
+ * allreduce(MAX) of the maxima, local rescale, allreduce(SUM). Results equal the single-device call up to the
+ * rounding of that merge (1e-13 relative; tests/test_gpu_distributed.py).
+ *
+ * coalgpu_comm_init / coalgpu_comm_finalize own the NCCL communicator (ncclCommInitAll over `devices`; NULL = devices
+ * 0..n_devices-1) and one stream per device; a communicator serves one call at a time. NCCL is bound at run time
+ * (libnccl.so.2); with n_devices == 1 it is never loaded. coalgpu_run_sampler_multi is the same call with a
+ * process-wide communicator per device list, created on first use and released by coalgpu_multi_shutdown. */
+typedef struct coalgpu_comm coalgpu_comm;
+int coalgpu_comm_init(int32_t n_devices, const int32_t* devices, coalgpu_comm** out);
+void coalgpu_comm_finalize(coalgpu_comm* comm);
+int coalgpu_comm_size(const coalgpu_comm* comm);
+int coalgpu_run_sampler_comm(coalgpu_comm* comm, const coalgpu_problem* problem, uint64_t n_samples,
+                             uint32_t quadrature_points, uint64_t seed, coalgpu_result* result);
+int coalgpu_run_sampler_multi(const coalgpu_problem* problem, uint64_t n_samples, uint32_t quadrature_points,
+                              uint64_t seed, int32_t n_devices, const int32_t* devices, coalgpu_result* result);
+void coalgpu_multi_shutdown(void);
+/* NCCL collectives issued by this library on the calling process so far (one per device and allreduce). */
+uint64_t coalgpu_nccl_calls(void);
+
 /* Emission-table mode of the samplers created AFTER the call (process-wide, thread-safe):
  *   COALGPU_EMISSION_REFERENCE (default): ConditionalSamplingHMM.cpp:184-226 in the reference's operation order --
  *       tables bit-identical to the reference's; entries below ~1e-13 are rounding noise / the epsilon clamp.
@@ -117,7 +144,11 @@ int coalgpu_set_emission_mode(int mode);
 int coalgpu_create(const coalgpu_problem* problem, uint32_t quadrature_points, int device, coalgpu_sampler** out);
 void coalgpu_destroy(coalgpu_sampler* s);
 
-/* Draw histories [first, first+n) on the sampler's device, asynchronously on `stream`
+/* One sampler serves ONE stream at a time: coalgpu_sample resets the sampler's device counters and work list per call,
+ * and its buffers are released in the order of the stream it was last used on; use one sampler per stream (or order the
+ * streams with events). Samplers of different locus pairs are independent.
+ *
+ * Draw histories [first, first+n) on the sampler's device, asynchronously on `stream`
  * (a cudaStream_t cast to void*, NULL = default stream). Device outputs (any may be NULL):
  *   d_weights[n*G], d_tmrca[n], d_lineages[n*T], d_nevents[n] (uint32)
  * Optional event trace for the first n_trace histories of this call: d_events[n_trace*max_events],

@@ -9,7 +9,7 @@ from conftest import ROOT
 
 
 def test_reference_arm_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-per-pair", "4"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-per-thread", "1", "--ref-per-thread-small", "1", "--ref-pairs", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -28,5 +28,10 @@ def test_bench_workload_is_deterministic():
     import bench
     a = [p.dumps() for p in bench.bench_problems()]
     b = [p.dumps() for p in bench.bench_problems()]
-    assert a == b and len(a) == len(bench.BENCH_PAIRS)
+    assert a == b and len(a) == 24 == len(bench.config_block("cfg2")["pairs"])
     assert all(p.T == 5 and p.n_lineages() == 50 for p in bench.bench_problems())
+    # the pair sample is seeded, not hand-picked, and both arms print the same config object
+    import random
+    assert bench.config_block("cfg2")["pairs"] == sorted(random.Random(bench.PAIR_SEED).sample(range(len(bench.bench_pairs("cfg2")[2])), 24))
+    g3 = bench.bench_problems("cfg3")
+    assert len(g3) == 32 and all(p.G == 1024 for p in g3)

@@ -199,3 +199,29 @@ def test_host_driver_two_gpus_same_files(tmp_path):
         assert r.returncode == 0, r.stderr + r.stdout
         outs.append((open(prefix + "_pairwise_loglikelihood.txt").read(), open(prefix + "_composite_loglikelihood.txt").read()))
     assert outs[0] == outs[1] and outs[0][0].count("\n") > 4
+
+
+@pytest.mark.gpu
+def test_host_driver_shard_samples_over_two_gpus(tmp_path):
+    """--gpus 2 --shard-samples: the importance samples of every pair are split over the two devices inside
+    libcoalgpu.so (coalgpu_run_sampler_multi, NCCL combine). Same histories as the single-GPU run, so every printed
+    value agrees to the rounding of the merge (the files print 6 significant digits)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from coalescenator_b200 import build as B
+    B.build_cuda()
+    build_host()
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    common = ["-f", fl, "-t", tl, "-v", vl, "-g", "1.5", "--loci-size", "30", "--mutation-list", "1e-5,2.5e-5", "--scale-list", "1000",
+              "--rho-list", "5e-5,1e-4", "-s", "77", "-i", "801", "--max-comp-dist", "60"]
+    rows = []
+    for extra in (["--gpus", "1"], ["--gpus", "2", "--shard-samples"]):
+        prefix = str(tmp_path / ("run" + str(len(rows))))
+        r = subprocess.run([HOST] + common + ["--output-file-prefix", prefix] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        rows.append([l.split("\t") for l in open(prefix + "_pairwise_loglikelihood.txt").read().splitlines()])
+    assert len(rows[0]) == len(rows[1]) > 4 and rows[0][0] == rows[1][0]
+    for a, b in zip(rows[0][1:], rows[1][1:]):
+        assert a[:5] == b[:5]
+        np.testing.assert_allclose([float(x) for x in a[5:]], [float(x) for x in b[5:]], rtol=1e-5)
