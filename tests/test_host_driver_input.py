@@ -224,4 +224,5 @@ def test_host_driver_shard_samples_over_two_gpus(tmp_path):
     assert len(rows[0]) == len(rows[1]) > 4 and rows[0][0] == rows[1][0]
     for a, b in zip(rows[0][1:], rows[1][1:]):
         assert a[:5] == b[:5]
-        np.testing.assert_allclose([float(x) for x in a[5:]], [float(x) for x in b[5:]], rtol=1e-5)
+        num = lambda cols: [float(x) for c in cols for x in c.split(",")]      # lineages_remaining is a comma-separated list
+        np.testing.assert_allclose(num(a[5:]), num(b[5:]), rtol=1e-5)
