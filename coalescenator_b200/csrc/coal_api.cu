@@ -74,6 +74,12 @@ int ensure_kernel_attributes(int device) {
         CU_OK(cudaFuncGetAttributes(&fa, fn));            // static shared memory (problem constants) counts against the limit
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     }
+    for (int NH : {16, 32}) for (int narrow = 0; narrow < 2; narrow++) {
+        const void* fn = (const void*)history_lockstep_select(NH, narrow != 0);
+        cudaFuncAttributes fa;
+        CU_OK(cudaFuncGetAttributes(&fa, fn));
+        CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    }
     done.fetch_or(bit);
     return 0;
 }
@@ -91,6 +97,8 @@ struct coalgpu_sampler {
     size_t block_partials_cap = 0;
     double* d_full_rows = nullptr;    // reference-layout rows on the device (device table builder only; owned through allocs)
     cudaStream_t last_stream = 0;     // stream of the most recent launch of this sampler: its buffers are freed in that stream's order
+    // lockstep form of K1 (coal_lockstep.cuh): `group` then holds NH, the histories per CTA (16 or 32), CTAs have 4 * NH threads
+    bool ls = false, fast_ls = false, wide_ls = false;
     int warp_bytes = 0, grid = 0, group = 32;   // warp_bytes = shared memory per history in flight; group = lanes per history of the full-store geometry (16 or 32; the reduced-store first pass may use 8)
     size_t smem_bytes = 0;
     // reduced-capacity first pass (see finish_device): same problem with a smaller type store
@@ -289,8 +297,35 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
 // per SM, the first pass uses it and defers the rare history that outgrows it to a second pass with the full store;
 // a history's draws depend on (seed, index) only, so the results do not depend on the scheme. `peak` > 0 (coalgpu_tune)
 // is the largest store any history of this sampler has needed so far: the reduced store is then sized from it.
-struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; };
+struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; bool ls = false; };
+// threads per CTA / histories per CTA of a geometry: the group form packs cta_threads(W) / W groups of W lanes, the
+// lockstep form advances NH = `group` histories with 4 * NH threads
+inline int geo_threads(int group, bool ls) { return ls ? 4 * group : cta_threads(group); }
+inline int geo_hist_per_cta(int group, bool ls) { return ls ? group : cta_threads(group) / group; }
+// Which form of K1: the lockstep form (default) or the group form (COALGPU_KERNEL=group, or a forced group width
+// COALGPU_GROUP=8|16|32, which the parity tests of the group form use).
+bool want_lockstep() {
+    if (const char* g = std::getenv("COALGPU_GROUP")) { const int W = std::atoi(g); if (W == 8 || W == 16 || W == 32) return false; }
+    if (const char* k = std::getenv("COALGPU_KERNEL")) return std::string(k) != "group";
+    return true;
+}
 Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
+    if (want_lockstep()) {
+        int forced_nh = 0;
+        if (const char* g = std::getenv("COALGPU_LOCKSTEP_NH")) { const int v = std::atoi(g); if (v == 16 || v == 32) forced_nh = v; }
+        auto eval = [&](int NH) {
+            Geometry g; g.group = NH; g.ls = true;
+            g.smem = history_lockstep_bytes(NH, kmax, pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32);
+            if (g.smem > 227 * 1024) return Geometry();
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_lockstep_select(NH, P.Ltot <= 32), 4 * NH, g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
+            g.per_sm = g.occ * NH;
+            return g;
+        };
+        if (forced_nh) return eval(forced_nh);
+        const Geometry g16 = eval(16), g32 = eval(32);
+        if (g16.per_sm > 0 || g32.per_sm > 0) return g32.per_sm > g16.per_sm ? g32 : g16;
+        // neither fits (type store beyond ~200 KB of shared memory per CTA): fall through to the group form
+    }
     int forced_w = 0;
     if (const char* g = std::getenv("COALGPU_GROUP")) { const int W = std::atoi(g); if (W == 8 || W == 16 || W == 32) forced_w = W; }
     auto eval = [&](int W) {
@@ -303,7 +338,7 @@ Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
     };
     if (forced_w) return eval(forced_w);
     Geometry best = eval(32);
-    if (P.Ltot + 1 <= 16) { const Geometry g16 = eval(16); if (g16.per_sm > best.per_sm) best = g16; }
+    { const Geometry g16 = eval(16); if (g16.per_sm > best.per_sm) best = g16; }
     if (allow8) { const Geometry g8 = eval(8); if (10 * g8.per_sm >= 13 * best.per_sm) best = g8; }
     return best;
 }
@@ -312,8 +347,8 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     DevProblem& P = s->P;
     const Geometry full = geometry_for(P, P.kmax, P.pvmax, false);
     if (full.per_sm < 1) return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA");
-    s->group = full.group; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
-    s->warp_bytes = (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group, P.stage_doubles);
+    s->group = full.group; s->ls = full.ls; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
+    s->warp_bytes = full.ls ? 0 : (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group, P.stage_doubles);
     P.warp_bytes = s->warp_bytes;
     s->fast = false; s->fast_forced = false; s->wide = false;
 
@@ -334,7 +369,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
         allow8 = need <= 44;
         for (int kf : {256, 128, 64}) if (kf > cand[0] && kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // larger stores that still raise the occupancy
     }
-    auto pick = [&](bool with8, DevProblem& Pout, int& grid, int& group, size_t& smem) -> bool {
+    auto pick = [&](bool with8, DevProblem& Pout, int& grid, int& group, size_t& smem, bool& ls) -> bool {
         Geometry bestf = full; int best_k = 0;
         for (int kf : cand) {
             kf = std::min(kf, P.kmax);                               // kf == kmax: same store, possibly narrower groups
@@ -345,13 +380,13 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
         Pout = P;
         Pout.kmax = best_k;
         Pout.pvmax = pv_for(best_k);
-        group = bestf.group; smem = bestf.smem; grid = s->sm_count * bestf.occ;
-        Pout.warp_bytes = (int)history_group_bytes(best_k, Pout.pvmax, P.Ltot, bestf.group, P.stage_doubles);
+        group = bestf.group; smem = bestf.smem; grid = s->sm_count * bestf.occ; ls = bestf.ls;
+        Pout.warp_bytes = bestf.ls ? 0 : (int)history_group_bytes(best_k, Pout.pvmax, P.Ltot, bestf.group, P.stage_doubles);
         return true;
     };
-    s->fast = pick(allow8, s->P_fast, s->fast_grid, s->fast_group, s->fast_smem);
+    s->fast = pick(allow8, s->P_fast, s->fast_grid, s->fast_group, s->fast_smem, s->fast_ls);
     s->fast_forced = s->fast && forced > 0;
-    s->wide = pick(false, s->P_wide, s->wide_grid, s->wide_group, s->wide_smem);
+    s->wide = pick(false, s->P_wide, s->wide_grid, s->wide_group, s->wide_smem, s->wide_ls);
     return 0;
 }
 
@@ -526,14 +561,15 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
     if (pass == 2) { a.list = d_defer; a.list_count = s->d_counters + 6; }
     const DevProblem& P = fast ? s->P_fast : wide ? s->P_wide : s->P;
     const int group = fast ? s->fast_group : wide ? s->wide_group : s->group;
+    const bool ls = fast ? s->fast_ls : wide ? s->wide_ls : s->ls;
     const size_t smem = fast ? s->fast_smem : wide ? s->wide_smem : s->smem_bytes;
     int grid = fast ? s->fast_grid : wide ? s->wide_grid : s->grid;
-    const int groups_per_cta = cta_threads(group) / group;
+    const int groups_per_cta = geo_hist_per_cta(group, ls);
     const unsigned long long todo = pass == 2 ? n_listed : n;
     const unsigned long long ctas_needed = (todo + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)std::max<unsigned long long>(ctas_needed, 1);
-    history_kernel_fn kfn = history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
-    kfn<<<grid, cta_threads(group), smem, st>>>(P, a);
+    history_kernel_fn kfn = ls ? history_lockstep_select(group, P.Ltot <= 32) : history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+    kfn<<<grid, geo_threads(group, ls), smem, st>>>(P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
     s->last_stream = st;
@@ -543,7 +579,7 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
 // The reduced-store first pass pays off when the launch can fill the device; a launch smaller than what the full-store
 // geometry keeps in flight is latency bound and runs single-pass with the wider groups.
 static bool use_two_pass(const coalgpu_sampler* s, uint64_t n) {
-    return s->fast && (s->fast_forced || n >= (uint64_t)s->grid * (cta_threads(s->group) / s->group));
+    return s->fast && (s->fast_forced || n >= (uint64_t)s->grid * geo_hist_per_cta(s->group, s->ls));
 }
 
 int coalgpu_sample(coalgpu_sampler* s, uint64_t seed, uint64_t first, uint64_t n, void* stream,
@@ -714,7 +750,7 @@ static int sample_range(coalgpu_sampler* s, uint64_t seed, uint64_t first0, uint
     // A long run starts with a pilot chunk; the reduced type store and the geometry of the rest are sized from what the
     // pilot histories needed (coalgpu_tune) instead of the input-based estimate. The pilot drains the device once, about
     // one history's latency: worth it from ~16x what the device holds in flight.
-    const uint64_t pilot = count >= 16 * (uint64_t)s->grid * (cta_threads(s->group) / s->group) ? 1024 : 0;
+    const uint64_t pilot = count >= 16 * (uint64_t)s->grid * geo_hist_per_cta(s->group, s->ls) ? 1024 : 0;
     uint64_t n = 0;
     for (uint64_t done = 0; done < count; done += n) {
         const uint64_t first = first0 + done;

@@ -864,6 +864,8 @@ history_kernel_fn history_kernel_select(int W, bool narrow) {
     return W == 8 ? history_kernel<8, false> : W == 16 ? history_kernel<16, false> : history_kernel<32, false>;
 }
 
+#include "coal_lockstep.cuh"
+
 // K2: batched pi_SMC from class vectors (parity seam for ConditionalSamplingHMM::piSMC): one query per thread, through
 // the same table rows and the same arithmetic (coal_math.h) as the history kernel. The class list of a thread sits in
 // its own shared-memory column.

@@ -1,0 +1,770 @@
+// K1, lockstep form: a CTA of NT = 4 * NH threads advances NH coalescent histories in lockstep, one "step" (an injection,
+// a collection boundary, or one backward event of ProposalEngine.cpp:134-566) per history and iteration, in phases
+// separated by CTA barriers:
+//
+//   S  (serial, ONE THREAD PER HISTORY: the first NH threads of the CTA)  finish the event of the previous step -- assemble
+//      the candidate probabilities, draw the move (sampleFromVector, ProposalEngine.cpp:568-583), apply it to the type
+//      store, book the target-density statistics --, then fetch / inject / choose the next lineage and waiting time
+//      (TypeContainer::sampleType, TypeContainer.cpp:641-745), handle a collection boundary, remove the chosen lineage,
+//      list the coalescence partners, issue the TMA copies of the table rows the event's queries read, and publish the
+//      event descriptor;
+//   G  (all threads, only in steps where some history closed an epoch or ended) the per-grid-point target density of the
+//      epoch from its sufficient statistics (coal_math.h: epoch_log_density), lanes over grid points;
+//   Q1 (all threads, ONE LANE PER (history, one-locus query)) the flattened list of all one-locus conditional sampling
+//      probabilities of the CTA's events (ConditionalSamplingHMM.cpp:332-370 as a dot product);
+//   Q2 (all threads, ONE LANE PER (history, two-locus query)) class list of the query (TypeContainer::getDifferences with
+//      the dA+dB collapse, TypeContainer.cpp:802-886) + its pi_SMC as a bilinear form (coal_math.h).
+//
+// Why: the group form of the kernel (coal_kernels.cu: a group of 8-32 lanes per history, every group its own control
+// flow) keeps 40-64 independent instruction streams per SM wandering through ~70 KB of code -- ncu: 3.9 stalled-for-
+// instruction-fetch warps per issue at 16 warps/SM, 15 of 32 lanes active (profiles/r2_v7_*). Here a warp instruction
+// serves 16-32 histories in the serial phase (one instruction stream per CTA and phase, each phase a small loop), and
+// the query phases run one query per lane over the queries of ALL histories of the CTA, so lanes are full whatever the
+// number of candidate moves of one event is. The type store is laid out slot-major / history-minor ([slot][NH]): in the
+// serial phase lane h touches bank h, in the query phases lanes of different histories touch different banks and lanes
+// of one history broadcast. Results are those of the group form: same canonical slot order, same draws, partial sums
+// of the categorical draws in plain index order (exactly the oracle's order).
+#pragma once
+
+namespace {
+
+constexpr int kLsFlagAccum = 1;    // snapshot: add the epoch's target density to the history's weights
+constexpr int kLsFlagFinal = 2;    //           ... and the final constant: the history ends
+constexpr int kLsFlagAbort = 4;    //           the history outgrew the type store: weights = NaN
+constexpr int kLsFlagFirst = 8;    //           first write of this history's weights (no read of the old value)
+
+struct LsDesc {                    // event descriptor of one history and step (written in S, read in Q1 / Q2 / next S)
+    unsigned long long xw;         // chosen haplotype
+    const double* crow;            // table row of the two-locus queries (shared-memory staging buffer or the table in HBM)
+    const double* row_m1;          // rows of the one-locus queries, biased so that (+ off_wEA / off_wEB) lands on the weight vectors
+    const double* row_alt;
+    double dtheta_own;             // A/B chosen: driving theta * multiplicity of the chosen type
+    double mA1, mA2, mB1, mB2;     // results of one-locus queries 0 and 1 on the two rows (A/B chosen: mA1 = pi0)
+    double pi0c;                   // C chosen: pi(x | H')
+    double rate, wait, hap_num, hap_den, nn, aa, dtheta_e, drho_e;
+    int valid, xg, ns, n, np, nm, nq, Lx, offb, pg;
+    int Ac, Bc, Cc;
+    unsigned int own, ownC, Cij, Ci, Cj, Ai, Bj, cn, nc_alt, tma_parity;
+};
+
+struct LsSnap {                    // what the G phase needs of a history that closed an epoch / ended in this step
+    EpochStats st;
+    double fin;
+    unsigned long long hidx;
+    int e, flags;
+};
+
+struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, total; };
+
+__host__ __device__ inline LsLayout ls_layout(int NH, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+    LsLayout L;
+    unsigned int o = 0;
+    auto place = [&o](size_t bytes) { const unsigned int at = o; o += (unsigned int)((bytes + 15) & ~(size_t)15); return at; };
+    const int NT = 4 * NH, nsum = Ltot + 2;
+    L.rowbuf = place((size_t)NH * stage_doubles * 8);
+    L.wbuf = place((size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8);
+    L.mbar = place((size_t)NH * 8);
+    L.pv = place((size_t)NH * pvmax * 8);
+    L.aux = place((size_t)NH * kmax * 8);
+    L.words = place((size_t)NH * kmax * (narrow ? 4 : 8));
+    L.cg = place((size_t)NH * kmax * 4);
+    L.xc = place((size_t)NH * kmax * 4);
+    L.plist = place((size_t)NH * kmax * 2);
+    L.scratch = place((size_t)NT * nsum * 4);
+    L.desc = place((size_t)NH * sizeof(LsDesc));
+    L.snap = place((size_t)NH * sizeof(LsSnap));
+    L.pre1 = place((size_t)(NH + 1) * 4);
+    L.pre2 = place((size_t)(NH + 1) * 4);
+    L.total = o;
+    return L;
+}
+
+#ifdef COAL_DEBUG_BOUNDS
+#define LS_ASSERT(cond) do { if (!(cond)) { printf("coalgpu lockstep: %s failed at line %d (block %d thread %d)\n", #cond, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define LS_ASSERT(cond) do { } while (0)
+#endif
+
+template <int NH, bool N32>
+struct LsCta {
+    typedef WordOps<N32> WO;
+    typedef typename WO::T WordT;
+    static constexpr int NT = 4 * NH;
+    WordT* words; unsigned int* cg; unsigned int* xc; unsigned short* plist; double* pv; double* aux;
+    double* rowbuf; double* wbuf; unsigned long long* mbar; unsigned int* scratch; LsDesc* desc; LsSnap* snap; int* pre1; int* pre2;
+
+    __device__ __forceinline__ void bind() {
+        const LsLayout L = ls_layout(NH, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32);
+        unsigned char* b = smem_dyn;
+        words = reinterpret_cast<WordT*>(b + L.words); cg = reinterpret_cast<unsigned int*>(b + L.cg); xc = reinterpret_cast<unsigned int*>(b + L.xc);
+        plist = reinterpret_cast<unsigned short*>(b + L.plist); pv = reinterpret_cast<double*>(b + L.pv); aux = reinterpret_cast<double*>(b + L.aux);
+        rowbuf = reinterpret_cast<double*>(b + L.rowbuf); wbuf = reinterpret_cast<double*>(b + L.wbuf); mbar = reinterpret_cast<unsigned long long*>(b + L.mbar);
+        scratch = reinterpret_cast<unsigned int*>(b + L.scratch); desc = reinterpret_cast<LsDesc*>(b + L.desc); snap = reinterpret_cast<LsSnap*>(b + L.snap);
+        pre1 = reinterpret_cast<int*>(b + L.pre1); pre2 = reinterpret_cast<int*>(b + L.pre2);
+    }
+    // slot-major / history-minor: element j of history h
+    static __device__ __forceinline__ int at(int j, int h) { return j * NH + h; }
+};
+
+// Per-history state of the serial phase: lives in the registers of the history's thread across steps.
+struct LsHist {
+    unsigned long long h;
+    PhiloxStream rng;
+    EpochStats st;
+    LogProd qprod, evprod;
+    double qsum, consts, tsum;
+    int nslots, nA, nB, nC, inj_lo, inj_hi, e, tset, peak;
+    unsigned int nev, npi, ncq, tma_phase;
+    bool have, done, injecting, post, tracing, overflow, wfirst, pending;
+};
+
+// TypeContainer::addType / removeType (TypeContainer.cpp:409-522) on the slot array of history h, serial form of
+// adjust_core: the multiplicity of type (g, w) changes by delta, the cross counts of every related slot follow; a type
+// that is not stored yet is appended; a slot whose count reaches 0 stays until ls_commit. Returns the slot (| kAppended
+// when a slot was appended) or -1 when the store is full. Out of line (three call sites), so it takes scalars only:
+// a reference to the caller's register state would force that state into local memory.
+template <int NH, bool N32>
+__device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long long w64, int delta) {
+    typedef LsCta<NH, N32> C;
+    typedef typename C::WO WO;
+    C m; m.bind();
+    const typename WO::T w = WO::narrow(w64), maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
+    const typename WO::T wa = w & maskA, wb = w & maskB;
+    int found = -1;
+    unsigned int newxc = 0;
+#pragma unroll 1
+    for (int j = 0; j < ns; j++) {
+        const typename WO::T wj = m.words[C::at(j, h)];
+        const unsigned int cgj = m.cg[C::at(j, h)];
+        const int gj = (int)(cgj >> 30);
+        const unsigned int cj = cgj & kCntMask;
+        if (gj == g && wj == w) found = j;
+        if (g == GA) {
+            if (gj == GC && (wj & maskA) == w) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj; }
+        } else if (g == GB) {
+            if (gj == GC && (wj & maskB) == w) { m.xc[C::at(j, h)] += (unsigned int)(delta * 65536); newxc += cj; }
+        } else {
+            if (gj == GA && wj == wa) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj; }
+            if (gj == GB && wj == wb) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj << 16; }
+        }
+    }
+    int ret = found;
+    if (found < 0) {
+        if (ns >= sP.kmax) return -1;
+        found = ns;
+        m.words[C::at(found, h)] = w; m.cg[C::at(found, h)] = (unsigned int)g << 30; m.xc[C::at(found, h)] = newxc;
+        ret = found | kAppended;
+    }
+    m.cg[C::at(found, h)] += (unsigned int)delta;
+    return ret;
+}
+template <int NH, bool N32>
+__device__ __forceinline__ int ls_adjust(const LsCta<NH, N32>&, int h, LsHist& s, int g, unsigned long long w64, int delta) {
+    int r = ls_adjust_core<NH, N32>(h, s.nslots, g, w64, delta);
+    if (r < 0) { s.overflow = true; return -1; }
+    if (r & kAppended) { s.nslots++; r &= ~kAppended; }
+    if (g == GA) s.nA += delta; else if (g == GB) s.nB += delta; else s.nC += delta;
+    return r;
+}
+
+// Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot (the canonical order
+// rule shared with the oracle's CANONICAL mode). Scanning downwards visits the empty slots in that order,
+// and everything above the scan position is already non-empty.
+template <int NH, bool N32>
+__device__ __forceinline__ void ls_commit(const LsCta<NH, N32>& m, int h, LsHist& s) {
+    typedef LsCta<NH, N32> C;
+    int ns = s.nslots;
+#pragma unroll 1
+    for (int j = ns - 1; j >= 0; j--) {
+        if ((m.cg[C::at(j, h)] & kCntMask) == 0) {
+            const int last = ns - 1;
+            if (j != last) {
+                m.words[C::at(j, h)] = m.words[C::at(last, h)]; m.cg[C::at(j, h)] = m.cg[C::at(last, h)]; m.xc[C::at(j, h)] = m.xc[C::at(last, h)];
+            }
+            ns = last;
+        }
+    }
+    s.nslots = ns;
+}
+
+// Categorical draw over pv[0..n) of history h: first k with cum > u*total (strict, TypeContainer.cpp:730) or with
+// cum >= u*total (ProposalEngine.cpp:574); partial sums in index order. Returns k; pidx = pv[k].
+template <int NH, bool N32>
+__device__ __forceinline__ int ls_pick(const LsCta<NH, N32>& m, int h, int n, double u, bool strict, double& pidx, double& total_out) {
+    typedef LsCta<NH, N32> C;
+    double total = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) total += m.pv[C::at(k, h)];
+    const double target = u * total;
+    double cum = 0.0;
+    int idx = n - 1;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+        const double v = m.pv[C::at(k, h)];
+        cum += v;
+        if (strict ? (cum > target && v > 0.0) : !(cum < target)) { idx = k; break; }
+    }
+    pidx = m.pv[C::at(idx, h)];
+    total_out = total;
+    return idx;
+}
+
+// item i of a flattened work list -> (history, local index): pre[] = exclusive prefix of the per-history item counts
+template <int NH>
+__device__ __forceinline__ int ls_find(const int* pre, int i) {
+    int lo = 0;
+#pragma unroll
+    for (int step = NH / 2; step > 0; step >>= 1) if (pre[lo + step] <= i) lo += step;
+    return lo;
+}
+
+template <int NH, bool N32>
+__device__ __forceinline__ void run_lockstep() {
+    typedef LsCta<NH, N32> C;
+    typedef typename C::WO WO;
+    constexpr int NT = C::NT;
+    C m; m.bind();
+    const int tid = threadIdx.x;
+    const bool serial = tid < NH;
+    const int h = tid;                   // history slot of a serial thread
+    const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
+    const int nsum = Ltot + 2;
+    const int wlen = ((Ltot + 2) + 1) & ~1;
+    constexpr bool kStaged =
+#ifdef COAL_TMA_ROWS
+        N32;
+#else
+        false;
+#endif
+    unsigned long long ev_total = 0, pi_total = 0, cq_total = 0;
+    unsigned int nh_lane = 0;
+    const unsigned long long n_todo = sA.list ? *sA.list_count : sA.n;
+
+    LsHist s;
+    s.h = 0; s.rng.init(0, 0); epoch_stats_clear(s.st); s.qprod.clear(); s.evprod.clear(); s.qsum = s.consts = s.tsum = 0.0;
+    s.nslots = s.nA = s.nB = s.nC = 0; s.inj_lo = s.inj_hi = 0; s.e = 0; s.tset = 0; s.peak = 0;
+    s.nev = s.npi = s.ncq = 0; s.tma_phase = 0;
+    s.have = false; s.done = !serial; s.injecting = false; s.post = true; s.tracing = false; s.overflow = false; s.wfirst = true; s.pending = false;
+    if (serial) {
+        m.desc[h].valid = 0; m.desc[h].nm = 0; m.desc[h].nq = 0;
+        m.snap[h].flags = 0;
+#ifdef COAL_TMA_ROWS
+        mbar_init(m.mbar + h);
+#endif
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (;;) {
+        int snap_flags = 0;
+        // =================================== S: one thread per history ===================================
+        if (serial && !s.done) {
+            LsDesc& D = m.desc[h];
+            bool end_now = false;
+            // ---- finish the event of the previous step (ProposalEngine.cpp:241-294, 341-371, 417-448, 455-546) ----
+            if (s.pending) {
+                s.pending = false;
+                const unsigned long long xw = D.xw;
+                const int xg = D.xg, np = D.np, Lx = D.Lx, offb = D.offb, pg = D.pg, n = D.n;
+                const bool isC = (xg == GC), isA = (xg == GA);
+                const unsigned int Cij = D.Cij, Ci = D.Ci, Cj = D.Cj, Ai = D.Ai, Bj = D.Bj, own = D.own, ownC = D.ownC;
+                const int Ac = D.Ac, Bc = D.Bc, Cc = D.Cc;
+                const unsigned long long xa = xw & sP.maskA, xb = xw & sP.maskB;
+                const double pi0 = isC ? D.pi0c : D.mA1;
+                const double inv_pi0 = 1.0 / pi0;
+                int ncand;
+                if (isC) {
+                    // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
+                    const double pj = 0.5 * D.mA1 * D.mB2 + 0.5 * D.mB1 * D.mA2;
+                    const double f = D.dtheta_e * (double)Cij;
+#pragma unroll 1
+                    for (int k = 0; k < Ltot; k++) m.pv[C::at(k, h)] = f * m.pv[C::at(k, h)] * inv_pi0;
+                    m.pv[C::at(Ltot, h)] = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
+                    m.pv[C::at(Ltot + 1, h)] = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
+                    m.pv[C::at(Ltot + 2, h)] = (Bj > 0) ? (double)(Bj * Cij) / D.mB1 : 0.0;
+                    m.pv[C::at(Ltot + 3, h)] = D.drho_e * (double)Cij * pj * inv_pi0;
+                    ncand = Ltot + 4;
+                    s.npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < Lx; k++) m.pv[C::at(k, h)] *= inv_pi0;
+                    m.pv[C::at(Lx + np, h)] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
+                    ncand = Lx + np + 1;
+                    s.npi += (unsigned int)(1 + Lx + 5 * np);
+                }
+                LS_ASSERT(ncand <= sP.pvmax);
+                // ---- sample the move (sampleFromVector :568-583) ----
+                double pidx, ptot;
+                const int idx = ls_pick<NH, N32>(m, h, ncand, s.rng.next(), false, pidx, ptot);
+                // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
+                const double qfac = (D.rate * D.hap_num * pidx) / (D.hap_den * ptot);
+                // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
+                double evc = 1.0; int kind = 0;          // kind: 0 coalescence, 1 mutation, 2 recombination
+                int ev_kind = 1; unsigned long long ev_aux = 0ull; int ev_site = 0xff;
+                int og0 = 0, og1 = 0, od0 = 0, od1 = 0, nops = 0; unsigned long long ow0 = 0ull, ow1 = 0ull;
+                if (idx < Lx) {                                                        // mutation of site idx
+                    ow0 = xw ^ (1ull << (offb + idx)); og0 = xg; od0 = +1; nops = 1;
+                    kind = 1; ev_kind = 0; ev_aux = ow0; ev_site = idx;
+                } else if (isC) {
+                    if (idx == Ltot) { evc = (double)((unsigned int)Cc * (Cij - 1)); }
+                    else if (idx == Ltot + 1) { og0 = GC; ow0 = xw; od0 = +1; og1 = GA; ow1 = xa; od1 = -1; nops = 2;
+                                                evc = (double)((unsigned int)Ac * Cij); ev_kind = 2; ev_aux = xa; }
+                    else if (idx == Ltot + 2) { og0 = GC; ow0 = xw; od0 = +1; og1 = GB; ow1 = xb; od1 = -1; nops = 2;
+                                                evc = (double)((unsigned int)Bc * Cij); ev_kind = 3; ev_aux = xb; }
+                    else { og0 = GA; ow0 = xa; od0 = +1; og1 = GB; ow1 = xb; od1 = +1; nops = 2; kind = 2; ev_kind = 4; }
+                } else if (idx < Lx + np) {                                            // A^B_k coalescence
+                    const int pslot = (int)m.plist[C::at(idx - Lx, h)];
+                    LS_ASSERT(pslot < s.nslots);
+                    const unsigned long long pw = (unsigned long long)m.words[C::at(pslot, h)];
+                    og0 = pg; ow0 = pw; od0 = -1; og1 = GC; ow1 = xw | pw; od1 = +1; nops = 2;
+                    ev_kind = 5; ev_aux = pw;
+                } else {
+                    evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
+                }
+                double after0 = 1.0, after1 = 1.0;
+                if (nops > 0) { const int slot = ls_adjust<NH, N32>(m, h, s, og0, ow0, od0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                if (nops > 1) { const int slot = ls_adjust<NH, N32>(m, h, s, og1, ow1, od1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                if (ev_kind == 0) evc = after0;
+                else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
+                else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
+                const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
+                ls_commit<NH, N32>(m, h, s);
+                if (s.tracing && s.nev < sA.max_events) {
+                    coalgpu_event& r = sA.events[(unsigned long long)s.h * sA.max_events + s.nev];
+                    r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
+                    r.epoch = (uint8_t)s.e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
+                }
+                s.nev++;
+                // ---- target density bookkeeping (:457-546) ----
+                s.tsum += D.wait;
+                if (ns_event > s.peak) s.peak = ns_event;
+                s.qsum += -D.rate * D.wait;
+                s.qprod.mul(qfac);
+                s.evprod.mul(evc);
+                s.st.s_nn += D.nn * D.wait; s.st.s_a += D.aa * D.wait; s.st.s_c += (double)Cc * D.wait;
+                if (kind == 1) s.st.n_mut++; else if (kind == 2) s.st.n_rec++;
+                if (s.post) { s.st.has_post = 1; s.st.post_nn = D.nn; s.st.post_a = D.aa; s.st.post_c = (double)Cc; }
+                else s.st.n_rate++;
+                s.post = false;
+                if (s.nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
+                end_now = s.overflow;
+            }
+            D.valid = 0; D.nm = 0; D.nq = 0;
+
+            // ---- fetch the next history ----
+            if (!end_now && !s.have) {
+                unsigned long long hx = atomicAdd(sA.counters + (sA.list ? 7 : 0), 1ull);
+                if (hx >= n_todo) {
+                    s.done = true;
+                } else {
+                    if (sA.list) hx = sA.list[hx];
+                    s.h = hx; s.have = true;
+                    s.rng.init(sA.seed, sA.first + hx);
+                    s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
+                    s.tracing = sA.events != nullptr && hx < sA.n_trace;
+                    s.nev = 0; s.npi = 0; s.ncq = 0;
+                    // initial configuration (TypeContainer ctor, TypeContainer.cpp:42-99), then injections at boundaries
+                    s.inj_lo = sP.type_off[0]; s.inj_hi = sP.type_off[1];
+                    s.injecting = true; s.post = true; s.wfirst = true;
+                    s.e = 0; s.tset = sP.set_of_epoch[0];
+                    s.qsum = 0.0; s.consts = 0.0; s.tsum = 0.0; s.peak = 0;
+                    s.qprod.clear(); s.evprod.clear(); epoch_stats_clear(s.st);
+                }
+            }
+
+            if (!s.done && !end_now && s.injecting) {
+                // TypeContainer::addTypeMap :525-591 + probabilityCombinatorics ProposalEngine.cpp:66-86
+                const int a0 = s.nA, b0 = s.nB, c0 = s.nC;
+                double comb = 0.0;
+#pragma unroll 1
+                for (int k = s.inj_lo; k < s.inj_hi; k++) {
+                    const unsigned int cgk = sP.type_cg[k];
+                    const int add = (int)(cgk & kCntMask);
+                    const int slot = ls_adjust<NH, N32>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
+                    if (slot < 0) break;
+                    const int now = (int)(m.cg[C::at(slot, h)] & kCntMask);
+                    comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
+                }
+                if (s.e > 0 && !s.overflow) {
+                    comb -= sP.lfact[s.nA] - sP.lfact[s.nA - a0] - sP.lfact[a0];
+                    comb -= sP.lfact[s.nB] - sP.lfact[s.nB - b0] - sP.lfact[b0];
+                    comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
+                    s.consts += comb;
+                }
+                if (s.nslots > s.peak) s.peak = s.nslots;
+                s.injecting = false;
+                end_now = s.overflow;
+            }
+
+            bool finish = false;
+            if (!s.done && !end_now) {
+                // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
+                const EpochConst* __restrict__ ecp = sP.ep + s.e;
+                const double dthA = __ldg(&ecp->dthA), dthB = __ldg(&ecp->dthB), drho_e = __ldg(&ecp->drho);
+                // lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721)
+                const int ns0 = s.nslots;
+#pragma unroll 1
+                for (int j = 0; j < ns0; j++) {
+                    const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
+                    const unsigned int c = cgj & kCntMask;
+                    const int gj = (int)(cgj >> 30);
+                    double wgt;
+                    if (gj == GC) wgt = ((((double)(c - 1) + (dthA + dthB)) + drho_e) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
+                    else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + dthA) * (double)c;
+                    else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + dthB) * (double)c;
+                    m.pv[C::at(j, h)] = wgt;
+                }
+                double hap_num, hap_den;
+                const int sx = ls_pick<NH, N32>(m, h, ns0, s.rng.next(), true, hap_num, hap_den);
+                const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
+                const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
+                const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
+                const double rate = Dd * __ldg(&ecp->inv2Ntau);
+                const double tsum = s.tsum;
+                const double wait = -dlog(s.rng.next()) / rate;
+                const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
+
+                // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
+                const bool boundary = (s.e < T - 1) && !(tsum + wait < sP.times[s.e + 1]);
+                finish = (s.e == T - 1) && (n <= 5);
+                if (boundary || finish) {
+                    if (boundary) {
+                        const double excess = sP.times[s.e + 1] - tsum;
+                        s.tsum = sP.times[s.e + 1];
+                        s.qsum += -rate * excess;
+                        s.st.s_nn += nn * excess; s.st.s_a += aa * excess; s.st.s_c += (double)Cc * excess;
+                        s.st.bnd_nn = nn; s.st.bnd_a = aa; s.st.bnd_c = (double)Cc; s.st.has_bnd = 1; s.st.n_rate += 1;
+                    }
+                    s.st.slog = logprod_value(s.evprod);
+                    LsSnap& sn = m.snap[h];
+                    sn.st = s.st; sn.e = s.e; sn.hidx = s.h; sn.fin = 0.0;
+                    snap_flags = kLsFlagAccum | (s.wfirst ? kLsFlagFirst : 0);
+                    s.wfirst = false;
+                    epoch_stats_clear(s.st); s.evprod.clear();
+                    if (sA.lineages) sA.lineages[s.h * (unsigned long long)T + s.e] = (double)n;
+                    if (finish) {
+                        end_now = true;
+                    } else {
+                        s.e++;
+                        s.inj_lo = sP.type_off[s.e]; s.inj_hi = sP.type_off[s.e + 1];
+                        s.injecting = true;
+                        s.post = true;
+                        s.tset = sP.set_of_epoch[s.e];
+                    }
+                } else {
+                    // ---- set up one event (ProposalEngine.cpp:134-238, 298-338, 375-414) ----
+                    const unsigned long long xw = (unsigned long long)m.words[C::at(sx, h)];
+                    const unsigned int xcg = m.cg[C::at(sx, h)], xxc = m.xc[C::at(sx, h)];
+                    const int xg = (int)(xcg >> 30);
+                    const unsigned int xcount = xcg & kCntMask;
+                    const bool isC = (xg == GC), isA = (xg == GA);
+                    const typename WO::T xa = WO::narrow(xw & sP.maskA), xb = WO::narrow(xw & sP.maskB);
+                    const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
+                    unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
+                    if (isC) {
+                        Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16;
+#pragma unroll 1
+                        for (int j = 0; j < ns0; j++) {
+                            const unsigned int cgj = m.cg[C::at(j, h)];
+                            if ((int)(cgj >> 30) == GC) {
+                                const typename WO::T wj = m.words[C::at(j, h)];
+                                if ((wj & maskA) == xa) Ci += cgj & kCntMask;
+                                if ((wj & maskB) == xb) Cj += cgj & kCntMask;
+                            }
+                        }
+                    } else if (isA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
+
+#ifdef COAL_TMA_ROWS
+                    // Stage what this event reads from the tables -- the row of its two-locus queries (n-1 lineages for a
+                    // C lineage, n-2 for a one-locus lineage) and the wEA|wEB tails of the two rows of its one-locus
+                    // queries -- with TMA bulk copies; they overlap the rest of the serial phase.
+                    {
+                        const double* g_m1 = row_ptr(s.tset, n - 1);
+                        const double* g_alt = row_ptr(s.tset, isC ? n : n - 2);
+                        const unsigned int rb = (unsigned int)sP.stage_doubles * 8u, wb = (unsigned int)(sP.row_doubles - sP.off_wEA) * 8u;
+                        unsigned long long* bar = m.mbar + h;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect(bar, rb + 2u * wb);
+                        if (rb) bulk_g2s(m.rowbuf + (size_t)h * sP.stage_doubles, isC ? g_m1 : g_alt, rb, bar);
+                        bulk_g2s(m.wbuf + (size_t)h * 2 * wlen, g_m1 + sP.off_wEA, wb, bar);
+                        bulk_g2s(m.wbuf + (size_t)h * 2 * wlen + wlen, g_alt + sP.off_wEA, wb, bar);
+                        D.tma_parity = s.tma_phase; s.tma_phase ^= 1u;
+                        D.row_m1 = m.wbuf + (size_t)h * 2 * wlen - sP.off_wEA;
+                        D.row_alt = m.wbuf + (size_t)h * 2 * wlen + wlen - sP.off_wEA;
+                        D.crow = kStaged ? (m.rowbuf + (size_t)h * sP.stage_doubles) : (isC ? g_m1 : g_alt);
+                    }
+#else
+                    D.row_m1 = row_ptr(s.tset, n - 1);
+                    D.row_alt = row_ptr(s.tset, isC ? n : n - 2);
+                    D.crow = isC ? D.row_m1 : D.row_alt;
+                    D.tma_parity = 0;
+#endif
+                    ls_adjust<NH, N32>(m, h, s, xg, xw, -1);               // H' = H - x  (:168)
+                    const int ns = s.nslots;
+                    const int Lx = isC ? Ltot : (isA ? LA : LB);
+                    const int pg = isA ? GB : GA;
+                    // partner list = stored types of the other one-locus class, slot order (:300 / :377)
+                    int np = 0;
+                    if (!isC) {
+#pragma unroll 1
+                        for (int j = 0; j < ns; j++) {
+                            const unsigned int cgj = m.cg[C::at(j, h)];
+                            if ((int)(cgj >> 30) == pg && (cgj & kCntMask) > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
+                        }
+                    }
+                    D.xw = xw; D.xg = xg; D.ns = ns; D.n = n; D.np = np; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = pg;
+                    D.nm = isC ? 2 : 1 + Lx + np;
+                    D.nq = isC ? Ltot + 1 : np;
+                    D.own = isA ? Ai : Bj; D.ownC = isA ? Ci : Cj;
+                    D.Cij = Cij; D.Ci = Ci; D.Cj = Cj; D.Ai = Ai; D.Bj = Bj; D.Ac = Ac; D.Bc = Bc; D.Cc = Cc;
+                    D.cn = isC ? (unsigned int)(n - 1) : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
+                    D.nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
+                    D.dtheta_e = __ldg(&ecp->dtheta); D.drho_e = drho_e;
+                    D.dtheta_own = D.dtheta_e * (double)D.own;
+                    D.rate = rate; D.wait = wait; D.hap_num = hap_num; D.hap_den = hap_den; D.nn = nn; D.aa = aa;
+                    D.valid = 1;
+                    s.pending = true;
+                    s.ncq += (unsigned int)D.nq;
+                    LS_ASSERT(Lx + np + 1 <= sP.pvmax && np <= sP.kmax);
+                }
+            }
+
+            if (end_now) {
+                // ---- final weight (ProposalEngine.cpp:817-858) ----
+                const double ln2 = 0.69314718055994530942;
+                const double q = s.qsum + logprod_value(s.qprod);
+                const double fin = s.consts + sP.perm_const - q
+                                 - ((double)(LA + LB) * ln2 * (double)s.nC + (double)LA * ln2 * (double)s.nA + (double)LB * ln2 * (double)s.nB);
+                LsSnap& sn = m.snap[h];
+                sn.hidx = s.h; sn.fin = fin;
+                if (s.overflow) snap_flags = kLsFlagAbort;
+                else snap_flags |= kLsFlagFinal;       // the final epoch's statistics were snapshotted above (finish)
+                if (sA.tmrca) sA.tmrca[s.h] = s.tsum;
+                if (sA.nevents) sA.nevents[s.h] = s.nev;
+                if (s.tracing && sA.event_counts) sA.event_counts[s.h] = s.nev;
+                if (!s.overflow) atomicMax(sA.counters + 8, (unsigned long long)s.peak);
+                if (s.overflow) {
+                    if (sA.defer_list) sA.defer_list[atomicAdd(sA.counters + 6, 1ull)] = s.h;   // drawn again with the full capacity
+                    else atomicAdd(sA.counters + 3, 1ull);
+                }
+                if (!(s.overflow && sA.defer_list)) { ev_total += s.nev; pi_total += s.npi; cq_total += s.ncq; }
+                s.have = false; s.pending = false;
+                D.valid = 0; D.nm = 0; D.nq = 0;
+            }
+            m.snap[h].flags = snap_flags;
+        }
+        // work lists of the query phases: exclusive prefixes of the per-history query counts (warp 0 scans; NH <= 32)
+        if (tid < 32) {
+            int c1 = 0, c2 = 0;
+            if (tid < NH) { c1 = m.desc[tid].nm; c2 = m.desc[tid].nq; }
+            int i1 = c1, i2 = c2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t1 = __shfl_up_sync(kFull, i1, o), t2 = __shfl_up_sync(kFull, i2, o);
+                if (tid >= o) { i1 += t1; i2 += t2; }
+            }
+            if (tid < NH) { m.pre1[tid + 1] = i1; m.pre2[tid + 1] = i2; }
+            if (tid == 0) { m.pre1[0] = 0; m.pre2[0] = 0; }
+        }
+        const int alive = __syncthreads_or((serial && !s.done) ? 1 : 0);
+        if (!alive) break;
+
+        // =================================== G: per-grid-point target density of closed epochs ===================================
+        if (__syncthreads_or(snap_flags)) {
+            if (sA.weights) {
+#pragma unroll 1
+                for (int hh = 0; hh < NH; hh++) {
+                    const int fl = m.snap[hh].flags;
+                    if (!fl) continue;
+                    double* wout = sA.weights + m.snap[hh].hidx * (unsigned long long)NG;
+                    if (fl & kLsFlagAbort) {
+                        const double bad = __longlong_as_double(0x7ff8000000000000ll);
+                        for (int g = tid; g < NG; g += NT) wout[g] = bad;
+                        continue;
+                    }
+                    const EpochStats st = m.snap[hh].st;
+                    const GridConst* gc = sP.grid + (size_t)m.snap[hh].e * NG;
+                    const double fin = (fl & kLsFlagFinal) ? m.snap[hh].fin : 0.0;
+#pragma unroll 1
+                    for (int g = tid; g < NG; g += NT) {
+                        const GridConst c = gc[g];
+                        double v = (fl & kLsFlagFirst) ? 0.0 : wout[g];
+                        v += epoch_log_density(st, c.theta, c.rho, c.inv2Ntau, c.log_theta, c.log_rho, c.log_2Ntau, [](double x) { return dlog(x); });
+                        if (fl & kLsFlagFinal) v += fin;
+                        wout[g] = v;
+                    }
+                }
+            }
+            // the snapshots are rewritten in the next S phase, after the barriers of the query phases
+        }
+
+        // =================================== Q1: one-locus queries, one per lane ===================================
+        //  C chosen: 0 = A part, 1 = B part, rows n-1 and n (:198-238 with :120-132)
+        //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
+        //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
+        {
+            const int M1 = m.pre1[NH];
+#pragma unroll 1
+            for (int it = tid; it < M1; it += NT) {
+                const int hh = ls_find<NH>(m.pre1, it);
+                const int qi = it - m.pre1[hh];
+                const LsDesc& D = m.desc[hh];
+#ifdef COAL_TMA_ROWS
+                mbar_wait(m.mbar + hh, D.tma_parity);
+#endif
+                const int xg = D.xg, Lx = D.Lx, ns = D.ns;
+                const bool isC = (xg == GC);
+                const bool partner = !isC && qi > Lx;
+                int qg; unsigned long long qw64; bool excl = false;
+                if (isC) { qg = (qi == 1) ? GB : GA; qw64 = D.xw & ((qi == 1) ? sP.maskB : sP.maskA); }
+                else if (partner) { qg = D.pg; qw64 = (unsigned long long)m.words[C::at((int)m.plist[C::at(qi - Lx - 1, hh)], hh)]; excl = true; }
+                else { qg = xg; qw64 = (qi >= 1) ? (D.xw ^ (1ull << (D.offb + qi - 1))) : D.xw; }
+                const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
+                const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
+                const double* __restrict__ wE1 = D.row_m1 + offw;
+                const double* __restrict__ wE2 = D.row_alt + offw;
+                const typename WO::T mask = WO::narrow((qg == GA) ? sP.maskA : sP.maskB), qw = WO::narrow(qw64);
+                double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
+#pragma unroll 1
+                for (int j = 0; j < ns; j++) {
+                    const typename WO::T wj = m.words[C::at(j, hh)];
+                    const unsigned int cgj = m.cg[C::at(j, hh)];
+                    const int gj = (int)(cgj >> 30);
+                    unsigned int c = cgj & kCntMask;
+                    if (gj == qg || gj == GC) {
+                        if (excl && gj == qg && wj == qw) c -= 1;
+                        const int d = WO::popc((wj ^ qw) & mask);
+                        const double cf = (double)c;
+                        num1 += cf * tab_ld(wE1 + d);
+                        num2 += cf * tab_ld(wE2 + d);
+                        ncomp += c;
+                    }
+                }
+                // fp64 division is a ~25-instruction sequence: reciprocals of lineage counts come from a table
+                const double inv_nc = __ldg(sP.rcp + ncomp);
+                const double v1 = marginal_finish_rcp(num1, inv_nc, ncomp, (unsigned int)(D.n - 1), powl, sP.wsum);
+                const double v2 = marginal_finish_rcp(num2, inv_nc, ncomp, D.nc_alt, powl, sP.wsum);
+                LsDesc& Dw = m.desc[hh];
+                if (qi == 0) { Dw.mA1 = v1; Dw.mA2 = v2; }
+                else if (isC) { Dw.mB1 = v1; Dw.mB2 = v2; }
+                else if (!partner) m.pv[C::at(qi - 1, hh)] = D.dtheta_own * v1;          // x 1/pi0 in the next S phase
+                else { m.pv[C::at(qi - 1, hh)] = v1; m.aux[C::at(qi - Lx - 1, hh)] = v2; }   // pv[Lx + k], joined in Q2
+            }
+        }
+        __syncthreads();
+
+        // =================================== Q2: two-locus queries, one per lane ===================================
+        //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
+        //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
+        {
+            const int M2 = m.pre2[NH];
+            const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
+            unsigned int* mine = m.scratch + tid;          // histogram / class list of this lane: element i at mine[i * NT]
+#pragma unroll 1
+            for (int it = tid; it < M2; it += NT) {
+                const int hh = ls_find<NH>(m.pre2, it);
+                const int qi = it - m.pre2[hh];
+                const LsDesc& D = m.desc[hh];
+                const bool isC = (D.xg == GC);
+                const int ns = D.ns;
+                // ---- class list (TypeContainer::getDifferences for a C query, TypeContainer.cpp:802-886) ----
+                unsigned long long qw64 = D.xw, delw64 = 0ull; int delg = -1; int pslot = 0;
+                if (isC) { if (qi > 0) qw64 = D.xw ^ (1ull << (qi - 1)); }
+                else { pslot = (int)m.plist[C::at(qi, hh)]; delw64 = (unsigned long long)m.words[C::at(pslot, hh)]; delg = D.pg; qw64 = D.xw | delw64; }
+                const typename WO::T qw = WO::narrow(qw64), delw = WO::narrow(delw64);
+#pragma unroll 1
+                for (int sidx = 0; sidx < nsum; sidx++) mine[sidx * NT] = 0xffff0000u;
+#pragma unroll 1
+                for (int j = 0; j < ns; j++) {
+                    const typename WO::T wj = m.words[C::at(j, hh)];
+                    const unsigned int cgj = m.cg[C::at(j, hh)];
+                    const int gj = (int)(cgj >> 30);
+                    unsigned int c = cgj & kCntMask;
+                    if (gj == delg && wj == delw) c -= 1;
+                    if (c > 0) {
+                        const typename WO::T y = wj ^ qw;
+                        const int da = WO::popc(y & maskA), db = WO::popc(y & maskB);
+                        int sidx; unsigned int rep;
+                        if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
+                        LS_ASSERT(sidx < nsum);
+                        const unsigned int v = mine[sidx * NT];
+                        mine[sidx * NT] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
+                    }
+                }
+                // compact the classes in place (ascending dA+dB) and collect the totals
+                int nH = 0;
+                ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
+#pragma unroll 1
+                for (int sidx = 0; sidx < nsum; sidx++) {
+                    const unsigned int v = mine[sidx * NT];
+                    const unsigned int cnt = v & 0xffffu;
+                    if (cnt) {
+                        const unsigned int rep = v >> 16;
+                        int dA, dB;
+                        if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
+                        mine[nH * NT] = pack_class(cnt, dA, dB);
+                        nH++;
+                        tot.n += cnt;
+                        if (dA >= 0) tot.ncompA += cnt;
+                        if (dB >= 0) tot.ncompB += cnt;
+                    }
+                }
+                nh_lane += (unsigned int)nH;
+                // ---- pi_SMC as a bilinear form (coal_math.h) ----
+                double pi;
+                if (D.cn == 0 || nH == 0) pi = sP.pow2negL;      // empty configuration, ConditionalSamplingHMM.cpp:277-298
+                else {
+                    const double* __restrict__ row = D.crow;
+                    auto ldmy = [row](int k) {
+                        const double2 v = kStaged ? *reinterpret_cast<const double2*>(row + 2 * k) : __ldg(reinterpret_cast<const double2*>(row + 2 * k));
+                        MYPair e; e.m = v.x; e.y = v.y; return e;
+                    };
+                    pi = pismc_bilinear(ldmy, sP.SB, LA, LB, mine, NT, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB),
+                                        __ldg(sP.rcp + tot.n), sP.pow2negLA, sP.pow2negLB);
+                }
+                if (isC) { if (qi == 0) m.desc[hh].pi0c = pi; else m.pv[C::at(qi - 1, hh)] = pi; }
+                else {
+                    // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
+                    const double v1 = m.pv[C::at(D.Lx + qi, hh)], v2 = m.aux[C::at(qi, hh)];
+                    const double joint = 0.5 * D.mA2 * v1 + 0.5 * v2 * D.mA1;
+                    m.pv[C::at(D.Lx + qi, hh)] = (double)D.own * (double)(m.cg[C::at(pslot, hh)] & kCntMask) * pi / joint;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // work counters of the launch
+    unsigned int nh_warp = warp_sum_u(nh_lane);
+    if ((tid & 31) == 0 && nh_warp) atomicAdd(sA.counters + 5, (unsigned long long)nh_warp);
+    if (serial) {
+        if (ev_total) atomicAdd(sA.counters + 1, ev_total);
+        if (pi_total) atomicAdd(sA.counters + 2, pi_total);
+        if (cq_total) atomicAdd(sA.counters + 4, cq_total);
+    }
+}
+
+}  // namespace
+
+// The launch: persistent CTAs of 4 * NH threads pull history indices from a global counter until the batch is drawn.
+#ifndef COAL_LS_MIN_CTAS_16
+#define COAL_LS_MIN_CTAS_16 6
+#endif
+#ifndef COAL_LS_MIN_CTAS_32
+#define COAL_LS_MIN_CTAS_32 3
+#endif
+template <int NH, bool N32>
+__global__ void __launch_bounds__(4 * NH, NH == 16 ? COAL_LS_MIN_CTAS_16 : COAL_LS_MIN_CTAS_32)
+history_lockstep_kernel(const DevProblem P, const SampleArgs A) {
+    if (threadIdx.x == 0) { sP = P; sA = A; }
+    __syncthreads();
+    run_lockstep<NH, N32>();
+}
+
+history_kernel_fn history_lockstep_select(int NH, bool narrow) {
+    if (narrow) return NH == 16 ? history_lockstep_kernel<16, true> : history_lockstep_kernel<32, true>;
+    return NH == 16 ? history_lockstep_kernel<16, false> : history_lockstep_kernel<32, false>;
+}
+size_t history_lockstep_bytes(int NH, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+    return ls_layout(NH, kmax, pvmax, Ltot, stage_doubles, narrow).total;
+}
