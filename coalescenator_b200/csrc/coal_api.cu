@@ -74,8 +74,8 @@ int ensure_kernel_attributes(int device) {
         CU_OK(cudaFuncGetAttributes(&fa, fn));            // static shared memory (problem constants) counts against the limit
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     }
-    for (int NH : {16, 32}) for (int narrow = 0; narrow < 2; narrow++) {
-        const void* fn = (const void*)history_lockstep_select(NH, narrow != 0);
+    for (int shape : {16 | (64 << 8), 32 | (64 << 8), 32 | (128 << 8)}) for (int narrow = 0; narrow < 2; narrow++) {
+        const void* fn = (const void*)history_lockstep_select(shape & 0xff, shape >> 8, narrow != 0);
         cudaFuncAttributes fa;
         CU_OK(cudaFuncGetAttributes(&fa, fn));
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
@@ -300,8 +300,9 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
 struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; bool ls = false; };
 // threads per CTA / histories per CTA of a geometry: the group form packs cta_threads(W) / W groups of W lanes, the
 // lockstep form advances NH = `group` histories with 4 * NH threads
-inline int geo_threads(int group, bool ls) { return ls ? 4 * group : cta_threads(group); }
-inline int geo_hist_per_cta(int group, bool ls) { return ls ? group : cta_threads(group) / group; }
+// (lockstep: `group` = NH | NT << 8)
+inline int geo_threads(int group, bool ls) { return ls ? (group >> 8) : cta_threads(group); }
+inline int geo_hist_per_cta(int group, bool ls) { return ls ? (group & 0xff) : cta_threads(group) / group; }
 // Which form of K1: the lockstep form (default) or the group form (COALGPU_KERNEL=group, or a forced group width
 // COALGPU_GROUP=8|16|32, which the parity tests of the group form use).
 bool want_lockstep() {
@@ -311,18 +312,19 @@ bool want_lockstep() {
 }
 Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
     if (want_lockstep()) {
-        int forced_nh = 0;
+        int forced_nh = 0, forced_nt = 0;
         if (const char* g = std::getenv("COALGPU_LOCKSTEP_NH")) { const int v = std::atoi(g); if (v == 16 || v == 32) forced_nh = v; }
-        auto eval = [&](int NH) {
-            Geometry g; g.group = NH; g.ls = true;
-            g.smem = history_lockstep_bytes(NH, kmax, pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32);
+        if (const char* g = std::getenv("COALGPU_LOCKSTEP_NT")) { const int v = std::atoi(g); if (v == 64 || v == 128) forced_nt = v; }
+        auto eval = [&](int NH, int NT) {
+            Geometry g; g.group = NH | (NT << 8); g.ls = true;
+            g.smem = history_lockstep_bytes(NH, NT, kmax, pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32);
             if (g.smem > 227 * 1024) return Geometry();
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_lockstep_select(NH, P.Ltot <= 32), 4 * NH, g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_lockstep_select(NH, NT, P.Ltot <= 32), NT, g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
             g.per_sm = g.occ * NH;
             return g;
         };
-        if (forced_nh) return eval(forced_nh);
-        const Geometry g16 = eval(16), g32 = eval(32);
+        if (forced_nh) return eval(forced_nh, forced_nh == 16 ? 64 : (forced_nt ? forced_nt : 128));
+        const Geometry g16 = eval(16, 64), g32 = eval(32, forced_nt ? forced_nt : 128);
         if (g16.per_sm > 0 || g32.per_sm > 0) return g32.per_sm > g16.per_sm ? g32 : g16;
         // neither fits (type store beyond ~200 KB of shared memory per CTA): fall through to the group form
     }
@@ -568,7 +570,7 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
     const unsigned long long todo = pass == 2 ? n_listed : n;
     const unsigned long long ctas_needed = (todo + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)std::max<unsigned long long>(ctas_needed, 1);
-    history_kernel_fn kfn = ls ? history_lockstep_select(group, P.Ltot <= 32) : history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+    history_kernel_fn kfn = ls ? history_lockstep_select(group & 0xff, group >> 8, P.Ltot <= 32) : history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
     kfn<<<grid, geo_threads(group, ls), smem, st>>>(P, a);
     g_launches++;
     CU_OK(cudaGetLastError());
@@ -633,7 +635,20 @@ int coalgpu_capacity_stats(coalgpu_sampler* s, uint64_t* n_deferred, uint32_t* s
     if (store_first_pass) *store_first_pass = (uint32_t)(s->fast ? s->P_fast.kmax : s->P.kmax);
     if (store_full) *store_full = (uint32_t)s->P.kmax;
     if (peak_types) *peak_types = (uint32_t)h[8];
-    if (lanes_per_history) *lanes_per_history = (uint32_t)(s->fast ? s->fast_group : s->group);
+    if (lanes_per_history) {      // lockstep form: histories per CTA (its serial phase runs one thread per history)
+        const int g = s->fast ? s->fast_group : s->group; const bool ls = s->fast ? s->fast_ls : s->ls;
+        *lanes_per_history = (uint32_t)(ls ? (g & 0xff) : g);
+    }
+    return 0;
+}
+
+// Debug builds with -DCOAL_LS_TIMING: phase clocks of the lockstep kernel (cycles in S, G, Q1, Q2 summed over CTAs, steps).
+int coalgpu_phase_clocks(coalgpu_sampler* s, uint64_t* out5) {
+    if (!s || !out5) return fail(COALGPU_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(s->device));
+    unsigned long long h[kCounters];
+    CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; i++) out5[i] = h[10 + i];
     return 0;
 }
 

@@ -690,7 +690,11 @@ __device__ __forceinline__ void run_group() {
 #else
                     false;
 #endif
+#ifdef COAL_TMA_ROWS
                 const double* crow = kStaged ? m.rowbuf : (isC ? row_ptr(tset, n - 1) : row_ptr(tset, n - 2));
+#else
+                const double* crow = isC ? row_ptr(tset, n - 1) : row_ptr(tset, n - 2);
+#endif
                 const unsigned int cn = isC ? (unsigned int)(n - 1) : nc_alt;
                 const int hstride = (Ltot + 2) | 1;
 #pragma unroll 1

@@ -1,4 +1,4 @@
-// K1, lockstep form: a CTA of NT = 4 * NH threads advances NH coalescent histories in lockstep, one "step" (an injection,
+// K1, lockstep form: a CTA of NT threads advances NH coalescent histories (NH <= 32 <= NT) in lockstep, one "step" (an injection,
 // a collection boundary, or one backward event of ProposalEngine.cpp:134-566) per history and iteration, in phases
 // separated by CTA barriers:
 //
@@ -28,6 +28,10 @@
 
 namespace {
 
+#ifndef COAL_LS_DENSE_MAX
+#define COAL_LS_DENSE_MAX 64
+#endif
+constexpr int kLsDenseMax = COAL_LS_DENSE_MAX;   // dense bilinear form up to this many (dA, dB) cells, class-list form beyond
 constexpr int kLsFlagAccum = 1;    // snapshot: add the epoch's target density to the history's weights
 constexpr int kLsFlagFinal = 2;    //           ... and the final constant: the history ends
 constexpr int kLsFlagAbort = 4;    //           the history outgrew the type store: weights = NaN
@@ -56,11 +60,11 @@ struct LsSnap {                    // what the G phase needs of a history that c
 
 struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, total; };
 
-__host__ __device__ inline LsLayout ls_layout(int NH, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+__host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
     LsLayout L;
     unsigned int o = 0;
     auto place = [&o](size_t bytes) { const unsigned int at = o; o += (unsigned int)((bytes + 15) & ~(size_t)15); return at; };
-    const int NT = 4 * NH, nsum = Ltot + 2;
+    const int nsum = Ltot + 2;
     L.rowbuf = place((size_t)NH * stage_doubles * 8);
     L.wbuf = place((size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8);
     L.mbar = place((size_t)NH * 8);
@@ -70,11 +74,11 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int kmax, int pvmax, int L
     L.cg = place((size_t)NH * kmax * 4);
     L.xc = place((size_t)NH * kmax * 4);
     L.plist = place((size_t)NH * kmax * 2);
-    L.scratch = place((size_t)NT * nsum * 4);
+    L.scratch = place((size_t)NT * 2 * nsum * 4);      // per thread: class histogram / class list [nsum] + the distance vectors of the dense form [nsum]
     L.desc = place((size_t)NH * sizeof(LsDesc));
     L.snap = place((size_t)NH * sizeof(LsSnap));
-    L.pre1 = place((size_t)(NH + 1) * 4);
-    L.pre2 = place((size_t)(NH + 1) * 4);
+    L.pre1 = place((size_t)(NT / 32) * (NH + 1) * 4);     // one copy of the work-list prefixes per warp
+    L.pre2 = place((size_t)(NT / 32) * (NH + 1) * 4);
     L.total = o;
     return L;
 }
@@ -85,16 +89,16 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int kmax, int pvmax, int L
 #define LS_ASSERT(cond) do { } while (0)
 #endif
 
-template <int NH, bool N32>
+template <int NH, int NT_, bool N32>
 struct LsCta {
     typedef WordOps<N32> WO;
     typedef typename WO::T WordT;
-    static constexpr int NT = 4 * NH;
+    static constexpr int NT = NT_;
     WordT* words; unsigned int* cg; unsigned int* xc; unsigned short* plist; double* pv; double* aux;
     double* rowbuf; double* wbuf; unsigned long long* mbar; unsigned int* scratch; LsDesc* desc; LsSnap* snap; int* pre1; int* pre2;
 
     __device__ __forceinline__ void bind() {
-        const LsLayout L = ls_layout(NH, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32);
+        const LsLayout L = ls_layout(NH, NT, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32);
         unsigned char* b = smem_dyn;
         words = reinterpret_cast<WordT*>(b + L.words); cg = reinterpret_cast<unsigned int*>(b + L.cg); xc = reinterpret_cast<unsigned int*>(b + L.xc);
         plist = reinterpret_cast<unsigned short*>(b + L.plist); pv = reinterpret_cast<double*>(b + L.pv); aux = reinterpret_cast<double*>(b + L.aux);
@@ -123,11 +127,15 @@ struct LsHist {
 // that is not stored yet is appended; a slot whose count reaches 0 stays until ls_commit. Returns the slot (| kAppended
 // when a slot was appended) or -1 when the store is full. Out of line (three call sites), so it takes scalars only:
 // a reference to the caller's register state would force that state into local memory.
-template <int NH, bool N32>
-__device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long long w64, int delta) {
-    typedef LsCta<NH, N32> C;
+template <int NH, int NT, bool N32>
+__device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long long w64, int delta, bool active) {
+    typedef LsCta<NH, NT, N32> C;
     typedef typename C::WO WO;
     C m; m.bind();
+    // Every history of the warp calls this at the same program points (a history without the operation passes
+    // active = false and idles through the call), so the histories that do have it walk their slots TOGETHER instead of
+    // one sub-set of lanes after the other.
+    if (!active) ns = 0;
     const typename WO::T w = WO::narrow(w64), maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
     const typename WO::T wa = w & maskA, wb = w & maskB;
     int found = -1;
@@ -148,6 +156,7 @@ __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long l
             if (gj == GB && wj == wb) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj << 16; }
         }
     }
+    if (!active) return -2;
     int ret = found;
     if (found < 0) {
         if (ns >= sP.kmax) return -1;
@@ -158,9 +167,10 @@ __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long l
     m.cg[C::at(found, h)] += (unsigned int)delta;
     return ret;
 }
-template <int NH, bool N32>
-__device__ __forceinline__ int ls_adjust(const LsCta<NH, N32>&, int h, LsHist& s, int g, unsigned long long w64, int delta) {
-    int r = ls_adjust_core<NH, N32>(h, s.nslots, g, w64, delta);
+template <int NH, int NT, bool N32>
+__device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, N32>&, int h, LsHist& s, int g, unsigned long long w64, int delta, bool active = true) {
+    int r = ls_adjust_core<NH, NT, N32>(h, s.nslots, g, w64, delta, active);
+    if (r == -2) return -1;
     if (r < 0) { s.overflow = true; return -1; }
     if (r & kAppended) { s.nslots++; r &= ~kAppended; }
     if (g == GA) s.nA += delta; else if (g == GB) s.nB += delta; else s.nC += delta;
@@ -170,9 +180,9 @@ __device__ __forceinline__ int ls_adjust(const LsCta<NH, N32>&, int h, LsHist& s
 // Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot (the canonical order
 // rule shared with the oracle's CANONICAL mode). Scanning downwards visits the empty slots in that order,
 // and everything above the scan position is already non-empty.
-template <int NH, bool N32>
-__device__ __forceinline__ void ls_commit(const LsCta<NH, N32>& m, int h, LsHist& s) {
-    typedef LsCta<NH, N32> C;
+template <int NH, int NT, bool N32>
+__device__ __forceinline__ void ls_commit(const LsCta<NH, NT, N32>& m, int h, LsHist& s) {
+    typedef LsCta<NH, NT, N32> C;
     int ns = s.nslots;
 #pragma unroll 1
     for (int j = ns - 1; j >= 0; j--) {
@@ -187,15 +197,11 @@ __device__ __forceinline__ void ls_commit(const LsCta<NH, N32>& m, int h, LsHist
     s.nslots = ns;
 }
 
-// Categorical draw over pv[0..n) of history h: first k with cum > u*total (strict, TypeContainer.cpp:730) or with
-// cum >= u*total (ProposalEngine.cpp:574); partial sums in index order. Returns k; pidx = pv[k].
-template <int NH, bool N32>
-__device__ __forceinline__ int ls_pick(const LsCta<NH, N32>& m, int h, int n, double u, bool strict, double& pidx, double& total_out) {
-    typedef LsCta<NH, N32> C;
-    double total = 0.0;
-#pragma unroll 1
-    for (int k = 0; k < n; k++) total += m.pv[C::at(k, h)];
-    const double target = u * total;
+// Categorical draw over pv[0..n) of history h given total = the sum of pv in index order: first k with cum > u*total
+// (strict, TypeContainer.cpp:730) or with cum >= u*total (ProposalEngine.cpp:574). Returns k; pidx = pv[k].
+template <int NH, int NT, bool N32>
+__device__ __forceinline__ int ls_scan(const LsCta<NH, NT, N32>& m, int h, int n, double target, bool strict, double& pidx) {
+    typedef LsCta<NH, NT, N32> C;
     double cum = 0.0;
     int idx = n - 1;
 #pragma unroll 1
@@ -205,7 +211,6 @@ __device__ __forceinline__ int ls_pick(const LsCta<NH, N32>& m, int h, int n, do
         if (strict ? (cum > target && v > 0.0) : !(cum < target)) { idx = k; break; }
     }
     pidx = m.pv[C::at(idx, h)];
-    total_out = total;
     return idx;
 }
 
@@ -218,15 +223,24 @@ __device__ __forceinline__ int ls_find(const int* pre, int i) {
     return lo;
 }
 
-template <int NH, bool N32>
+template <int NH, int NT, bool N32>
 __device__ __forceinline__ void run_lockstep() {
-    typedef LsCta<NH, N32> C;
+    typedef LsCta<NH, NT, N32> C;
     typedef typename C::WO WO;
-    constexpr int NT = C::NT;
     C m; m.bind();
     const int tid = threadIdx.x;
-    const bool serial = tid < NH;
-    const int h = tid;                   // history slot of a serial thread
+    // Serial threads: the histories of the CTA are dealt to its warps (NH / warps each, the first lanes of every warp),
+    // so the warps run their serial phases side by side and fewer histories share -- and serialise -- one warp's branches.
+#ifndef COAL_LS_SPREAD
+#define COAL_LS_SPREAD 1
+#endif
+    constexpr int kWarps = NT / 32;
+    constexpr int HPW = COAL_LS_SPREAD ? NH / kWarps : NH;           // histories per serial warp
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool serial = COAL_LS_SPREAD ? (lane < HPW) : (tid < NH);
+    const int h = COAL_LS_SPREAD ? warp * HPW + lane : tid;          // history slot of a serial thread
+    int* const pre1 = m.pre1 + warp * (NH + 1);
+    int* const pre2 = m.pre2 + warp * (NH + 1);
     const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
     const int nsum = Ltot + 2;
     const int wlen = ((Ltot + 2) + 1) & ~1;
@@ -254,6 +268,12 @@ __device__ __forceinline__ void run_lockstep() {
     }
     __syncthreads();
 
+#ifdef COAL_LS_TIMING
+    long long tS = 0, tG = 0, tQ1 = 0, tQ2 = 0, tsteps = 0, t_mark = clock64();
+#define LS_TICK(acc) do { const long long _t = clock64(); acc += _t - t_mark; t_mark = _t; } while (0)
+#else
+#define LS_TICK(acc) do { } while (0)
+#endif
 #pragma unroll 1
     for (;;) {
         int snap_flags = 0;
@@ -273,29 +293,35 @@ __device__ __forceinline__ void run_lockstep() {
                 const double pi0 = isC ? D.pi0c : D.mA1;
                 const double inv_pi0 = 1.0 / pi0;
                 int ncand;
+                double ptot = 0.0;               // sum of the candidate probabilities, index order (vectorSum, ProposalEngine.cpp:585-594)
                 if (isC) {
                     // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
                     const double pj = 0.5 * D.mA1 * D.mB2 + 0.5 * D.mB1 * D.mA2;
                     const double f = D.dtheta_e * (double)Cij;
-#pragma unroll 1
-                    for (int k = 0; k < Ltot; k++) m.pv[C::at(k, h)] = f * m.pv[C::at(k, h)] * inv_pi0;
-                    m.pv[C::at(Ltot, h)] = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
-                    m.pv[C::at(Ltot + 1, h)] = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
-                    m.pv[C::at(Ltot + 2, h)] = (Bj > 0) ? (double)(Bj * Cij) / D.mB1 : 0.0;
-                    m.pv[C::at(Ltot + 3, h)] = D.drho_e * (double)Cij * pj * inv_pi0;
+#pragma unroll 2
+                    for (int k = 0; k < Ltot; k++) { const double v = f * m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
+                    const double v0 = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
+                    const double v1 = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
+                    const double v2 = (Bj > 0) ? (double)(Bj * Cij) / D.mB1 : 0.0;
+                    const double v3 = D.drho_e * (double)Cij * pj * inv_pi0;
+                    m.pv[C::at(Ltot, h)] = v0; m.pv[C::at(Ltot + 1, h)] = v1; m.pv[C::at(Ltot + 2, h)] = v2; m.pv[C::at(Ltot + 3, h)] = v3;
+                    ptot += v0; ptot += v1; ptot += v2; ptot += v3;
                     ncand = Ltot + 4;
                     s.npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
                 } else {
-#pragma unroll 1
-                    for (int k = 0; k < Lx; k++) m.pv[C::at(k, h)] *= inv_pi0;
-                    m.pv[C::at(Lx + np, h)] = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
+#pragma unroll 2
+                    for (int k = 0; k < Lx; k++) { const double v = m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
+#pragma unroll 2
+                    for (int k = 0; k < np; k++) ptot += m.pv[C::at(Lx + k, h)];
+                    const double v0 = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
+                    m.pv[C::at(Lx + np, h)] = v0; ptot += v0;
                     ncand = Lx + np + 1;
                     s.npi += (unsigned int)(1 + Lx + 5 * np);
                 }
                 LS_ASSERT(ncand <= sP.pvmax);
                 // ---- sample the move (sampleFromVector :568-583) ----
-                double pidx, ptot;
-                const int idx = ls_pick<NH, N32>(m, h, ncand, s.rng.next(), false, pidx, ptot);
+                double pidx;
+                const int idx = ls_scan<NH, NT, N32>(m, h, ncand, s.rng.next() * ptot, false, pidx);
                 // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
                 const double qfac = (D.rate * D.hap_num * pidx) / (D.hap_den * ptot);
                 // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
@@ -322,13 +348,13 @@ __device__ __forceinline__ void run_lockstep() {
                     evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
                 }
                 double after0 = 1.0, after1 = 1.0;
-                if (nops > 0) { const int slot = ls_adjust<NH, N32>(m, h, s, og0, ow0, od0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
-                if (nops > 1) { const int slot = ls_adjust<NH, N32>(m, h, s, og1, ow1, od1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                { const int slot = ls_adjust<NH, NT, N32>(m, h, s, og0, ow0, od0, nops > 0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                { const int slot = ls_adjust<NH, NT, N32>(m, h, s, og1, ow1, od1, nops > 1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
                 if (ev_kind == 0) evc = after0;
                 else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
                 else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
                 const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
-                ls_commit<NH, N32>(m, h, s);
+                ls_commit<NH, NT, N32>(m, h, s);
                 if (s.tracing && s.nev < sA.max_events) {
                     coalgpu_event& r = sA.events[(unsigned long long)s.h * sA.max_events + s.nev];
                     r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
@@ -380,7 +406,7 @@ __device__ __forceinline__ void run_lockstep() {
                 for (int k = s.inj_lo; k < s.inj_hi; k++) {
                     const unsigned int cgk = sP.type_cg[k];
                     const int add = (int)(cgk & kCntMask);
-                    const int slot = ls_adjust<NH, N32>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
+                    const int slot = ls_adjust<NH, NT, N32>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
                     if (slot < 0) break;
                     const int now = (int)(m.cg[C::at(slot, h)] & kCntMask);
                     comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
@@ -403,7 +429,8 @@ __device__ __forceinline__ void run_lockstep() {
                 const double dthA = __ldg(&ecp->dthA), dthB = __ldg(&ecp->dthB), drho_e = __ldg(&ecp->drho);
                 // lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721)
                 const int ns0 = s.nslots;
-#pragma unroll 1
+                double hap_den = 0.0;
+#pragma unroll 2
                 for (int j = 0; j < ns0; j++) {
                     const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
                     const unsigned int c = cgj & kCntMask;
@@ -413,9 +440,10 @@ __device__ __forceinline__ void run_lockstep() {
                     else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + dthA) * (double)c;
                     else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + dthB) * (double)c;
                     m.pv[C::at(j, h)] = wgt;
+                    hap_den += wgt;
                 }
-                double hap_num, hap_den;
-                const int sx = ls_pick<NH, N32>(m, h, ns0, s.rng.next(), true, hap_num, hap_den);
+                double hap_num;
+                const int sx = ls_scan<NH, NT, N32>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
                 const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
                 const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
                 const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
@@ -461,18 +489,8 @@ __device__ __forceinline__ void run_lockstep() {
                     const typename WO::T xa = WO::narrow(xw & sP.maskA), xb = WO::narrow(xw & sP.maskB);
                     const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
                     unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
-                    if (isC) {
-                        Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16;
-#pragma unroll 1
-                        for (int j = 0; j < ns0; j++) {
-                            const unsigned int cgj = m.cg[C::at(j, h)];
-                            if ((int)(cgj >> 30) == GC) {
-                                const typename WO::T wj = m.words[C::at(j, h)];
-                                if ((wj & maskA) == xa) Ci += cgj & kCntMask;
-                                if ((wj & maskB) == xb) Cj += cgj & kCntMask;
-                            }
-                        }
-                    } else if (isA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
+                    if (isC) { Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16; }
+                    else if (isA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
 
 #ifdef COAL_TMA_ROWS
                     // Stage what this event reads from the tables -- the row of its two-locus queries (n-1 lineages for a
@@ -499,18 +517,37 @@ __device__ __forceinline__ void run_lockstep() {
                     D.crow = isC ? D.row_m1 : D.row_alt;
                     D.tma_parity = 0;
 #endif
-                    ls_adjust<NH, N32>(m, h, s, xg, xw, -1);               // H' = H - x  (:168)
-                    const int ns = s.nslots;
+                    // ONE pass over the stored types: H' = H - x (:168; the cross counts of the related slots follow, as in
+                    // ls_adjust_core with delta = -1 -- x is stored, nothing is appended), the counts of the C types that share
+                    // x's A part / B part BEFORE the removal (:149-158), and the partner list = stored types of the other
+                    // one-locus class, slot order (:300 / :377; the removal does not touch that class).
+                    const int ns = ns0;
                     const int Lx = isC ? Ltot : (isA ? LA : LB);
                     const int pg = isA ? GB : GA;
-                    // partner list = stored types of the other one-locus class, slot order (:300 / :377)
                     int np = 0;
-                    if (!isC) {
-#pragma unroll 1
+                    {
+                        const typename WO::T xwn = WO::narrow(xw);
+#pragma unroll 2
                         for (int j = 0; j < ns; j++) {
+                            const typename WO::T wj = m.words[C::at(j, h)];
                             const unsigned int cgj = m.cg[C::at(j, h)];
-                            if ((int)(cgj >> 30) == pg && (cgj & kCntMask) > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
+                            const int gj = (int)(cgj >> 30);
+                            const unsigned int cj = cgj & kCntMask;
+                            if (isC) {
+                                if (gj == GC) {
+                                    if ((wj & maskA) == xa) Ci += cj;
+                                    if ((wj & maskB) == xb) Cj += cj;
+                                } else if (gj == GA) { if (wj == xa) m.xc[C::at(j, h)] -= 1u; }
+                                else { if (wj == xb) m.xc[C::at(j, h)] -= 1u; }
+                            } else {
+                                if (gj == GC) {
+                                    if (isA) { if ((wj & maskA) == xwn) m.xc[C::at(j, h)] -= 1u; }
+                                    else { if ((wj & maskB) == xwn) m.xc[C::at(j, h)] -= 65536u; }
+                                } else if (gj == pg && cj > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
+                            }
                         }
+                        m.cg[C::at(sx, h)] -= 1u;
+                        if (isC) s.nC--; else if (isA) s.nA--; else s.nB--;
                     }
                     D.xw = xw; D.xg = xg; D.ns = ns; D.n = n; D.np = np; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = pg;
                     D.nm = isC ? 2 : 1 + Lx + np;
@@ -553,21 +590,24 @@ __device__ __forceinline__ void run_lockstep() {
             }
             m.snap[h].flags = snap_flags;
         }
-        // work lists of the query phases: exclusive prefixes of the per-history query counts (warp 0 scans; NH <= 32)
-        if (tid < 32) {
+        const int alive = __syncthreads_or((serial && !s.done) ? 1 : 0);
+        LS_TICK(tS);
+        if (!alive) break;
+        // work lists of the query phases: exclusive prefixes of the per-history query counts; every warp scans the NH counts
+        // itself (NH <= 32) into its own copy, so no further CTA barrier is needed
+        {
             int c1 = 0, c2 = 0;
-            if (tid < NH) { c1 = m.desc[tid].nm; c2 = m.desc[tid].nq; }
+            if (lane < NH) { c1 = m.desc[lane].nm; c2 = m.desc[lane].nq; }
             int i1 = c1, i2 = c2;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t1 = __shfl_up_sync(kFull, i1, o), t2 = __shfl_up_sync(kFull, i2, o);
-                if (tid >= o) { i1 += t1; i2 += t2; }
+                if (lane >= o) { i1 += t1; i2 += t2; }
             }
-            if (tid < NH) { m.pre1[tid + 1] = i1; m.pre2[tid + 1] = i2; }
-            if (tid == 0) { m.pre1[0] = 0; m.pre2[0] = 0; }
+            if (lane < NH) { pre1[lane + 1] = i1; pre2[lane + 1] = i2; }
+            if (lane == 0) { pre1[0] = 0; pre2[0] = 0; }
+            __syncwarp();
         }
-        const int alive = __syncthreads_or((serial && !s.done) ? 1 : 0);
-        if (!alive) break;
 
         // =================================== G: per-grid-point target density of closed epochs ===================================
         if (__syncthreads_or(snap_flags)) {
@@ -598,16 +638,17 @@ __device__ __forceinline__ void run_lockstep() {
             // the snapshots are rewritten in the next S phase, after the barriers of the query phases
         }
 
+        LS_TICK(tG);
         // =================================== Q1: one-locus queries, one per lane ===================================
         //  C chosen: 0 = A part, 1 = B part, rows n-1 and n (:198-238 with :120-132)
         //  A/B chosen: 0 = x (rows n-1, n-2), 1..Lx = mutants (row n-1), then one per partner b_k:
         //              pi(b_k | H'-b_k+x) on row n-1 and pi(b_k | H'-b_k) on row n-2 (:304-330 / :381-406)
         {
-            const int M1 = m.pre1[NH];
+            const int M1 = pre1[NH];
 #pragma unroll 1
             for (int it = tid; it < M1; it += NT) {
-                const int hh = ls_find<NH>(m.pre1, it);
-                const int qi = it - m.pre1[hh];
+                const int hh = ls_find<NH>(pre1, it);
+                const int qi = it - pre1[hh];
                 const LsDesc& D = m.desc[hh];
 #ifdef COAL_TMA_ROWS
                 mbar_wait(m.mbar + hh, D.tma_parity);
@@ -652,18 +693,20 @@ __device__ __forceinline__ void run_lockstep() {
             }
         }
         __syncthreads();
+        LS_TICK(tQ1);
 
         // =================================== Q2: two-locus queries, one per lane ===================================
         //  C chosen: x and its Ltot one-site mutants against H' (:169, :179-187)
         //  A/B chosen: the joined haplotype (x, b_k) against H' - b_k (:325 / :402)
         {
-            const int M2 = m.pre2[NH];
+            const int M2 = pre2[NH];
             const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
             unsigned int* mine = m.scratch + tid;          // histogram / class list of this lane: element i at mine[i * NT]
+            const bool dense = (LA + 1) * (LB + 1) <= kLsDenseMax;   // uniform over the launch (one locus pair)
 #pragma unroll 1
             for (int it = tid; it < M2; it += NT) {
-                const int hh = ls_find<NH>(m.pre2, it);
-                const int qi = it - m.pre2[hh];
+                const int hh = ls_find<NH>(pre2, it);
+                const int qi = it - pre2[hh];
                 const LsDesc& D = m.desc[hh];
                 const bool isC = (D.xg == GC);
                 const int ns = D.ns;
@@ -691,37 +734,63 @@ __device__ __forceinline__ void run_lockstep() {
                         mine[sidx * NT] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
                     }
                 }
-                // compact the classes in place (ascending dA+dB) and collect the totals
+                const double* __restrict__ row = D.crow;
+                auto ldmy = [row](int k) {
+                    const double2 v = kStaged ? *reinterpret_cast<const double2*>(row + 2 * k) : __ldg(reinterpret_cast<const double2*>(row + 2 * k));
+                    MYPair e; e.m = v.x; e.y = v.y; return e;
+                };
                 int nH = 0;
                 ClassTotals tot; tot.n = 0; tot.ncompA = 0; tot.ncompB = 0;
+                double pi;
+                if (dense) {
+                    // short loci: scatter the classes (ascending dA+dB) into the two distance vectors, collect the totals and
+                    // the term of the classes ancestral at both loci; then the (LA+1)(LB+1) bilinear form (coal_math.h)
+                    unsigned int* vecA = mine + nsum * NT;
+                    unsigned int* vecB = vecA + (LA + 1) * NT;
 #pragma unroll 1
-                for (int sidx = 0; sidx < nsum; sidx++) {
-                    const unsigned int v = mine[sidx * NT];
-                    const unsigned int cnt = v & 0xffffu;
-                    if (cnt) {
-                        const unsigned int rep = v >> 16;
-                        int dA, dB;
-                        if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
-                        mine[nH * NT] = pack_class(cnt, dA, dB);
-                        nH++;
-                        tot.n += cnt;
-                        if (dA >= 0) tot.ncompA += cnt;
-                        if (dB >= 0) tot.ncompB += cnt;
+                    for (int i = 0; i < nsum; i++) vecA[i * NT] = 0u;
+                    double t2 = 0.0;
+#pragma unroll 1
+                    for (int sidx = 0; sidx < nsum; sidx++) {
+                        const unsigned int v = mine[sidx * NT];
+                        const unsigned int cnt = v & 0xffffu;
+                        if (cnt) {
+                            const unsigned int rep = v >> 16;
+                            int dA, dB;
+                            if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
+                            nH++;
+                            tot.n += cnt;
+                            if (dA >= 0) { tot.ncompA += cnt; vecA[dA * NT] += cnt | (dB < 0 ? cnt << 16 : 0u); }
+                            if (dB >= 0) { tot.ncompB += cnt; vecB[dB * NT] += cnt | (dA < 0 ? cnt << 16 : 0u); }
+                            if (dA >= 0 && dB >= 0) t2 += (double)cnt * ldmy(dA * sP.SB + dB).y;
+                        }
                     }
+                    if (D.cn == 0 || nH == 0) pi = sP.pow2negL;      // empty configuration, ConditionalSamplingHMM.cpp:277-298
+                    else pi = pismc_bilinear_dense(ldmy, sP.SB, LA, LB, vecA, vecB, NT, t2, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB),
+                                                   __ldg(sP.rcp + tot.n), sP.pow2negLA, sP.pow2negLB);
+                } else {
+                    // compact the classes in place (ascending dA+dB) and collect the totals
+#pragma unroll 1
+                    for (int sidx = 0; sidx < nsum; sidx++) {
+                        const unsigned int v = mine[sidx * NT];
+                        const unsigned int cnt = v & 0xffffu;
+                        if (cnt) {
+                            const unsigned int rep = v >> 16;
+                            int dA, dB;
+                            if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
+                            mine[nH * NT] = pack_class(cnt, dA, dB);
+                            nH++;
+                            tot.n += cnt;
+                            if (dA >= 0) tot.ncompA += cnt;
+                            if (dB >= 0) tot.ncompB += cnt;
+                        }
+                    }
+                    // ---- pi_SMC as a bilinear form over the class list (coal_math.h) ----
+                    if (D.cn == 0 || nH == 0) pi = sP.pow2negL;
+                    else pi = pismc_bilinear(ldmy, sP.SB, LA, LB, mine, NT, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB),
+                                             __ldg(sP.rcp + tot.n), sP.pow2negLA, sP.pow2negLB);
                 }
                 nh_lane += (unsigned int)nH;
-                // ---- pi_SMC as a bilinear form (coal_math.h) ----
-                double pi;
-                if (D.cn == 0 || nH == 0) pi = sP.pow2negL;      // empty configuration, ConditionalSamplingHMM.cpp:277-298
-                else {
-                    const double* __restrict__ row = D.crow;
-                    auto ldmy = [row](int k) {
-                        const double2 v = kStaged ? *reinterpret_cast<const double2*>(row + 2 * k) : __ldg(reinterpret_cast<const double2*>(row + 2 * k));
-                        MYPair e; e.m = v.x; e.y = v.y; return e;
-                    };
-                    pi = pismc_bilinear(ldmy, sP.SB, LA, LB, mine, NT, nH, tot, __ldg(sP.rcp + tot.ncompA), __ldg(sP.rcp + tot.ncompB),
-                                        __ldg(sP.rcp + tot.n), sP.pow2negLA, sP.pow2negLB);
-                }
                 if (isC) { if (qi == 0) m.desc[hh].pi0c = pi; else m.pv[C::at(qi - 1, hh)] = pi; }
                 else {
                     // joint: 0.5 [pi(x|H'-b) pi(b|H'-b+x) + pi(b|H'-b) pi(x|H')]   (:326 / :403 with :120-132)
@@ -732,7 +801,18 @@ __device__ __forceinline__ void run_lockstep() {
             }
         }
         __syncthreads();
+        LS_TICK(tQ2);
+#ifdef COAL_LS_TIMING
+        tsteps++;
+#endif
     }
+#ifdef COAL_LS_TIMING
+    if (tid == 0) {     // phase clocks of this CTA (cycles between the barriers, as seen by thread 0) and its step count
+        atomicAdd(sA.counters + 10, (unsigned long long)tS); atomicAdd(sA.counters + 11, (unsigned long long)tG);
+        atomicAdd(sA.counters + 12, (unsigned long long)tQ1); atomicAdd(sA.counters + 13, (unsigned long long)tQ2);
+        atomicAdd(sA.counters + 14, (unsigned long long)tsteps);
+    }
+#endif
 
     // work counters of the launch
     unsigned int nh_warp = warp_sum_u(nh_lane);
@@ -746,25 +826,27 @@ __device__ __forceinline__ void run_lockstep() {
 
 }  // namespace
 
-// The launch: persistent CTAs of 4 * NH threads pull history indices from a global counter until the batch is drawn.
-#ifndef COAL_LS_MIN_CTAS_16
-#define COAL_LS_MIN_CTAS_16 6
+// The launch: persistent CTAs of NT threads and NH histories pull history indices from a global counter until the batch is drawn.
+// Shapes (NH, NT): (16, 64), (32, 64), (32, 128).
+#ifndef COAL_LS_MIN_CTAS_64
+#define COAL_LS_MIN_CTAS_64 6
 #endif
-#ifndef COAL_LS_MIN_CTAS_32
-#define COAL_LS_MIN_CTAS_32 3
+#ifndef COAL_LS_MIN_CTAS_128
+#define COAL_LS_MIN_CTAS_128 3
 #endif
-template <int NH, bool N32>
-__global__ void __launch_bounds__(4 * NH, NH == 16 ? COAL_LS_MIN_CTAS_16 : COAL_LS_MIN_CTAS_32)
+template <int NH, int NT, bool N32>
+__global__ void __launch_bounds__(NT, NT == 64 ? COAL_LS_MIN_CTAS_64 : COAL_LS_MIN_CTAS_128)
 history_lockstep_kernel(const DevProblem P, const SampleArgs A) {
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
-    run_lockstep<NH, N32>();
+    run_lockstep<NH, NT, N32>();
 }
 
-history_kernel_fn history_lockstep_select(int NH, bool narrow) {
-    if (narrow) return NH == 16 ? history_lockstep_kernel<16, true> : history_lockstep_kernel<32, true>;
-    return NH == 16 ? history_lockstep_kernel<16, false> : history_lockstep_kernel<32, false>;
+history_kernel_fn history_lockstep_select(int NH, int NT, bool narrow) {
+    if (NH == 16) return narrow ? history_lockstep_kernel<16, 64, true> : history_lockstep_kernel<16, 64, false>;
+    if (NT == 64) return narrow ? history_lockstep_kernel<32, 64, true> : history_lockstep_kernel<32, 64, false>;
+    return narrow ? history_lockstep_kernel<32, 128, true> : history_lockstep_kernel<32, 128, false>;
 }
-size_t history_lockstep_bytes(int NH, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
-    return ls_layout(NH, kmax, pvmax, Ltot, stage_doubles, narrow).total;
+size_t history_lockstep_bytes(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+    return ls_layout(NH, NT, kmax, pvmax, Ltot, stage_doubles, narrow).total;
 }

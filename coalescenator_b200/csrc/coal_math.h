@@ -89,24 +89,24 @@ template <class LoadMY>
 COAL_HD double pismc_bilinear(LoadMY ldmy, int SB, int LA, int LB, const uint32_t* cls, int cstride, int nH,
                               ClassTotals tot, double invA, double invB, double inv_n, double pow2negLA, double pow2negLB) {
     if (tot.ncompA != 0 && tot.ncompB != 0) {
+        // Branch-free in the class kinds: a class that is not ancestral at A (B) enters with weight 0 and distance 0, so
+        // the lanes of a warp -- one query each -- run the same nH x nH instruction sequence (adding 0 * M changes no sum).
         double t1 = 0.0, ty = 0.0;
         for (int k = 0; k < nH; k++) {
             const uint32_t v = cls[k * cstride];
-            const int dA = (int)((v >> 16) & 0xffu) - 1;
-            if (dA < 0) continue;                                   // B-only class: enters through the k2 loop of the others
-            const double c = (double)(v & 0xffffu);
-            const double fk = (v >> 24) == 0 ? invB : 0.0;          // A-only class: mean B emission of CB (T3)
-            const int rowoff = dA * SB;
+            const uint32_t a1 = (v >> 16) & 0xffu, b1 = v >> 24;
+            const double c = a1 ? (double)(v & 0xffffu) : 0.0;      // B-only class: enters through the k2 loop of the others
+            const double fk = b1 == 0 ? invB : 0.0;                  // A-only class: mean B emission of CB (T3)
+            const int rowoff = (a1 ? (int)a1 - 1 : 0) * SB;
             double sm = 0.0, sy = 0.0;
             for (int k2 = 0; k2 < nH; k2++) {
                 const uint32_t v2 = cls[k2 * cstride];
-                const int dB2 = (int)(v2 >> 24) - 1;
-                if (dB2 < 0) continue;
-                const double c2 = (double)(v2 & 0xffffu);
-                const MYPair e = ldmy(rowoff + dB2);
+                const uint32_t a2 = (v2 >> 16) & 0xffu, b2 = v2 >> 24;
+                const double c2 = b2 ? (double)(v2 & 0xffffu) : 0.0;
+                const MYPair e = ldmy(rowoff + (b2 ? (int)b2 - 1 : 0));
                 sm += c2 * e.m;
-                const double f = fk + (((v2 >> 16) & 0xffu) == 0 ? invA : 0.0);   // B-only partner: mean A emission of CA (T4)
-                sy += (k2 == k ? 1.0 : c2 * f) * e.y;               // k2 == k: the class itself, ancestral at both loci (T2)
+                const double f = fk + (a2 == 0 ? invA : 0.0);        // B-only partner: mean A emission of CA (T4)
+                sy += (k2 == k ? (b2 ? 1.0 : 0.0) : c2 * f) * e.y;   // k2 == k: the class itself, ancestral at both loci (T2)
             }
             t1 += c * sm; ty += c * sy;
         }
@@ -132,6 +132,50 @@ COAL_HD double pismc_bilinear(LoadMY ldmy, int SB, int LA, int LB, const uint32_
         const double c = (double)(v & 0xffffu);
         const MYPair e = ldmy(dA * SB + LB + 1);
         sm += c * e.m; sy += c * e.y;
+    }
+    return pow2negLB * (sm * invA + sy * inv_n);
+}
+
+// Dense form of the same expression, for short loci: the classes are first scattered into two count vectors over distances,
+//   vecA[dA] = cA | aAo << 16   lineages in classes ancestral at A with distance dA | of these, in A-only classes
+//   vecB[dB] = cB | bBo << 16   likewise for B
+// and t2 = sum over the classes ancestral at both loci of c_k Y[dA_k][dB_k] (T2) is collected on the way. Then
+//   pi = invA invB sum_{dA,dB} cA cB M + ( t2 + invB sum_{dA,dB} aAo cB Y + invA sum_{dA,dB} cA bBo Y ) / n
+// in (LA+1)(LB+1) iterations whatever the class list looks like: the lanes of a warp -- one query each, all of the same
+// locus pair -- run the same trip count, where the class-list form makes every lane wait for the longest list squared.
+template <class LoadMY>
+COAL_HD double pismc_bilinear_dense(LoadMY ldmy, int SB, int LA, int LB, const uint32_t* vecA, const uint32_t* vecB, int vstride,
+                                    double t2, ClassTotals tot, double invA, double invB, double inv_n, double pow2negLA, double pow2negLB) {
+    if (tot.ncompA != 0 && tot.ncompB != 0) {
+        double t1 = 0.0, ty = 0.0;
+        for (int dA = 0; dA <= LA; dA++) {
+            const uint32_t va = vecA[dA * vstride];
+            const double ca = (double)(va & 0xffffu), ao = (double)(va >> 16);
+            double sm = 0.0, s3 = 0.0, s4 = 0.0;
+            for (int dB = 0; dB <= LB; dB++) {
+                const uint32_t vb = vecB[dB * vstride];
+                const double cb = (double)(vb & 0xffffu), bo = (double)(vb >> 16);
+                const MYPair e = ldmy(dA * SB + dB);
+                sm += cb * e.m; s3 += cb * e.y; s4 += bo * e.y;
+            }
+            t1 += ca * sm;
+            ty += ao * s3 * invB + ca * s4 * invA;
+        }
+        return t1 * invA * invB + (t2 + ty) * inv_n;
+    }
+    double sm = 0.0, sy = 0.0;
+    if (tot.ncompA == 0) {
+        for (int dB = 0; dB <= LB; dB++) {
+            const double cb = (double)(vecB[dB * vstride] & 0xffffu);
+            const MYPair e = ldmy((LA + 1) * SB + dB);
+            sm += cb * e.m; sy += cb * e.y;
+        }
+        return pow2negLA * (sm * invB + sy * inv_n);
+    }
+    for (int dA = 0; dA <= LA; dA++) {
+        const double ca = (double)(vecA[dA * vstride] & 0xffffu);
+        const MYPair e = ldmy(dA * SB + LB + 1);
+        sm += ca * e.m; sy += ca * e.y;
     }
     return pow2negLB * (sm * invA + sy * inv_n);
 }

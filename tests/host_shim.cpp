@@ -66,7 +66,8 @@ double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int3
         return marginal_finish(num, ncomp, nH > 0 ? (uint32_t)n_all : 0u, gamma == 0 ? p2A : p2B, wsum);
     }
     if (nH == 0) return p2A * p2B;
-    (void)p;   // the interval axis is summed out of the bilinear form: nothing left to split over lanes
+    // the interval axis is summed out of the bilinear form: nothing left to split over lanes; p selects the class-list form
+    // (p != 2) or the dense form of the lockstep kernel (p == 2)
     std::vector<uint32_t> cls(nH);
     ClassTotals tot{0, 0, 0};
     for (int k = 0; k < nH; k++) {
@@ -75,6 +76,17 @@ double hs_pismc(void* hp, int gamma, int n_all, int time_idx, int nH, const int3
     }
     const double* drow = t.dev_row(t.set_of_epoch[time_idx], n_all);
     auto ldmy = [drow](int k) { MYPair e; e.m = drow[2 * k]; e.y = drow[2 * k + 1]; return e; };
+    if (p == 2) {
+        std::vector<uint32_t> vecA(lay.LA + 1, 0), vecB(lay.LB + 1, 0);
+        double t2 = 0;
+        for (int k = 0; k < nH; k++) {
+            if (dA[k] >= 0) vecA[dA[k]] += (uint32_t)cnt[k] | (dB[k] < 0 ? (uint32_t)cnt[k] << 16 : 0u);
+            if (dB[k] >= 0) vecB[dB[k]] += (uint32_t)cnt[k] | (dA[k] < 0 ? (uint32_t)cnt[k] << 16 : 0u);
+            if (dA[k] >= 0 && dB[k] >= 0) t2 += (double)cnt[k] * ldmy(dA[k] * lay.dev_sb + dB[k]).y;
+        }
+        return pismc_bilinear_dense(ldmy, lay.dev_sb, lay.LA, lay.LB, vecA.data(), vecB.data(), 1, t2, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0,
+                                    tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, 1.0 / (double)tot.n, p2A, p2B);
+    }
     return pismc_bilinear(ldmy, lay.dev_sb, lay.LA, lay.LB, cls.data(), 1, nH, tot, tot.ncompA ? 1.0 / (double)tot.ncompA : 0.0,
                           tot.ncompB ? 1.0 / (double)tot.ncompB : 0.0, 1.0 / (double)tot.n, p2A, p2B);
 }
