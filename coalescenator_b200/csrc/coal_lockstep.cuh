@@ -140,21 +140,26 @@ __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long l
     const typename WO::T wa = w & maskA, wb = w & maskB;
     int found = -1;
     unsigned int newxc = 0;
-#pragma unroll 1
+    // The related slots as two match rules (class, mask, key) -> (cross-count change, contribution to a new slot's cross
+    // counts), so that the loop body is the same instruction sequence whatever g is: the histories of a warp change types of
+    // different classes at the same time, and a branch per class would run one class after the other.
+    //   g = A: C slots with this A part (count of their A part += delta)        g = B: C slots with this B part (<< 16)
+    //   g = C: the A slot of its A part and the B slot of its B part (C lineages carrying it += delta)
+    const int t1 = (g == GC) ? GA : GC, t2 = (g == GC) ? GB : 3;
+    const typename WO::T m1 = (g == GA) ? maskA : (g == GB) ? maskB : (typename WO::T)~(typename WO::T)0;
+    const typename WO::T k1 = (g == GC) ? wa : w, k2 = wb;
+    const unsigned int d1 = (g == GB) ? (unsigned int)(delta * 65536) : (unsigned int)delta, d2 = (unsigned int)delta;
+#pragma unroll 2
     for (int j = 0; j < ns; j++) {
         const typename WO::T wj = m.words[C::at(j, h)];
         const unsigned int cgj = m.cg[C::at(j, h)];
         const int gj = (int)(cgj >> 30);
         const unsigned int cj = cgj & kCntMask;
         if (gj == g && wj == w) found = j;
-        if (g == GA) {
-            if (gj == GC && (wj & maskA) == w) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj; }
-        } else if (g == GB) {
-            if (gj == GC && (wj & maskB) == w) { m.xc[C::at(j, h)] += (unsigned int)(delta * 65536); newxc += cj; }
-        } else {
-            if (gj == GA && wj == wa) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj; }
-            if (gj == GB && wj == wb) { m.xc[C::at(j, h)] += (unsigned int)delta; newxc += cj << 16; }
-        }
+        const bool h1 = (gj == t1) && ((wj & m1) == k1), h2 = (gj == t2) && (wj == k2);
+        const unsigned int xadd = (h1 ? d1 : 0u) + (h2 ? d2 : 0u);
+        if (xadd) m.xc[C::at(j, h)] += xadd;
+        newxc += (h1 ? cj : 0u) + (h2 ? (cj << 16) : 0u);
     }
     if (!active) return -2;
     int ret = found;
@@ -435,10 +440,15 @@ __device__ __forceinline__ void run_lockstep() {
                     const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
                     const unsigned int c = cgj & kCntMask;
                     const int gj = (int)(cgj >> 30);
-                    double wgt;
-                    if (gj == GC) wgt = ((((double)(c - 1) + (dthA + dthB)) + drho_e) + (double)(xcj & 0xffffu) + (double)(xcj >> 16)) * (double)c;
-                    else if (gj == GA) wgt = ((double)(c - 1 + (unsigned int)s.nB + xcj) + dthA) * (double)c;
-                    else wgt = ((double)(c - 1 + (unsigned int)s.nA + xcj) + dthB) * (double)c;
+                    // one instruction sequence for the three classes (adding 0.0 to a non-negative sum is exact):
+                    //   C: (c-1 + thA+thB + rho + cA + cB) c     A: (c-1 + nB + cCa + thA) c     B: (c-1 + nA + cCb + thB) c
+                    const bool jC = (gj == GC);
+                    const unsigned int ti = c - 1 + (jC ? 0u : ((gj == GA ? (unsigned int)s.nB : (unsigned int)s.nA) + xcj));
+                    double v = (double)ti + (jC ? (dthA + dthB) : (gj == GA ? dthA : dthB));
+                    v = v + (jC ? drho_e : 0.0);
+                    v = v + (jC ? (double)(xcj & 0xffffu) : 0.0);
+                    v = v + (jC ? (double)(xcj >> 16) : 0.0);
+                    const double wgt = v * (double)c;
                     m.pv[C::at(j, h)] = wgt;
                     hap_den += wgt;
                 }
@@ -527,24 +537,24 @@ __device__ __forceinline__ void run_lockstep() {
                     int np = 0;
                     {
                         const typename WO::T xwn = WO::narrow(xw);
+                        // match rules of the removal (see ls_adjust_core): which slots' cross counts lose one
+                        const int t1 = isC ? GA : GC, t2 = isC ? GB : 3;
+                        const typename WO::T m1 = isA ? maskA : (isC ? (typename WO::T)~(typename WO::T)0 : maskB);
+                        const typename WO::T k1 = isC ? xa : xwn;
+                        const unsigned int d1 = (!isC && !isA) ? 65536u : 1u;
 #pragma unroll 2
                         for (int j = 0; j < ns; j++) {
                             const typename WO::T wj = m.words[C::at(j, h)];
                             const unsigned int cgj = m.cg[C::at(j, h)];
                             const int gj = (int)(cgj >> 30);
                             const unsigned int cj = cgj & kCntMask;
-                            if (isC) {
-                                if (gj == GC) {
-                                    if ((wj & maskA) == xa) Ci += cj;
-                                    if ((wj & maskB) == xb) Cj += cj;
-                                } else if (gj == GA) { if (wj == xa) m.xc[C::at(j, h)] -= 1u; }
-                                else { if (wj == xb) m.xc[C::at(j, h)] -= 1u; }
-                            } else {
-                                if (gj == GC) {
-                                    if (isA) { if ((wj & maskA) == xwn) m.xc[C::at(j, h)] -= 1u; }
-                                    else { if ((wj & maskB) == xwn) m.xc[C::at(j, h)] -= 65536u; }
-                                } else if (gj == pg && cj > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
-                            }
+                            const bool jC = (gj == GC);
+                            Ci += (isC && jC && (wj & maskA) == xa) ? cj : 0u;
+                            Cj += (isC && jC && (wj & maskB) == xb) ? cj : 0u;
+                            const bool h1 = (gj == t1) && ((wj & m1) == k1), h2 = (gj == t2) && (wj == xb);
+                            const unsigned int xsub = (h1 ? d1 : 0u) + (h2 ? 1u : 0u);
+                            if (xsub) m.xc[C::at(j, h)] -= xsub;
+                            if (!isC && gj == pg && cj > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
                         }
                         m.cg[C::at(sx, h)] -= 1u;
                         if (isC) s.nC--; else if (isA) s.nA--; else s.nB--;

@@ -1,0 +1,14 @@
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_ls4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_ls4.log; tail -12 gpurun_out/r2_pytest_ls4.log
+B="timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e"
+$B > gpurun_out/r2_e_def.json 2> gpurun_out/r2_e_def.err
+for v in nospread; do COALGPU_LIB=/root/repo/variants/$v.so $B > gpurun_out/r2_e_$v.json 2> gpurun_out/r2_e_$v.err; done
+COALGPU_LOCKSTEP_NH=32 COALGPU_LOCKSTEP_NT=128 $B > gpurun_out/r2_e_32128.json 2> gpurun_out/r2_e_32128.err
+COALGPU_LOCKSTEP_NH=32 COALGPU_LOCKSTEP_NT=64 $B > gpurun_out/r2_e_3264.json 2> gpurun_out/r2_e_3264.err
+for v in def nospread 32128 3264; do python -c "
+import json
+try:
+    d=json.loads(open('gpurun_out/r2_e_$v.json').read().strip().splitlines()[-1])
+    print('$v', round(d['value']), round(d['roofline']['kernel_ms'],1))
+except Exception as e: print('$v', 'FAILED', e)
+"; done
+COALGPU_LIB=/root/repo/variants/timing.so python scripts_tmp/phase_clocks.py 16 2 11
