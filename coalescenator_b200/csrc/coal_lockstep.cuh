@@ -676,20 +676,20 @@ __device__ __forceinline__ void run_lockstep() {
                 const double* __restrict__ wE2 = D.row_alt + offw;
                 const typename WO::T mask = WO::narrow((qg == GA) ? sP.maskA : sP.maskB), qw = WO::narrow(qw64);
                 double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
-#pragma unroll 1
+                // branch-free: the lanes of a warp walk the slots of different histories (different classes at the same j); a
+                // slot that is not ancestral at the query's locus enters with count 0 (adding 0 * wE changes no sum)
+#pragma unroll 2
                 for (int j = 0; j < ns; j++) {
                     const typename WO::T wj = m.words[C::at(j, hh)];
                     const unsigned int cgj = m.cg[C::at(j, hh)];
                     const int gj = (int)(cgj >> 30);
-                    unsigned int c = cgj & kCntMask;
-                    if (gj == qg || gj == GC) {
-                        if (excl && gj == qg && wj == qw) c -= 1;
-                        const int d = WO::popc((wj ^ qw) & mask);
-                        const double cf = (double)c;
-                        num1 += cf * tab_ld(wE1 + d);
-                        num2 += cf * tab_ld(wE2 + d);
-                        ncomp += c;
-                    }
+                    const bool rel = (gj == qg) || (gj == GC);
+                    const unsigned int c = rel ? (cgj & kCntMask) - ((excl && gj == qg && wj == qw) ? 1u : 0u) : 0u;
+                    const int d = WO::popc((wj ^ qw) & mask);
+                    const double cf = (double)c;
+                    num1 += cf * tab_ld(wE1 + d);
+                    num2 += cf * tab_ld(wE2 + d);
+                    ncomp += c;
                 }
                 // fp64 division is a ~25-instruction sequence: reciprocals of lineage counts come from a table
                 const double inv_nc = __ldg(sP.rcp + ncomp);
@@ -727,22 +727,22 @@ __device__ __forceinline__ void run_lockstep() {
                 const typename WO::T qw = WO::narrow(qw64), delw = WO::narrow(delw64);
 #pragma unroll 1
                 for (int sidx = 0; sidx < nsum; sidx++) mine[sidx * NT] = 0xffff0000u;
-#pragma unroll 1
+                // branch-free (see Q1): a slot without lineages (the removed x, the left-out partner) adds count 0 and leaves
+                // the class representative alone
+#pragma unroll 2
                 for (int j = 0; j < ns; j++) {
                     const typename WO::T wj = m.words[C::at(j, hh)];
                     const unsigned int cgj = m.cg[C::at(j, hh)];
                     const int gj = (int)(cgj >> 30);
-                    unsigned int c = cgj & kCntMask;
-                    if (gj == delg && wj == delw) c -= 1;
-                    if (c > 0) {
-                        const typename WO::T y = wj ^ qw;
-                        const int da = WO::popc(y & maskA), db = WO::popc(y & maskB);
-                        int sidx; unsigned int rep;
-                        if (gj == GA) { sidx = da; rep = 0; } else if (gj == GB) { sidx = db; rep = 1; } else { sidx = da + db + 1; rep = 2 + da; }
-                        LS_ASSERT(sidx < nsum);
-                        const unsigned int v = mine[sidx * NT];
-                        mine[sidx * NT] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
-                    }
+                    const unsigned int c = (cgj & kCntMask) - ((gj == delg && wj == delw) ? 1u : 0u);
+                    const typename WO::T y = wj ^ qw;
+                    const int da = WO::popc(y & maskA), db = WO::popc(y & maskB);
+                    const bool jA = (gj == GA), jB = (gj == GB);
+                    const int sidx = jA ? da : (jB ? db : da + db + 1);
+                    const unsigned int rep = c ? (jA ? 0u : (jB ? 1u : 2u + (unsigned int)da)) : 0xffffu;
+                    LS_ASSERT(sidx < nsum);
+                    const unsigned int v = mine[sidx * NT];
+                    mine[sidx * NT] = ((v & 0xffffu) + c) | (min(v >> 16, rep) << 16);
                 }
                 const double* __restrict__ row = D.crow;
                 auto ldmy = [row](int k) {

@@ -1,10 +1,10 @@
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_ls5.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_ls5.log; tail -12 gpurun_out/r2_pytest_ls5.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_ls6.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_ls6.log; tail -12 gpurun_out/r2_pytest_ls6.log
 B="timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e"
-$B > gpurun_out/r2_f_def.json 2> gpurun_out/r2_f_def.err
+$B > gpurun_out/r2_g_def.json 2> gpurun_out/r2_g_def.err
 for v in def; do python -c "
 import json
 try:
-    d=json.loads(open('gpurun_out/r2_f_$v.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/r2_g_$v.json').read().strip().splitlines()[-1])
     print('$v', round(d['value']), round(d['roofline']['kernel_ms'],1))
 except Exception as e: print('$v', 'FAILED', e)
 "; done
