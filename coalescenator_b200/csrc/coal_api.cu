@@ -642,6 +642,69 @@ int coalgpu_capacity_stats(coalgpu_sampler* s, uint64_t* n_deferred, uint32_t* s
     return 0;
 }
 
+// Parity seam of the device EVENT code (VERDICT r1 task 5): the given configurations go through the history kernel's own
+// phases -- removal of the chosen lineage, partner list, one-locus and two-locus queries, candidate assembly -- and the
+// unnormalised proposal probabilities of every backward move come back instead of a move being drawn.
+int coalgpu_score_events(coalgpu_sampler* s, int64_t n_cfg, const int32_t* cfg_offsets, const uint8_t* gamma, const uint64_t* words,
+                         const uint32_t* counts, const uint8_t* chosen_gamma, const uint64_t* chosen_words, const int32_t* epochs,
+                         int32_t max_cand, double* out_pv, uint64_t* out_partner_words, int32_t* out_ncand) {
+    if (!s || !cfg_offsets || !gamma || !words || !counts || !chosen_gamma || !chosen_words || !epochs || !out_pv || !out_partner_words || !out_ncand)
+        return fail(COALGPU_EINVAL, "null argument");
+    if (n_cfg <= 0) return 0;
+    if (!s->ls) return fail(COALGPU_EINVAL, "coalgpu_score_events runs the lockstep form of the history kernel (unset COALGPU_KERNEL / COALGPU_GROUP)");
+    if (max_cand < 1) return fail(COALGPU_EINVAL, "max_cand must be positive");
+    const uint64_t maskA = s->P.maskA, maskB = s->P.maskB;
+    for (int64_t q = 0; q < n_cfg; q++) {
+        if (cfg_offsets[q + 1] < cfg_offsets[q] || cfg_offsets[0] != 0) return fail(COALGPU_EINVAL, "cfg_offsets must start at 0 and be non-decreasing");
+        if (epochs[q] < 0 || epochs[q] >= s->T) return fail(COALGPU_EINVAL, "epoch out of range");
+        long long n = 0; bool has = false;
+        if (cfg_offsets[q + 1] - cfg_offsets[q] > s->P.kmax) return fail(COALGPU_EINVAL, "configuration has more types than the sampler's type store");
+        for (int k = cfg_offsets[q]; k < cfg_offsets[q + 1]; k++) {
+            if (gamma[k] > 2 || counts[k] == 0) return fail(COALGPU_EINVAL, "bad type record");
+            const uint64_t allowed = gamma[k] == COALGPU_GAMMA_A ? maskA : (gamma[k] == COALGPU_GAMMA_B ? maskB : (maskA | maskB));
+            if (words[k] & ~allowed) return fail(COALGPU_EINVAL, "haplotype word has bits outside its loci");
+            n += counts[k];
+            has = has || (gamma[k] == chosen_gamma[q] && words[k] == chosen_words[q]);
+        }
+        if (!has) return fail(COALGPU_EINVAL, "the chosen lineage is not in its configuration");
+        if (n < 1 || n > s->tab.n_max) return fail(COALGPU_EINVAL, "configuration has more lineages than the sampler's tables cover");
+    }
+    CU_OK(cudaSetDevice(s->device));
+    const size_t nt = (size_t)cfg_offsets[n_cfg];
+    std::vector<void*> tmp;
+    auto freeall = [&]() { for (void* p : tmp) dev_free(p); };
+    int *d_off = nullptr, *d_ep = nullptr, *d_nc = nullptr; unsigned char *d_g = nullptr, *d_xg = nullptr;
+    unsigned long long *d_w = nullptr, *d_xw = nullptr, *d_pw = nullptr; unsigned int* d_c = nullptr; double* d_pv = nullptr;
+#define SC_TMP(ptr, bytes, src) do { cudaError_t _e = dev_alloc((void**)&ptr, std::max<size_t>(bytes, 8)); if (_e == cudaSuccess) { tmp.push_back(ptr); if (src) _e = cudaMemcpy(ptr, src, bytes, cudaMemcpyHostToDevice); } if (_e != cudaSuccess) { freeall(); return fail(COALGPU_ECUDA, cudaGetErrorString(_e)); } } while (0)
+    SC_TMP(d_off, (size_t)(n_cfg + 1) * 4, cfg_offsets); SC_TMP(d_g, nt, gamma); SC_TMP(d_w, nt * 8, words); SC_TMP(d_c, nt * 4, counts);
+    SC_TMP(d_xg, (size_t)n_cfg, chosen_gamma); SC_TMP(d_xw, (size_t)n_cfg * 8, chosen_words); SC_TMP(d_ep, (size_t)n_cfg * 4, epochs);
+    SC_TMP(d_pv, (size_t)n_cfg * max_cand * 8, (const void*)nullptr); SC_TMP(d_pw, (size_t)n_cfg * max_cand * 8, (const void*)nullptr);
+    SC_TMP(d_nc, (size_t)n_cfg * 4, (const void*)nullptr);
+#undef SC_TMP
+    cudaError_t e = cudaMemset(d_nc, 0xff, (size_t)n_cfg * 4);          // -1: not scored (type store overflow)
+    if (e == cudaSuccess) e = cudaMemset(d_pv, 0, (size_t)n_cfg * max_cand * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        SampleArgs a{};
+        a.n = (unsigned long long)n_cfg; a.counters = s->d_counters;
+        a.score_off = d_off; a.score_g = d_g; a.score_w = d_w; a.score_c = d_c; a.score_xg = d_xg; a.score_xw = d_xw; a.score_epoch = d_ep;
+        a.score_pv = d_pv; a.score_pw = d_pw; a.score_ncand = d_nc; a.score_stride = max_cand;
+        const int NH = s->group & 0xff, NT = s->group >> 8;
+        int grid = (int)std::min<long long>(s->grid, (n_cfg + NH - 1) / NH);
+        history_kernel_fn kfn = history_lockstep_select(NH, NT, s->P.Ltot <= 32);
+        kfn<<<std::max(grid, 1), NT, s->smem_bytes, 0>>>(s->P, a);
+        g_launches++;
+        e = cudaGetLastError();
+        s->last_stream = 0;
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_pv, d_pv, (size_t)n_cfg * max_cand * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_partner_words, d_pw, (size_t)n_cfg * max_cand * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_ncand, d_nc, (size_t)n_cfg * 4, cudaMemcpyDeviceToHost);
+    freeall();
+    if (e != cudaSuccess) return fail(COALGPU_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
 // Debug builds with -DCOAL_LS_TIMING: phase clocks of the lockstep kernel (cycles in S, G, Q1, Q2 summed over CTAs, steps).
 int coalgpu_phase_clocks(coalgpu_sampler* s, uint64_t* out5) {
     if (!s || !out5) return fail(COALGPU_EINVAL, "null argument");

@@ -71,6 +71,14 @@ struct SampleArgs {
     unsigned long long* defer_list;
     const unsigned long long* list;
     const unsigned long long* list_count;
+    // Score mode (coalgpu_score_events, the parity seam of the device event code): "history" h is the given configuration
+    // h -- its type list is loaded instead of the sampled lineages, the given lineage is chosen instead of drawn, ONE event is
+    // scored through the same phases as a drawn event, and the unnormalised candidate probabilities are written out instead
+    // of a move being drawn. score_off == nullptr everywhere else.
+    const int* score_off;                 // [n+1] ranges into the three arrays below
+    const unsigned char* score_g; const unsigned long long* score_w; const unsigned int* score_c;
+    const unsigned char* score_xg; const unsigned long long* score_xw; const int* score_epoch;   // [n] chosen lineage, epoch
+    double* score_pv; unsigned long long* score_pw; int* score_ncand; int score_stride;          // [n*stride], [n*stride], [n]
 };
 
 #ifndef COAL_PHILOX_UNROLL

@@ -324,6 +324,18 @@ __device__ __forceinline__ void run_lockstep() {
                     s.npi += (unsigned int)(1 + Lx + 5 * np);
                 }
                 LS_ASSERT(ncand <= sP.pvmax);
+                if (sA.score_off) {
+                    // score mode: the candidate vector (and the partner haplotypes that label its A^B_k entries) goes out, nothing
+                    // is drawn or applied, the slot takes the next configuration
+                    const size_t ob = (size_t)s.h * sA.score_stride;
+#pragma unroll 1
+                    for (int k = 0; k < ncand && k < sA.score_stride; k++) {
+                        sA.score_pv[ob + k] = m.pv[C::at(k, h)];
+                        sA.score_pw[ob + k] = (!isC && k >= Lx && k < Lx + np) ? (unsigned long long)m.words[C::at((int)m.plist[C::at(k - Lx, h)], h)] : 0ull;
+                    }
+                    sA.score_ncand[s.h] = ncand;
+                    s.have = false;
+                } else {
                 // ---- sample the move (sampleFromVector :568-583) ----
                 double pidx;
                 const int idx = ls_scan<NH, NT, N32>(m, h, ncand, s.rng.next() * ptot, false, pidx);
@@ -379,6 +391,7 @@ __device__ __forceinline__ void run_lockstep() {
                 s.post = false;
                 if (s.nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
                 end_now = s.overflow;
+                }
             }
             D.valid = 0; D.nm = 0; D.nq = 0;
 
@@ -400,6 +413,14 @@ __device__ __forceinline__ void run_lockstep() {
                     s.e = 0; s.tset = sP.set_of_epoch[0];
                     s.qsum = 0.0; s.consts = 0.0; s.tsum = 0.0; s.peak = 0;
                     s.qprod.clear(); s.evprod.clear(); epoch_stats_clear(s.st);
+                    if (sA.score_off) {      // score mode: the given configuration instead of the sampled lineages
+#pragma unroll 1
+                        for (int k = sA.score_off[hx]; k < sA.score_off[hx + 1]; k++)
+                            if (ls_adjust<NH, NT, N32>(m, h, s, (int)sA.score_g[k], sA.score_w[k], (int)sA.score_c[k]) < 0) break;
+                        s.injecting = false;
+                        s.e = sA.score_epoch[hx]; s.tset = sP.set_of_epoch[s.e];
+                        end_now = s.overflow;
+                    }
                 }
             }
 
@@ -453,18 +474,26 @@ __device__ __forceinline__ void run_lockstep() {
                     hap_den += wgt;
                 }
                 double hap_num;
-                const int sx = ls_scan<NH, NT, N32>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
+                int sx;
+                if (sA.score_off) {          // score mode: the given lineage
+                    sx = 0; hap_num = 1.0; hap_den = 1.0;
+                    const typename WO::T cw = WO::narrow(sA.score_xw[s.h]); const unsigned int cgx = (unsigned int)sA.score_xg[s.h];
+#pragma unroll 1
+                    for (int j = 0; j < ns0; j++) if (m.words[C::at(j, h)] == cw && (m.cg[C::at(j, h)] >> 30) == cgx) sx = j;
+                } else {
+                    sx = ls_scan<NH, NT, N32>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
+                }
                 const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
                 const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
                 const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
                 const double rate = Dd * __ldg(&ecp->inv2Ntau);
                 const double tsum = s.tsum;
-                const double wait = -dlog(s.rng.next()) / rate;
+                const double wait = sA.score_off ? 1.0 : -dlog(s.rng.next()) / rate;
                 const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
 
                 // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
-                const bool boundary = (s.e < T - 1) && !(tsum + wait < sP.times[s.e + 1]);
-                finish = (s.e == T - 1) && (n <= 5);
+                const bool boundary = !sA.score_off && (s.e < T - 1) && !(tsum + wait < sP.times[s.e + 1]);
+                finish = !sA.score_off && (s.e == T - 1) && (n <= 5);
                 if (boundary || finish) {
                     if (boundary) {
                         const double excess = sP.times[s.e + 1] - tsum;

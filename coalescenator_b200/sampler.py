@@ -57,7 +57,7 @@ EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create",
            "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
            "coalgpu_capacity_stats", "coalgpu_tune", "coalgpu_set_emission_mode",
            "coalgpu_comm_init", "coalgpu_comm_finalize", "coalgpu_comm_size", "coalgpu_run_sampler_comm",
-           "coalgpu_run_sampler_multi", "coalgpu_multi_shutdown", "coalgpu_nccl_calls"]
+           "coalgpu_run_sampler_multi", "coalgpu_multi_shutdown", "coalgpu_nccl_calls", "coalgpu_score_events"]
 
 
 def load_library():
@@ -95,6 +95,7 @@ def load_library():
         L.coalgpu_run_sampler_multi.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
         L.coalgpu_multi_shutdown.restype = None
         L.coalgpu_nccl_calls.restype = C.c_uint64
+        L.coalgpu_score_events.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 3
         _lib = L
     return _lib
 
@@ -355,6 +356,30 @@ class DeviceSampler:
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
         _check(self.L.coalgpu_tables(self._h, int(n_all), int(time_idx), vp(w), vp(y), vp(z), vp(EA), vp(EB)))
         return dict(w=w, y=y, z=z, EA=EA, EB=EB)
+
+    def score_events(self, configs, chosen, epochs, max_cand=None):
+        """The device event code on given configurations (coalgpu_score_events): configs = list of type lists
+        [(gamma, word, count), ...] in slot order, chosen = list of (gamma, word), epochs = list of sampling epochs.
+        Returns a list of dicts(values=[...], partner_words=[...]) in the kernel's candidate order, None where the
+        configuration outgrew the type store."""
+        p = self.problem
+        if max_cand is None:
+            max_cand = max(p.LA + p.LB + 4, max(p.LA, p.LB) + max((len(c) for c in configs), default=0) + 1)
+        offs = np.zeros(len(configs) + 1, dtype=np.int32)
+        g, w, c = [], [], []
+        for q, cfg in enumerate(configs):
+            for (gg, ww, cc) in cfg:
+                g.append(gg); w.append(ww); c.append(cc)
+            offs[q + 1] = len(g)
+        g = np.asarray(g, dtype=np.uint8); w = np.asarray(w, dtype=np.uint64); c = np.asarray(c, dtype=np.uint32)
+        xg = np.asarray([x[0] for x in chosen], dtype=np.uint8); xw = np.asarray([x[1] for x in chosen], dtype=np.uint64)
+        ep = np.asarray(epochs, dtype=np.int32)
+        pv = np.zeros((len(configs), max_cand)); pw = np.zeros((len(configs), max_cand), dtype=np.uint64)
+        nc = np.zeros(len(configs), dtype=np.int32)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)
+        _check(self.L.coalgpu_score_events(self._h, len(configs), vp(offs), vp(g), vp(w), vp(c), vp(xg), vp(xw), vp(ep), int(max_cand),
+                                           vp(pv), vp(pw), vp(nc)))
+        return [None if nc[q] < 0 else dict(values=pv[q, :nc[q]].copy(), partner_words=pw[q, :nc[q]].copy()) for q in range(len(configs))]
 
     def pismc_classes(self, gamma, n_all, time_idx, class_offsets, counts, dA, dB) -> np.ndarray:
         """Batched piSMC from getDifferences output (ConditionalSamplingHMM.cpp:265-448) on the GPU."""

@@ -203,6 +203,20 @@ int coalgpu_pismc_classes(coalgpu_sampler* s, int64_t n_queries, const uint8_t* 
                           const int32_t* time_idx, const int64_t* class_offsets, const int32_t* counts,
                           const int32_t* dA, const int32_t* dB, double* out_pi);
 
+/* The device EVENT code on given configurations: configuration q = the types [cfg_offsets[q], cfg_offsets[q+1]) (gamma, word,
+ * count; slot order = list order) with the chosen lineage (chosen_gamma[q], chosen_words[q]) still in it, at sampling epoch
+ * epochs[q]. The history kernel removes the chosen lineage and scores every backward move exactly as it does for a drawn
+ * event (ProposalEngine.cpp:168-238, 298-338, 375-414); instead of drawing, the unnormalised proposal probabilities come
+ * back: out_pv[q*max_cand + k], k < out_ncand[q], in the kernel's candidate order --
+ *   C chosen:   k < LA+LB mutation of site k, then C^C, C^A, C^B, recombination;
+ *   A/B chosen: k < L mutation of site k, then one A^B_k per stored type of the other one-locus class in slot order
+ *               (its haplotype in out_partner_words[q*max_cand + k]), last the coalescence within the class.
+ * out_ncand[q] = -1 if the configuration outgrew the type store. Host buffers, blocking. */
+int coalgpu_score_events(coalgpu_sampler* s, int64_t n_cfg, const int32_t* cfg_offsets, const uint8_t* gamma,
+                         const uint64_t* words, const uint32_t* counts, const uint8_t* chosen_gamma,
+                         const uint64_t* chosen_words, const int32_t* epochs, int32_t max_cand, double* out_pv,
+                         uint64_t* out_partner_words, int32_t* out_ncand);
+
 /* Kernel launches issued by this library on the calling process so far (bench.py's gpu_launches). */
 uint64_t coalgpu_launch_count(void);
 const char* coalgpu_last_error(void);

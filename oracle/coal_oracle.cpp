@@ -652,6 +652,14 @@ struct Engine {
     Ctx& cx; Store& H; Rng& rng; Tracer* tr;
     int64_t n_pismc = 0, n_events = 0;
     std::vector<coalo_event>* evlog = nullptr;
+    // Candidate-vector dump (tests of the device event code, coalo_set_score_dump): per event one line
+    //   V <epoch> <chosen gamma> <chosen word> <ntypes> (<gamma> <word> <count>)* <ncand> (<label> <value>)*
+    // with the configuration BEFORE the removal of the chosen lineage, in the store's sampling order, and the unnormalised
+    // proposal probabilities of ProposalEngine.cpp:171-238 / 298-338 / 375-414 labelled by move: m<site>, cc, ca, cb, rec
+    // (C chosen); m<site>, p<partner word>, same (A / B chosen).
+    FILE* vdump = nullptr;
+    std::vector<std::string> vlabels;
+    std::vector<double>* vcapture = nullptr;      // coalo_score_event: keep the vector, stop before the draw
     Engine(Ctx& c, Store& s, Rng& r, Tracer* t) : cx(c), H(s), rng(r), tr(t) {}
 
     double pismc(const Hap& q, uint tidx) {
@@ -713,6 +721,19 @@ struct Engine {
         return h;
     }
 
+    // candidate-vector dump / capture; returns true when the caller must stop before the draw (coalo_score_event)
+    bool score_hook(const Hap& x, uint c, const std::vector<TypeRec>& cfg, const std::vector<double>& pv) {
+        if (vdump) {
+            fprintf(vdump, "V %u %d %llx %zu", c, x.gamma, (unsigned long long)x.word, cfg.size());
+            for (const TypeRec& r : cfg) fprintf(vdump, " %d %llx %u", r.gamma, (unsigned long long)r.word, r.count);
+            fprintf(vdump, " %zu", pv.size());
+            for (size_t k = 0; k < pv.size(); k++) fprintf(vdump, " %s %.17g", vlabels[k].c_str(), pv[k]);
+            fprintf(vdump, "\n");
+        }
+        if (vcapture) { *vcapture = pv; return true; }
+        return false;
+    }
+
     void log_event(const Hap& x, int kind, uint64_t aux, int site, uint c, uint n_before) {
         n_events++;
         if (!evlog) return;
@@ -734,6 +755,10 @@ struct Engine {
         const uint n = H.n(), C = H.nC, A = H.nA, B = H.nB;
         double ec = 0; int kind = -1;   // 0 coalescence, 1 mutation, 2 recombination
         std::vector<double> pv; uint idx = 0;
+        std::vector<TypeRec> vcfg;
+        if (vdump || vcapture) { H.sampling_order(vcfg); vlabels.clear(); }
+        auto label = [&](const std::string& l) { if (vdump || vcapture) vlabels.push_back(l); };
+        char lb[40];
 
         H.remove(x);                                   // :168
         const double pi0 = pismc(x, c);                // :169
@@ -744,7 +769,9 @@ struct Engine {
                 Hap m{COALO_GAMMA_C, x.word ^ (1ULL << s)};
                 double pm = pismc(m, c);
                 pv[s] = dtheta * Cij * pm / pi0;
+                snprintf(lb, sizeof lb, "m%u", s); label(lb);
             }
+            label("cc"); label("ca"); label("cb"); label("rec");
             pv[Ltot] = (Cij > 1) ? Cij * (Cij - 1) / pi0 : 0;      // :190-195
             const Hap xa{COALO_GAMMA_A, H.partA(x.word)}, xb{COALO_GAMMA_B, H.partB(x.word)};
             if (Ai > 0) {                              // :198-212
@@ -761,6 +788,7 @@ struct Engine {
             }
             double pj = pismc_jointly(xa, xb, c);      // :232-238
             pv[Ltot + 3] = drho * Cij * pj / pi0;
+            if (score_hook(x, c, vcfg, pv)) return 0.0;
             idx = sample_from(pv);                     // :241
             if (idx < Ltot) {                          // :242-249
                 Hap m{COALO_GAMMA_C, x.word ^ (1ULL << idx)};
@@ -795,7 +823,10 @@ struct Engine {
                 Hap m{x.gamma, x.word ^ (1ULL << (off + s))};
                 double pm = pismc(m, c);
                 pv[s] = dtheta * own * pm / pi0;
+                snprintf(lb, sizeof lb, "m%u", s); label(lb);
             }
+            for (size_t k = 0; k < partners.size(); k++) { snprintf(lb, sizeof lb, "p%llx", (unsigned long long)partners[k]); label(lb); }
+            label("same");
             for (size_t k = 0; k < partners.size(); k++) {   // :315-330 / :392-406
                 Hap pt{isA ? COALO_GAMMA_B : COALO_GAMMA_A, partners[k]};
                 Hap joined{COALO_GAMMA_C, x.word | pt.word};
@@ -809,6 +840,7 @@ struct Engine {
                 H.pop_temp(o);
             }
             pv[Lx + partners.size()] = (own > 1 || ownC > 0) ? own * (own - 1 + ownC) / pi0 : 0;   // :333-338 / :409-414
+            if (score_hook(x, c, vcfg, pv)) return 0.0;
             idx = sample_from(pv);                     // :341 / :417
             if (idx < Lx) {                            // :342-350 / :418-426
                 Hap m{x.gamma, x.word ^ (1ULL << (off + idx))};
@@ -984,6 +1016,39 @@ double coalo_pismc_classes(const coalo_problem* p, int Q, int gamma, int n_all, 
     return pismc_classes(*cache, gamma, n_all, time_idx, k);
 }
 
+static std::string g_score_dump_path;
+static int64_t g_score_dump_histories = 0;
+void coalo_set_score_dump(const char* path, int64_t n_histories) { g_score_dump_path = path ? path : ""; g_score_dump_histories = n_histories; }
+
+// The candidate vector of ONE event in CANONICAL mode: the configuration is rebuilt from the given type list (slot order =
+// list order, the chosen lineage still in it), the chosen lineage is removed and every backward move is scored exactly as
+// Engine::event does before its draw. out_vals[k] / labels as in the V records; returns the number of candidates or < 0.
+int coalo_score_event(const coalo_problem* p, int Q, int epoch, int n_types, const uint8_t* gamma, const uint64_t* words,
+                      const uint32_t* counts, int chosen_gamma, uint64_t chosen_word, int max_cand, double* out_vals,
+                      char* out_labels /* max_cand * 24 bytes */) {
+    Ctx cx; if (!init_ctx(cx, p, Q)) return -1;
+    if (epoch < 0 || epoch >= cx.T) return -2;
+    CanonStore store(cx);
+    PhiloxRng rng(0);
+    Engine eng(cx, store, rng, nullptr);
+    std::vector<TypeRec> init;
+    for (int k = 0; k < n_types; k++) init.push_back(TypeRec{(int)gamma[k], words[k], counts[k]});
+    store.reset(init);
+    std::vector<double> pv, L(cx.G, 0.0);
+    eng.vcapture = &pv;
+    const double V = cx.viral[epoch];
+    const double dN = cx.dlambda * V, dtheta = 4 * cx.dmu * dN, drho = 4 * cx.drho * dN;
+    bool post = true;
+    Hap x{chosen_gamma, chosen_word};
+    eng.event(dN, dtheta, drho, L, x, 1.0, (uint)epoch, V, post, false);
+    if ((int)pv.size() > max_cand) return -3;
+    for (size_t k = 0; k < pv.size(); k++) {
+        out_vals[k] = pv[k];
+        if (out_labels) { snprintf(out_labels + 24 * k, 24, "%s", eng.vlabels[k].c_str()); }
+    }
+    return (int)pv.size();
+}
+
 int coalo_run(const coalo_problem* p, int Q, int mode, uint64_t seed, uint64_t first, uint64_t n,
               double* weights, double* tmrca, double* lineages, int64_t* n_events, int64_t* n_pismc,
               const char* trace_path, int64_t trace_max,
@@ -998,9 +1063,11 @@ int coalo_run(const coalo_problem* p, int Q, int mode, uint64_t seed, uint64_t f
     Tracer tr; tr.cx = &cx;
     if (trace_path) { tr.f = fopen(trace_path, "w"); if (!tr.f) return -5; store->tr = &tr; }
     Engine eng(cx, *store, *rng, trace_path ? &tr : nullptr);
+    FILE* vfile = g_score_dump_path.empty() ? nullptr : fopen(g_score_dump_path.c_str(), "w");
     std::vector<double> L, left; double t;
     std::vector<coalo_event> evlog;
     for (uint64_t h = 0; h < n; h++) {
+        eng.vdump = (vfile && (int64_t)h < g_score_dump_histories) ? vfile : nullptr;
         rng->begin_history(first + h);
         if (trace_path) { tr.hist = (long)h; tr.on = (int64_t)h < trace_max; tr.epoch = 0; tr.delta.clear(); if (tr.on) fprintf(tr.f, "B %ld\n", tr.hist); }
         const bool want_ev = events && (int64_t)h < n_event_hist;
@@ -1019,6 +1086,7 @@ int coalo_run(const coalo_problem* p, int Q, int mode, uint64_t seed, uint64_t f
         }
     }
     if (tr.f) fclose(tr.f);
+    if (vfile) fclose(vfile);
     return 0;
 }
 

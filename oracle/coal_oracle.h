@@ -85,6 +85,17 @@ int coalo_run(const coalo_problem* p, int Q, int mode, uint64_t seed, uint64_t f
               const char* trace_path, int64_t trace_max,
               coalo_event* events, int64_t n_event_hist, int64_t max_events, int64_t* event_counts);
 
+/* Candidate vectors of the events (tests of the device event code): the next coalo_run calls write one "V" line per event
+ * of their first n_histories histories to `path` (NULL / "" switches the dump off); format in coal_oracle.cpp (Engine). */
+void coalo_set_score_dump(const char* path, int64_t n_histories);
+
+/* The unnormalised proposal probabilities of ONE event (ProposalEngine.cpp:171-238, 298-338, 375-414) in CANONICAL mode:
+ * configuration = the given type list in slot order with the chosen lineage still in it. Returns the number of
+ * candidates (labels: 24 bytes each, as in the V lines) or a negative error. */
+int coalo_score_event(const coalo_problem* p, int Q, int epoch, int n_types, const uint8_t* gamma, const uint64_t* words,
+                      const uint32_t* counts, int chosen_gamma, uint64_t chosen_word, int max_cand, double* out_vals,
+                      char* out_labels);
+
 /* sumSamples (SamplerOutput.cpp:115-133, LikelihoodSamples.cpp:56-70): descending-order
  * logAddition per grid point. out_* are [G], out_lineages is [T*G]; normalisation as the reference
  * (log-sum, not log-mean; tmrca and lineages divided by the likelihood). */

@@ -125,6 +125,41 @@ def reduce(weights, tmrca, lineages):
     return dict(likelihood=a, likelihoodSq=b, tmrca=c, lineages=d)
 
 
+def set_score_dump(path, n_histories=0):
+    """The next run() calls write one 'V' line per event of their first n_histories histories to `path` (None: off)."""
+    lib().coalo_set_score_dump(path.encode() if path else None, C.c_int64(n_histories))
+
+
+def parse_score_dump(path):
+    """'V epoch gamma word ntypes (gamma word count)* ncand (label value)*' -> list of dicts."""
+    out = []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if not t or t[0] != "V":
+                continue
+            nt = int(t[4])
+            cfg = [(int(t[5 + 3 * k]), int(t[6 + 3 * k], 16), int(t[7 + 3 * k])) for k in range(nt)]
+            o = 5 + 3 * nt
+            nc = int(t[o])
+            cand = [(t[o + 1 + 2 * k], float(t[o + 2 + 2 * k])) for k in range(nc)]
+            out.append(dict(epoch=int(t[1]), chosen=(int(t[2]), int(t[3], 16)), config=cfg, cand=cand))
+    return out
+
+
+def score_event(p, config, chosen, epoch, Q=16, max_cand=512):
+    """Candidate vector of one event in CANONICAL mode (coalo_score_event): list of (label, value)."""
+    op = OracleProblem(p)
+    g = np.asarray([c[0] for c in config], dtype=np.uint8); w = np.asarray([c[1] for c in config], dtype=np.uint64)
+    c = np.asarray([c[2] for c in config], dtype=np.uint32)
+    vals = np.zeros(max_cand); labels = C.create_string_buffer(24 * max_cand)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    n = lib().coalo_score_event(op.ref, Q, int(epoch), len(config), vp(g), vp(w), vp(c), int(chosen[0]), C.c_uint64(int(chosen[1])),
+                                max_cand, vp(vals), labels)
+    assert n >= 0, n
+    return [(labels.raw[24 * k:24 * k + 24].split(b"\0")[0].decode(), float(vals[k])) for k in range(n)]
+
+
 def uniform(seed, hist, k):
     return lib().coalo_uniform(seed, hist, k)
 

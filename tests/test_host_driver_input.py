@@ -226,3 +226,64 @@ def test_host_driver_shard_samples_over_two_gpus(tmp_path):
         assert a[:5] == b[:5]
         num = lambda cols: [float(x) for c in cols for x in c.split(",")]      # lineages_remaining is a comma-separated list
         np.testing.assert_allclose(num(a[5:]), num(b[5:]), rtol=1e-5)
+
+
+REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "coalref_main")
+REF_MAIN_GPU = os.path.join(ROOT, "oracle", "_ref", "coalref_main_gpu")
+_DRIVER_ARGS = ["-g", "1.5", "--loci-size", "30", "--mutation-list", "1e-5,2.5e-5,1e-4", "--scale-list", "500,1000",
+                "--rho-list", "5e-5,1e-4", "-s", "77", "--max-comp-dist", "60"]
+
+
+def test_reference_program_runs_from_its_own_main(tmp_path):
+    """oracle/_ref/coalref_main = the reference's UNMODIFIED main.cpp (+ its 8 translation units) behind a stand-in for
+    boost::program_options: the whole reference program runs here on the CPU, parses the same command line as the host
+    driver and writes its two files (main.cpp:232-240, 288-340). Its loci / pair / grid columns are what the host
+    driver must print (the numbers differ: CPU mt19937 histories vs GPU Philox histories)."""
+    if not os.path.exists(REF_MAIN):
+        pytest.skip("oracle/_ref/coalref_main not built (needs /root/reference)")
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    prefix = str(tmp_path / "ref")
+    r = subprocess.run([REF_MAIN, "-f", fl, "-t", tl, "-v", vl] + _DRIVER_ARGS + ["-i", "40", "-p", "2", "--output-file-prefix", prefix],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr + r.stdout[-2000:]
+    assert "Coalescenated succesfully." in r.stdout
+    rows = [l.split("\t") for l in open(prefix + "_pairwise_loglikelihood.txt").read().splitlines()]
+    assert rows[0] == ["locus1", "locus2", "mu", "rho", "lambda", "loglikelihood", "tmrca", "lineages_remaining", "loglikelihoodSq"]
+    assert len(rows) > 1 and (len(rows) - 1) % (3 * 2 * 2) == 0
+    comp = [l.split("\t") for l in open(prefix + "_composite_loglikelihood.txt").read().splitlines()]
+    assert comp[0] == ["mu", "rho", "lambda", "likelihood", "tmrca"] and len(comp) == 1 + 3 * 2 * 2
+    # the host driver's problem dump lists the same locus pairs in the same order (CPU-only part of the driver)
+    build_host()
+    dump = tmp_path / "dump"; dump.mkdir()
+    assert subprocess.run([HOST, "-f", fl, "-t", tl, "-v", vl] + _DRIVER_ARGS + ["-i", "40", "--dump-problems", str(dump)], capture_output=True).returncode == 0
+    pairs_ref = []
+    for x in rows[1:]:
+        if (x[0], x[1]) not in pairs_ref:
+            pairs_ref.append((x[0], x[1]))
+    assert len(pairs_ref) == len(list(dump.glob("*.coalprob")))
+
+
+@pytest.mark.gpu
+def test_host_driver_files_are_byte_identical_to_the_reference_writer(tmp_path):
+    """VERDICT r1 task 8: oracle/_ref/coalref_main_gpu is the reference's UNMODIFIED main.cpp with the sampler type at
+    main.cpp:281 swapped for include/GpuImportanceSampler.hpp (a force-included header does the one-line change of
+    INTEGRATION.md). It and the host driver coalescenator-gpu get the same numbers from libcoalgpu.so (a history is a
+    pure function of (seed, index); batched and single calls agree bit for bit), so every BYTE of the two output files
+    -- header, locus labels, grid columns, number formatting of main.cpp:288-340, the composite tmrca quirk Q8 -- must
+    agree between the reference's writer and the driver's."""
+    if not os.path.exists(REF_MAIN_GPU):
+        pytest.skip("oracle/_ref/coalref_main_gpu not built (needs /root/reference at build time)")
+    from coalescenator_b200 import build as B
+    B.build_cuda()
+    build_host()
+    fl, tl, vl = write_fasta_set(str(tmp_path))
+    outs = []
+    for exe, tag in ((REF_MAIN_GPU, "ref"), (HOST, "mine")):
+        prefix = str(tmp_path / tag)
+        r = subprocess.run([exe, "-f", fl, "-t", tl, "-v", vl] + _DRIVER_ARGS + ["-i", "700", "--output-file-prefix", prefix],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (tag, r.stderr, r.stdout[-2000:])
+        outs.append((open(prefix + "_pairwise_loglikelihood.txt", "rb").read(), open(prefix + "_composite_loglikelihood.txt", "rb").read()))
+    assert outs[0][0].count(b"\n") > 12
+    assert outs[0][0] == outs[1][0], "pairwise files differ"
+    assert outs[0][1] == outs[1][1], "composite files differ"
