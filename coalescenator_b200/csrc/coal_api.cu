@@ -197,6 +197,16 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
             if (!hit) { type_w.push_back(w); type_cg.push_back(((unsigned int)g << 30) | c); }
             n_bound += (g == COALGPU_GAMMA_C) ? 2ll * c : c;
         }
+        // Canonical input order: the merged types of a sampling time sorted by (class, packed haplotype). The slot order of a
+        // history's type store -- hence which history a given (seed, index) draws -- then no longer depends on the order in
+        // which the caller happens to list the types (the reference binding lists them in unordered_map iteration order, the
+        // host driver in first-appearance order: both now get the same numbers, byte-identical output files).
+        {
+            std::vector<std::pair<std::pair<int, unsigned long long>, unsigned int>> blk;
+            for (size_t i = start; i < type_w.size(); i++) blk.push_back({{(int)(type_cg[i] >> 30), type_w[i]}, type_cg[i]});
+            std::sort(blk.begin(), blk.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+            for (size_t i = start; i < type_w.size(); i++) { type_w[i] = blk[i - start].first.second; type_cg[i] = blk[i - start].second; }
+        }
         type_off[t + 1] = (int)type_w.size();
         // probabilitySamplePermutation, ProposalEngine.cpp:88-118
         for (int g = 0; g < 3; g++) {

@@ -1058,7 +1058,14 @@ int coalo_run(const coalo_problem* p, int Q, int mode, uint64_t seed, uint64_t f
     std::unique_ptr<Store> store;
     std::unique_ptr<Rng> rng;
     if (mode == COALO_MODE_STRICT) { store.reset(new StrictStore(cx)); rng.reset(new MtRng((uint)seed)); }
-    else if (mode == COALO_MODE_CANONICAL) { store.reset(new CanonStore(cx)); rng.reset(new PhiloxRng(seed)); }
+    else if (mode == COALO_MODE_CANONICAL) {
+        // canonical input order (shared with the CUDA path, coal_api.cu:prepare_host): the types of a sampling time sorted by
+        // (class, packed haplotype), so that the histories do not depend on the order in which a caller lists them (the
+        // reference's own order is the iteration order of its unordered_maps; STRICT mode keeps the given order for that)
+        for (auto& block : cx.types)
+            std::stable_sort(block.begin(), block.end(), [](const TypeRec& a, const TypeRec& b) { return a.gamma != b.gamma ? a.gamma < b.gamma : a.word < b.word; });
+        store.reset(new CanonStore(cx)); rng.reset(new PhiloxRng(seed));
+    }
     else return -4;
     Tracer tr; tr.cx = &cx;
     if (trace_path) { tr.f = fopen(trace_path, "w"); if (!tr.f) return -5; store->tr = &tr; }

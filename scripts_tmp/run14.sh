@@ -1,4 +1,3 @@
-timeout 600 python -m pytest tests/test_host_driver_input.py -m gpu -x -q > gpurun_out/r2_pytest_host.log 2>&1; tail -15 gpurun_out/r2_pytest_host.log
 B="timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e"
 for v in r8 notma notma_r8 r7; do COALGPU_LIB=/root/repo/variants/$v.so $B > gpurun_out/r2_h_$v.json 2> gpurun_out/r2_h_$v.err; done
 COALGPU_LOCKSTEP_NH=32 COALGPU_LOCKSTEP_NT=128 $B > gpurun_out/r2_h_32128.json 2> gpurun_out/r2_h_32128.err
