@@ -32,6 +32,13 @@ namespace {
 #define COAL_LS_DENSE_MAX 64
 #endif
 constexpr int kLsDenseMax = COAL_LS_DENSE_MAX;   // dense bilinear form up to this many (dA, dB) cells, class-list form beyond
+#ifndef COAL_LS_UNROLL_S
+#define COAL_LS_UNROLL_S 2
+#endif
+#ifndef COAL_LS_UNROLL_Q
+#define COAL_LS_UNROLL_Q 2
+#endif
+constexpr int kLsUnrollS = COAL_LS_UNROLL_S, kLsUnrollQ = COAL_LS_UNROLL_Q;   // unroll factors of the slot loops (serial / query phases)
 constexpr int kLsFlagAccum = 1;    // snapshot: add the epoch's target density to the history's weights
 constexpr int kLsFlagFinal = 2;    //           ... and the final constant: the history ends
 constexpr int kLsFlagAbort = 4;    //           the history outgrew the type store: weights = NaN
@@ -149,7 +156,7 @@ __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long l
     const typename WO::T m1 = (g == GA) ? maskA : (g == GB) ? maskB : (typename WO::T)~(typename WO::T)0;
     const typename WO::T k1 = (g == GC) ? wa : w, k2 = wb;
     const unsigned int d1 = (g == GB) ? (unsigned int)(delta * 65536) : (unsigned int)delta, d2 = (unsigned int)delta;
-#pragma unroll 2
+#pragma unroll kLsUnrollS
     for (int j = 0; j < ns; j++) {
         const typename WO::T wj = m.words[C::at(j, h)];
         const unsigned int cgj = m.cg[C::at(j, h)];
@@ -303,7 +310,7 @@ __device__ __forceinline__ void run_lockstep() {
                     // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
                     const double pj = 0.5 * D.mA1 * D.mB2 + 0.5 * D.mB1 * D.mA2;
                     const double f = D.dtheta_e * (double)Cij;
-#pragma unroll 2
+#pragma unroll kLsUnrollS
                     for (int k = 0; k < Ltot; k++) { const double v = f * m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
                     const double v0 = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
                     const double v1 = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
@@ -314,9 +321,9 @@ __device__ __forceinline__ void run_lockstep() {
                     ncand = Ltot + 4;
                     s.npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
                 } else {
-#pragma unroll 2
+#pragma unroll kLsUnrollS
                     for (int k = 0; k < Lx; k++) { const double v = m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
-#pragma unroll 2
+#pragma unroll kLsUnrollS
                     for (int k = 0; k < np; k++) ptot += m.pv[C::at(Lx + k, h)];
                     const double v0 = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
                     m.pv[C::at(Lx + np, h)] = v0; ptot += v0;
@@ -456,7 +463,7 @@ __device__ __forceinline__ void run_lockstep() {
                 // lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721)
                 const int ns0 = s.nslots;
                 double hap_den = 0.0;
-#pragma unroll 2
+#pragma unroll kLsUnrollS
                 for (int j = 0; j < ns0; j++) {
                     const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
                     const unsigned int c = cgj & kCntMask;
@@ -571,7 +578,7 @@ __device__ __forceinline__ void run_lockstep() {
                         const typename WO::T m1 = isA ? maskA : (isC ? (typename WO::T)~(typename WO::T)0 : maskB);
                         const typename WO::T k1 = isC ? xa : xwn;
                         const unsigned int d1 = (!isC && !isA) ? 65536u : 1u;
-#pragma unroll 2
+#pragma unroll kLsUnrollS
                         for (int j = 0; j < ns; j++) {
                             const typename WO::T wj = m.words[C::at(j, h)];
                             const unsigned int cgj = m.cg[C::at(j, h)];
@@ -707,7 +714,7 @@ __device__ __forceinline__ void run_lockstep() {
                 double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
                 // branch-free: the lanes of a warp walk the slots of different histories (different classes at the same j); a
                 // slot that is not ancestral at the query's locus enters with count 0 (adding 0 * wE changes no sum)
-#pragma unroll 2
+#pragma unroll kLsUnrollQ
                 for (int j = 0; j < ns; j++) {
                     const typename WO::T wj = m.words[C::at(j, hh)];
                     const unsigned int cgj = m.cg[C::at(j, hh)];
@@ -758,7 +765,7 @@ __device__ __forceinline__ void run_lockstep() {
                 for (int sidx = 0; sidx < nsum; sidx++) mine[sidx * NT] = 0xffff0000u;
                 // branch-free (see Q1): a slot without lineages (the removed x, the left-out partner) adds count 0 and leaves
                 // the class representative alone
-#pragma unroll 2
+#pragma unroll kLsUnrollQ
                 for (int j = 0; j < ns; j++) {
                     const typename WO::T wj = m.words[C::at(j, hh)];
                     const unsigned int cgj = m.cg[C::at(j, hh)];
