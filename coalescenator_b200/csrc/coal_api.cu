@@ -74,8 +74,8 @@ int ensure_kernel_attributes(int device) {
         CU_OK(cudaFuncGetAttributes(&fa, fn));            // static shared memory (problem constants) counts against the limit
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     }
-    for (int shape : {16 | (64 << 8), 32 | (64 << 8), 32 | (128 << 8)}) for (int narrow = 0; narrow < 2; narrow++) {
-        const void* fn = (const void*)history_lockstep_select(shape & 0xff, shape >> 8, narrow != 0);
+    for (int shape : {8 | (32 << 8), 16 | (64 << 8), 16 | (128 << 8), 32 | (64 << 8), 32 | (128 << 8), 16 | (64 << 8) | (1 << 16)}) for (int narrow = 0; narrow < 2; narrow++) {
+        const void* fn = (const void*)history_lockstep_select(shape & 0xff, (shape >> 8) & 0xff, narrow != 0, (shape >> 16) != 0);
         cudaFuncAttributes fa;
         CU_OK(cudaFuncGetAttributes(&fa, fn));
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
@@ -310,8 +310,16 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
 struct Geometry { int group = 0, occ = 0, per_sm = 0; size_t smem = 0; bool ls = false; };
 // threads per CTA / histories per CTA of a geometry: the group form packs cta_threads(W) / W groups of W lanes, the
 // lockstep form advances NH = `group` histories with 4 * NH threads
-// (lockstep: `group` = NH | NT << 8)
-inline int geo_threads(int group, bool ls) { return ls ? (group >> 8) : cta_threads(group); }
+// (lockstep: `group` = NH | NT << 8 | gstore << 16; gstore = the capacity tier with the type store in global memory)
+inline int geo_threads(int group, bool ls) { return ls ? ((group >> 8) & 0xff) : cta_threads(group); }
+inline bool geo_gstore(int group, bool ls) { return ls && (group >> 16) != 0; }
+inline history_kernel_fn geo_kernel(int group, bool ls, bool narrow) {
+    return ls ? history_lockstep_select(group & 0xff, (group >> 8) & 0xff, narrow, (group >> 16) != 0) : history_kernel_select(group, narrow);
+}
+// bytes of the global-memory type store one CTA of a capacity-tier launch needs (0 for every other geometry)
+inline size_t geo_store_bytes(const DevProblem& P, int group, bool ls) {
+    return geo_gstore(group, ls) ? history_lockstep_store_bytes(group & 0xff, (group >> 8) & 0xff, P.kmax, P.pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32) : 0;
+}
 inline int geo_hist_per_cta(int group, bool ls) { return ls ? (group & 0xff) : cta_threads(group) / group; }
 // Which form of K1: the lockstep form (default) or the group form (COALGPU_KERNEL=group, or a forced group width
 // COALGPU_GROUP=8|16|32, which the parity tests of the group form use).
@@ -320,24 +328,26 @@ bool want_lockstep() {
     if (const char* k = std::getenv("COALGPU_KERNEL")) return std::string(k) != "group";
     return true;
 }
-Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
+Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8, bool gstore = false) {
     if (want_lockstep()) {
         int forced_nh = 0, forced_nt = 0;
-        if (const char* g = std::getenv("COALGPU_LOCKSTEP_NH")) { const int v = std::atoi(g); if (v == 16 || v == 32) forced_nh = v; }
+        if (const char* g = std::getenv("COALGPU_LOCKSTEP_NH")) { const int v = std::atoi(g); if (v == 8 || v == 16 || v == 32) forced_nh = v; }
         if (const char* g = std::getenv("COALGPU_LOCKSTEP_NT")) { const int v = std::atoi(g); if (v == 64 || v == 128) forced_nt = v; }
-        auto eval = [&](int NH, int NT) {
-            Geometry g; g.group = NH | (NT << 8); g.ls = true;
-            g.smem = history_lockstep_bytes(NH, NT, kmax, pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32);
+        auto eval = [&](int NH, int NT, bool gstore) {
+            Geometry g; g.group = NH | (NT << 8) | (gstore ? 1 << 16 : 0); g.ls = true;
+            g.smem = history_lockstep_bytes(NH, NT, kmax, pvmax, P.Ltot, P.stage_doubles, P.Ltot <= 32, gstore);
             if (g.smem > 227 * 1024) return Geometry();
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_lockstep_select(NH, NT, P.Ltot <= 32), NT, g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ, (const void*)history_lockstep_select(NH, NT, P.Ltot <= 32, gstore), NT, g.smem) != cudaSuccess) { cudaGetLastError(); return Geometry(); }
             g.per_sm = g.occ * NH;
             return g;
         };
-        if (forced_nh) return eval(forced_nh, forced_nh == 16 ? 64 : (forced_nt ? forced_nt : 128));
-        const Geometry g16 = eval(16, 64), g32 = eval(32, forced_nt ? forced_nt : 128);
+        if (gstore) return eval(16, 64, true);
+        if (forced_nh) return eval(forced_nh, forced_nh == 8 ? 32 : (forced_nt ? forced_nt : (forced_nh == 16 ? 64 : 128)), false);
+        const Geometry g16 = eval(16, 64, false), g32 = eval(32, forced_nt ? forced_nt : 128, false);
         if (g16.per_sm > 0 || g32.per_sm > 0) return g32.per_sm > g16.per_sm ? g32 : g16;
         // neither fits (type store beyond ~200 KB of shared memory per CTA): fall through to the group form
     }
+    if (gstore) return Geometry();
     int forced_w = 0;
     if (const char* g = std::getenv("COALGPU_GROUP")) { const int W = std::atoi(g); if (W == 8 || W == 16 || W == 32) forced_w = W; }
     auto eval = [&](int W) {
@@ -357,8 +367,14 @@ Geometry geometry_for(const DevProblem& P, int kmax, int pvmax, bool allow8) {
 
 int choose_geometry(coalgpu_sampler* s, int peak) {
     DevProblem& P = s->P;
-    const Geometry full = geometry_for(P, P.kmax, P.pvmax, false);
-    if (full.per_sm < 1) return fail(COALGPU_EINVAL, "problem too large for the shared-memory state of one CTA");
+    Geometry full = geometry_for(P, P.kmax, P.pvmax, false);
+    // Capacity tier: a worst-case type store beyond one CTA's shared memory (about 1,500 slots) goes to global memory. It is the
+    // store of last resort -- the reduced-store first pass below still runs out of shared memory whenever one fits, and only the
+    // histories that outgrow that are drawn here (COALGPU_GSTORE=1 forces the tier: parity tests).
+    const char* gs_env = std::getenv("COALGPU_GSTORE");
+    const bool gs = full.per_sm < 1 || (gs_env && std::atoi(gs_env) > 0);
+    if (gs) full = geometry_for(P, P.kmax, P.pvmax, false, true);
+    if (full.per_sm < 1) return fail(COALGPU_EINVAL, "problem too large: the per-event state of one CTA does not fit shared memory (lockstep form required: unset COALGPU_KERNEL / COALGPU_GROUP)");
     s->group = full.group; s->ls = full.ls; s->smem_bytes = full.smem; s->grid = s->sm_count * full.occ;
     s->warp_bytes = full.ls ? 0 : (int)history_group_bytes(P.kmax, P.pvmax, P.Ltot, s->group, P.stage_doubles);
     P.warp_bytes = s->warp_bytes;
@@ -383,6 +399,7 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     }
     auto pick = [&](bool with8, DevProblem& Pout, int& grid, int& group, size_t& smem, bool& ls) -> bool {
         Geometry bestf = full; int best_k = 0;
+        if (gs) bestf.per_sm = 0;        // any store that fits shared memory beats the capacity tier
         for (int kf : cand) {
             kf = std::min(kf, P.kmax);                               // kf == kmax: same store, possibly narrower groups
             const Geometry g = geometry_for(P, kf, pv_for(kf), with8);
@@ -580,10 +597,17 @@ static int sample_pass(coalgpu_sampler* s, int pass, uint64_t seed, uint64_t fir
     const unsigned long long todo = pass == 2 ? n_listed : n;
     const unsigned long long ctas_needed = (todo + groups_per_cta - 1) / groups_per_cta;
     if ((unsigned long long)grid > ctas_needed) grid = (int)std::max<unsigned long long>(ctas_needed, 1);
-    history_kernel_fn kfn = ls ? history_lockstep_select(group & 0xff, group >> 8, P.Ltot <= 32) : history_kernel_select(group, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+    history_kernel_fn kfn = geo_kernel(group, ls, P.Ltot <= 32);   // shared-memory limit: ensure_kernel_attributes
+    void* d_store = nullptr;
+    if (const size_t sb = geo_store_bytes(P, group, ls)) {           // capacity tier: one slice of global memory per CTA
+        CU_OK(dev_alloc(&d_store, sb * (size_t)grid, st));
+        a.gstore = (unsigned char*)d_store;
+    }
     kfn<<<grid, geo_threads(group, ls), smem, st>>>(P, a);
     g_launches++;
-    CU_OK(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    dev_free(d_store, st);
+    CU_OK(le);
     s->last_stream = st;
     return 0;
 }
@@ -699,12 +723,17 @@ int coalgpu_score_events(coalgpu_sampler* s, int64_t n_cfg, const int32_t* cfg_o
         a.n = (unsigned long long)n_cfg; a.counters = s->d_counters;
         a.score_off = d_off; a.score_g = d_g; a.score_w = d_w; a.score_c = d_c; a.score_xg = d_xg; a.score_xw = d_xw; a.score_epoch = d_ep;
         a.score_pv = d_pv; a.score_pw = d_pw; a.score_ncand = d_nc; a.score_stride = max_cand;
-        const int NH = s->group & 0xff, NT = s->group >> 8;
-        int grid = (int)std::min<long long>(s->grid, (n_cfg + NH - 1) / NH);
-        history_kernel_fn kfn = history_lockstep_select(NH, NT, s->P.Ltot <= 32);
-        kfn<<<std::max(grid, 1), NT, s->smem_bytes, 0>>>(s->P, a);
-        g_launches++;
-        e = cudaGetLastError();
+        const int NH = s->group & 0xff, NT = geo_threads(s->group, true);
+        const int grid = std::max((int)std::min<long long>(s->grid, (n_cfg + NH - 1) / NH), 1);
+        history_kernel_fn kfn = geo_kernel(s->group, true, s->P.Ltot <= 32);
+        void* d_store = nullptr;
+        if (const size_t sb = geo_store_bytes(s->P, s->group, true)) { e = dev_alloc(&d_store, sb * (size_t)grid, 0); a.gstore = (unsigned char*)d_store; }
+        if (e == cudaSuccess) {
+            kfn<<<grid, NT, s->smem_bytes, 0>>>(s->P, a);
+            g_launches++;
+            e = cudaGetLastError();
+        }
+        dev_free(d_store, 0);
         s->last_stream = 0;
     }
     if (e == cudaSuccess) e = cudaMemcpy(out_pv, d_pv, (size_t)n_cfg * max_cand * 8, cudaMemcpyDeviceToHost);

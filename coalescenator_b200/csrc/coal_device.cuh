@@ -71,6 +71,7 @@ struct SampleArgs {
     unsigned long long* defer_list;
     const unsigned long long* list;
     const unsigned long long* list_count;
+    unsigned char* gstore;    // capacity tier of the lockstep form: the launch's arena of per-CTA type stores in global memory (coal_lockstep.cuh: ls_layout)
     // Score mode (coalgpu_score_events, the parity seam of the device event code): "history" h is the given configuration
     // h -- its type list is loaded instead of the sampled lineages, the given lineage is chosen instead of drawn, ONE event is
     // scored through the same phases as a drawn event, and the unnormalised candidate probabilities are written out instead

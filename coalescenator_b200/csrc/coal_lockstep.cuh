@@ -65,28 +65,34 @@ struct LsSnap {                    // what the G phase needs of a history that c
     int e, flags;
 };
 
-struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, total; };
+// Shared memory of a CTA. Capacity tier (gstore): the arrays that grow with the type store -- pv, aux, words, cg, xc, plist,
+// 34 bytes per slot and history -- live in the CTA's slice of a global-memory arena instead (gtotal bytes per CTA,
+// offsets relative to the slice): histories with thousands of lineages (TypeContainer has no size limit,
+// TypeContainer.cpp:409-522) then run at L2 speed instead of not at all. Everything per event stays in shared memory.
+struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, total; size_t gtotal; };
 
-__host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+__host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow, bool gstore = false) {
     LsLayout L;
-    unsigned int o = 0;
+    unsigned int o = 0, og = 0;
     auto place = [&o](size_t bytes) { const unsigned int at = o; o += (unsigned int)((bytes + 15) & ~(size_t)15); return at; };
+    auto place_store = [&o, &og, gstore](size_t bytes) { unsigned int& c = gstore ? og : o; const unsigned int at = c; c += (unsigned int)((bytes + 15) & ~(size_t)15); return at; };
     const int nsum = Ltot + 2;
     L.rowbuf = place((size_t)NH * stage_doubles * 8);
     L.wbuf = place((size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8);
     L.mbar = place((size_t)NH * 8);
-    L.pv = place((size_t)NH * pvmax * 8);
-    L.aux = place((size_t)NH * kmax * 8);
-    L.words = place((size_t)NH * kmax * (narrow ? 4 : 8));
-    L.cg = place((size_t)NH * kmax * 4);
-    L.xc = place((size_t)NH * kmax * 4);
-    L.plist = place((size_t)NH * kmax * 2);
+    L.pv = place_store((size_t)NH * pvmax * 8);
+    L.aux = place_store((size_t)NH * kmax * 8);
+    L.words = place_store((size_t)NH * kmax * (narrow ? 4 : 8));
+    L.cg = place_store((size_t)NH * kmax * 4);
+    L.xc = place_store((size_t)NH * kmax * 4);
+    L.plist = place_store((size_t)NH * kmax * 2);
     L.scratch = place((size_t)NT * 2 * nsum * 4);      // per thread: class histogram / class list [nsum] + the distance vectors of the dense form [nsum]
     L.desc = place((size_t)NH * sizeof(LsDesc));
     L.snap = place((size_t)NH * sizeof(LsSnap));
     L.pre1 = place((size_t)(NT / 32) * (NH + 1) * 4);     // one copy of the work-list prefixes per warp
     L.pre2 = place((size_t)(NT / 32) * (NH + 1) * 4);
     L.total = o;
+    L.gtotal = ((size_t)og + 255) & ~(size_t)255;
     return L;
 }
 
@@ -96,8 +102,10 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvma
 #define LS_ASSERT(cond) do { } while (0)
 #endif
 
-template <int NH, int NT_, bool N32>
+template <int NH, int NT_, int MD>
 struct LsCta {
+    static constexpr bool N32 = (MD & 1) != 0;     // 32-bit haplotype words (LA + LB <= 32)
+    static constexpr bool GS = (MD & 2) != 0;      // type store in global memory (capacity tier, see ls_layout)
     typedef WordOps<N32> WO;
     typedef typename WO::T WordT;
     static constexpr int NT = NT_;
@@ -105,10 +113,11 @@ struct LsCta {
     double* rowbuf; double* wbuf; unsigned long long* mbar; unsigned int* scratch; LsDesc* desc; LsSnap* snap; int* pre1; int* pre2;
 
     __device__ __forceinline__ void bind() {
-        const LsLayout L = ls_layout(NH, NT, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32);
+        const LsLayout L = ls_layout(NH, NT, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32, GS);
         unsigned char* b = smem_dyn;
-        words = reinterpret_cast<WordT*>(b + L.words); cg = reinterpret_cast<unsigned int*>(b + L.cg); xc = reinterpret_cast<unsigned int*>(b + L.xc);
-        plist = reinterpret_cast<unsigned short*>(b + L.plist); pv = reinterpret_cast<double*>(b + L.pv); aux = reinterpret_cast<double*>(b + L.aux);
+        unsigned char* sb = GS ? sA.gstore + (size_t)blockIdx.x * L.gtotal : b;     // the CTA's slice of the launch's arena
+        words = reinterpret_cast<WordT*>(sb + L.words); cg = reinterpret_cast<unsigned int*>(sb + L.cg); xc = reinterpret_cast<unsigned int*>(sb + L.xc);
+        plist = reinterpret_cast<unsigned short*>(sb + L.plist); pv = reinterpret_cast<double*>(sb + L.pv); aux = reinterpret_cast<double*>(sb + L.aux);
         rowbuf = reinterpret_cast<double*>(b + L.rowbuf); wbuf = reinterpret_cast<double*>(b + L.wbuf); mbar = reinterpret_cast<unsigned long long*>(b + L.mbar);
         scratch = reinterpret_cast<unsigned int*>(b + L.scratch); desc = reinterpret_cast<LsDesc*>(b + L.desc); snap = reinterpret_cast<LsSnap*>(b + L.snap);
         pre1 = reinterpret_cast<int*>(b + L.pre1); pre2 = reinterpret_cast<int*>(b + L.pre2);
@@ -134,9 +143,9 @@ struct LsHist {
 // that is not stored yet is appended; a slot whose count reaches 0 stays until ls_commit. Returns the slot (| kAppended
 // when a slot was appended) or -1 when the store is full. Out of line (three call sites), so it takes scalars only:
 // a reference to the caller's register state would force that state into local memory.
-template <int NH, int NT, bool N32>
+template <int NH, int NT, int MD>
 __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long long w64, int delta, bool active) {
-    typedef LsCta<NH, NT, N32> C;
+    typedef LsCta<NH, NT, MD> C;
     typedef typename C::WO WO;
     C m; m.bind();
     // Every history of the warp calls this at the same program points (a history without the operation passes
@@ -179,9 +188,9 @@ __device__ __noinline__ int ls_adjust_core(int h, int ns, int g, unsigned long l
     m.cg[C::at(found, h)] += (unsigned int)delta;
     return ret;
 }
-template <int NH, int NT, bool N32>
-__device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, N32>&, int h, LsHist& s, int g, unsigned long long w64, int delta, bool active = true) {
-    int r = ls_adjust_core<NH, NT, N32>(h, s.nslots, g, w64, delta, active);
+template <int NH, int NT, int MD>
+__device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, MD>&, int h, LsHist& s, int g, unsigned long long w64, int delta, bool active = true) {
+    int r = ls_adjust_core<NH, NT, MD>(h, s.nslots, g, w64, delta, active);
     if (r == -2) return -1;
     if (r < 0) { s.overflow = true; return -1; }
     if (r & kAppended) { s.nslots++; r &= ~kAppended; }
@@ -192,9 +201,9 @@ __device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, N32>&, int h, LsHis
 // Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot (the canonical order
 // rule shared with the oracle's CANONICAL mode). Scanning downwards visits the empty slots in that order,
 // and everything above the scan position is already non-empty.
-template <int NH, int NT, bool N32>
-__device__ __forceinline__ void ls_commit(const LsCta<NH, NT, N32>& m, int h, LsHist& s) {
-    typedef LsCta<NH, NT, N32> C;
+template <int NH, int NT, int MD>
+__device__ __forceinline__ void ls_commit(const LsCta<NH, NT, MD>& m, int h, LsHist& s) {
+    typedef LsCta<NH, NT, MD> C;
     int ns = s.nslots;
 #pragma unroll 1
     for (int j = ns - 1; j >= 0; j--) {
@@ -211,9 +220,9 @@ __device__ __forceinline__ void ls_commit(const LsCta<NH, NT, N32>& m, int h, Ls
 
 // Categorical draw over pv[0..n) of history h given total = the sum of pv in index order: first k with cum > u*total
 // (strict, TypeContainer.cpp:730) or with cum >= u*total (ProposalEngine.cpp:574). Returns k; pidx = pv[k].
-template <int NH, int NT, bool N32>
-__device__ __forceinline__ int ls_scan(const LsCta<NH, NT, N32>& m, int h, int n, double target, bool strict, double& pidx) {
-    typedef LsCta<NH, NT, N32> C;
+template <int NH, int NT, int MD>
+__device__ __forceinline__ int ls_scan(const LsCta<NH, NT, MD>& m, int h, int n, double target, bool strict, double& pidx) {
+    typedef LsCta<NH, NT, MD> C;
     double cum = 0.0;
     int idx = n - 1;
 #pragma unroll 1
@@ -235,9 +244,9 @@ __device__ __forceinline__ int ls_find(const int* pre, int i) {
     return lo;
 }
 
-template <int NH, int NT, bool N32>
+template <int NH, int NT, int MD>
 __device__ __forceinline__ void run_lockstep() {
-    typedef LsCta<NH, NT, N32> C;
+    typedef LsCta<NH, NT, MD> C;
     typedef typename C::WO WO;
     C m; m.bind();
     const int tid = threadIdx.x;
@@ -258,7 +267,7 @@ __device__ __forceinline__ void run_lockstep() {
     const int wlen = ((Ltot + 2) + 1) & ~1;
     constexpr bool kStaged =
 #ifdef COAL_TMA_ROWS
-        N32;
+        C::N32;
 #else
         false;
 #endif
@@ -345,7 +354,7 @@ __device__ __forceinline__ void run_lockstep() {
                 } else {
                 // ---- sample the move (sampleFromVector :568-583) ----
                 double pidx;
-                const int idx = ls_scan<NH, NT, N32>(m, h, ncand, s.rng.next() * ptot, false, pidx);
+                const int idx = ls_scan<NH, NT, MD>(m, h, ncand, s.rng.next() * ptot, false, pidx);
                 // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
                 const double qfac = (D.rate * D.hap_num * pidx) / (D.hap_den * ptot);
                 // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
@@ -372,13 +381,13 @@ __device__ __forceinline__ void run_lockstep() {
                     evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
                 }
                 double after0 = 1.0, after1 = 1.0;
-                { const int slot = ls_adjust<NH, NT, N32>(m, h, s, og0, ow0, od0, nops > 0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
-                { const int slot = ls_adjust<NH, NT, N32>(m, h, s, og1, ow1, od1, nops > 1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                { const int slot = ls_adjust<NH, NT, MD>(m, h, s, og0, ow0, od0, nops > 0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                { const int slot = ls_adjust<NH, NT, MD>(m, h, s, og1, ow1, od1, nops > 1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
                 if (ev_kind == 0) evc = after0;
                 else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
                 else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
                 const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
-                ls_commit<NH, NT, N32>(m, h, s);
+                ls_commit<NH, NT, MD>(m, h, s);
                 if (s.tracing && s.nev < sA.max_events) {
                     coalgpu_event& r = sA.events[(unsigned long long)s.h * sA.max_events + s.nev];
                     r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
@@ -423,7 +432,7 @@ __device__ __forceinline__ void run_lockstep() {
                     if (sA.score_off) {      // score mode: the given configuration instead of the sampled lineages
 #pragma unroll 1
                         for (int k = sA.score_off[hx]; k < sA.score_off[hx + 1]; k++)
-                            if (ls_adjust<NH, NT, N32>(m, h, s, (int)sA.score_g[k], sA.score_w[k], (int)sA.score_c[k]) < 0) break;
+                            if (ls_adjust<NH, NT, MD>(m, h, s, (int)sA.score_g[k], sA.score_w[k], (int)sA.score_c[k]) < 0) break;
                         s.injecting = false;
                         s.e = sA.score_epoch[hx]; s.tset = sP.set_of_epoch[s.e];
                         end_now = s.overflow;
@@ -439,7 +448,7 @@ __device__ __forceinline__ void run_lockstep() {
                 for (int k = s.inj_lo; k < s.inj_hi; k++) {
                     const unsigned int cgk = sP.type_cg[k];
                     const int add = (int)(cgk & kCntMask);
-                    const int slot = ls_adjust<NH, NT, N32>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
+                    const int slot = ls_adjust<NH, NT, MD>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
                     if (slot < 0) break;
                     const int now = (int)(m.cg[C::at(slot, h)] & kCntMask);
                     comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
@@ -488,7 +497,7 @@ __device__ __forceinline__ void run_lockstep() {
 #pragma unroll 1
                     for (int j = 0; j < ns0; j++) if (m.words[C::at(j, h)] == cw && (m.cg[C::at(j, h)] >> 30) == cgx) sx = j;
                 } else {
-                    sx = ls_scan<NH, NT, N32>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
+                    sx = ls_scan<NH, NT, MD>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
                 }
                 const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
                 const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
@@ -873,26 +882,36 @@ __device__ __forceinline__ void run_lockstep() {
 }  // namespace
 
 // The launch: persistent CTAs of NT threads and NH histories pull history indices from a global counter until the batch is drawn.
-// Shapes (NH, NT): (16, 64), (32, 64), (32, 128).
+// Shapes (NH, NT): (8, 32), (16, 64), (16, 128), (32, 64), (32, 128); the capacity tier (type store in global memory): (16, 64).
+#ifndef COAL_LS_MIN_CTAS_32
+#define COAL_LS_MIN_CTAS_32 12
+#endif
 #ifndef COAL_LS_MIN_CTAS_64
 #define COAL_LS_MIN_CTAS_64 6
 #endif
 #ifndef COAL_LS_MIN_CTAS_128
 #define COAL_LS_MIN_CTAS_128 3
 #endif
-template <int NH, int NT, bool N32>
-__global__ void __launch_bounds__(NT, NT == 64 ? COAL_LS_MIN_CTAS_64 : COAL_LS_MIN_CTAS_128)
+template <int NH, int NT, int MD>
+__global__ void __launch_bounds__(NT, NT == 32 ? COAL_LS_MIN_CTAS_32 : NT == 64 ? COAL_LS_MIN_CTAS_64 : COAL_LS_MIN_CTAS_128)
 history_lockstep_kernel(const DevProblem P, const SampleArgs A) {
     if (threadIdx.x == 0) { sP = P; sA = A; }
     __syncthreads();
-    run_lockstep<NH, NT, N32>();
+    run_lockstep<NH, NT, MD>();
 }
 
-history_kernel_fn history_lockstep_select(int NH, int NT, bool narrow) {
-    if (NH == 16) return narrow ? history_lockstep_kernel<16, 64, true> : history_lockstep_kernel<16, 64, false>;
-    if (NT == 64) return narrow ? history_lockstep_kernel<32, 64, true> : history_lockstep_kernel<32, 64, false>;
-    return narrow ? history_lockstep_kernel<32, 128, true> : history_lockstep_kernel<32, 128, false>;
+// gstore: the capacity tier (type store in global memory), shape (16, 64) only
+history_kernel_fn history_lockstep_select(int NH, int NT, bool narrow, bool gstore) {
+    if (gstore) return narrow ? history_lockstep_kernel<16, 64, 3> : history_lockstep_kernel<16, 64, 2>;
+    if (NH == 8) return narrow ? history_lockstep_kernel<8, 32, 1> : history_lockstep_kernel<8, 32, 0>;
+    if (NH == 16 && NT == 128) return narrow ? history_lockstep_kernel<16, 128, 1> : history_lockstep_kernel<16, 128, 0>;
+    if (NH == 16) return narrow ? history_lockstep_kernel<16, 64, 1> : history_lockstep_kernel<16, 64, 0>;
+    if (NT == 64) return narrow ? history_lockstep_kernel<32, 64, 1> : history_lockstep_kernel<32, 64, 0>;
+    return narrow ? history_lockstep_kernel<32, 128, 1> : history_lockstep_kernel<32, 128, 0>;
 }
-size_t history_lockstep_bytes(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
-    return ls_layout(NH, NT, kmax, pvmax, Ltot, stage_doubles, narrow).total;
+size_t history_lockstep_bytes(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow, bool gstore) {
+    return ls_layout(NH, NT, kmax, pvmax, Ltot, stage_doubles, narrow, gstore).total;
+}
+size_t history_lockstep_store_bytes(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow) {
+    return ls_layout(NH, NT, kmax, pvmax, Ltot, stage_doubles, narrow, true).gtotal;
 }

@@ -171,10 +171,21 @@ int main(int argc, char** argv) {
         if (loci.size() == 1) { std::cout << "\n[" << now() << "] Only a single loci left no remcobination estimation possible - exiting!" << std::endl; return 0; }   // :202-207
 
         struct Pair { size_t i, j; unsigned dist; };
+        size_t n_skipped_long = 0;
         std::vector<Pair> pairs;                                                       // :211-225, :242-252
         for (size_t i = 0; i < loci.size(); i++) for (size_t j = i + 1; j < loci.size(); j++) {
             const unsigned dist = orig[j].first - orig[i].second - 1;
             if (dist < o.min_dist || dist > o.max_dist) continue;
+            // libcoalgpu.so packs the two loci of a pair into one 64-bit haplotype word; a pair with more segregating sites is
+            // reported and left out instead of failing the whole analysis (the reference itself loses accuracy beyond ~30
+            // segregating sites per locus and cannot run beyond 1029, ConditionalSamplingHMM.cpp:73-82,196-209)
+            const size_t lsum = (loci[i].second - loci[i].first + 1) + (loci[j].second - loci[j].first + 1);
+            if (lsum > 64) {
+                std::cout << "[" << now() << "] WARNING: skipping locus pair (" << orig[i].first << ", " << orig[i].second << ") and (" << orig[j].first << ", "
+                          << orig[j].second << "): " << lsum << " segregating sites exceed the 64 a packed locus pair holds (use a smaller --loci-size)." << std::endl;
+                n_skipped_long++;
+                continue;
+            }
             pairs.push_back({i, j, dist});
         }
         std::cout << "\n[" << now() << "] For each of the " << pairs.size() << " loci combination(s) generate " << o.mc_samples << " importance samples. "

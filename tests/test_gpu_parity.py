@@ -789,3 +789,64 @@ def test_device_event_code_against_reference_candidate_vectors(cuda_lib, oracle,
             total_ok += 1
         print(name, "events", len(recs), "with a C-C class tie (skipped for the reference comparison)", n_tie)
     assert total_ok >= 10000, total_ok
+
+
+@pytest.mark.parametrize("shape", [(8, 32), (16, 64), (16, 128), (32, 64), (32, 128)])
+def test_every_lockstep_shape_is_bit_exact(oracle, cuda_lib, monkeypatch, shape):
+    """The lockstep form of the history kernel is instantiated for several (histories per CTA, threads per CTA) shapes; the
+    sampler picks one by occupancy. Every shape is forced here (read when the sampler is created): event encodings
+    bit-identical to the oracle on goldens with missing data, a grid and five time points, and on 64-bit haplotype words."""
+    from coalescenator_b200.problem import synth_alignment, tile_loci, locus_pairs, sub_problem
+    monkeypatch.setenv("COALGPU_LOCKSTEP_NH", str(shape[0]))
+    monkeypatch.setenv("COALGPU_LOCKSTEP_NT", str(shape[1]))
+    for name, n, seed in (("cfg2_pair0", 80, 5), ("missing_pair3", 48, 6), ("grid_pair5", 24, 7), ("varV_req_n", 32, 8)):
+        p, _, _ = load_golden(name)
+        _compare_histories(oracle, p, n, seed=seed)
+    aln = synth_alignment(11, 2, 5, 400, 100)
+    loci = tile_loci(aln, 80)
+    best = max(locus_pairs(loci), key=lambda t: (loci[t[0]][3] - loci[t[0]][2]) + (loci[t[1]][3] - loci[t[1]][2]))
+    p = sub_problem(aln, loci, *best)
+    assert 32 < p.LA + p.LB <= 64
+    _compare_histories(oracle, p, 12, seed=10, max_events=32768)
+
+
+def test_capacity_tier_type_store_in_global_memory(oracle, cuda_lib, monkeypatch):
+    """The type store of a history normally lives in shared memory, which bounds it to about 1,500 types per CTA; the
+    reference's TypeContainer has no such bound (TypeContainer.cpp:409-522, Sample.cpp:386-411). The capacity tier keeps
+    the store in global memory instead. (1) Forced on small problems (COALGPU_GSTORE=1), alone and as the second pass
+    behind a 16-type first-pass store: bit-identical to the oracle. (2) The stress reading of BASELINE config 4 --
+    10 sampling times x 200 sequences = 2,000 lineages, worst-case store 4,032 types -- which no shared-memory geometry
+    holds: runs, and is bit-identical to the oracle."""
+    import torch
+    from coalescenator_b200.problem import synth_alignment, tile_loci, locus_pairs, sub_problem
+    monkeypatch.setenv("COALGPU_GSTORE", "1")
+    for name, n, seed in (("cfg2_pair0", 64, 5), ("missing_pair3", 48, 6), ("grid_pair5", 24, 7)):
+        p, _, _ = load_golden(name)
+        _compare_histories(oracle, p, n, seed=seed)
+    monkeypatch.setenv("COALGPU_KMAX_FAST", "16")
+    p, _, _ = load_golden("cfg2_pair0")
+    s = _sampler(p)
+    n = 400
+    buf = s.alloc(n, n_trace=64, max_events=4096)
+    s.sample(buf, 31, 0, n); torch.cuda.synchronize()
+    c = s.counters()
+    assert c["n_deferred"] > 0 and c["n_overflow"] == 0, c
+    ref = oracle.run(p, 64, 31, mode=oracle.MODE_CANONICAL, n_event_hist=64, max_events=4096)
+    ev = s.events(buf)
+    for h in range(64):
+        assert np.array_equal(ev[h], ref["events"][h])
+    np.testing.assert_allclose(buf["weights"].cpu().numpy()[:64], ref["weights"], rtol=RTOL_WEIGHT)
+    s.close()
+    monkeypatch.delenv("COALGPU_KMAX_FAST")
+    monkeypatch.delenv("COALGPU_GSTORE")
+    # 2,000 lineages
+    aln = synth_alignment(3, 10, 200, 4000, 120)
+    loci = tile_loci(aln, 100)
+    p = sub_problem(aln, loci, *locus_pairs(loci)[3])
+    assert p.T == 10 and p.n_lineages() == 2000
+    buf, ref = _compare_histories(oracle, p, 40, seed=7, n_trace=8, max_events=1 << 15)
+    assert ref["n_events"].min() > 4000
+    import coalescenator_b200 as cb
+    out = cb.ImportanceSampler().run_sampler(p, 40, seed=7)        # the drop-in call takes the same route
+    red = oracle.reduce(ref["weights"], ref["tmrca"], ref["lineages"])
+    np.testing.assert_allclose(out.likelihood.ravel(), red["likelihood"], rtol=1e-9)
