@@ -284,7 +284,11 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
     P.pvmax = (P.pvmax + 1) & ~1;
     P.row_doubles = lay.dev_row_doubles;
     P.SB = lay.dev_sb; P.off_wEA = lay.dev_off_wEA; P.off_wEB = lay.dev_off_wEB;
+#ifdef COAL_NO_TMA
+    P.stage_doubles = 0;                                            // comparison build: every table row is read through L1 (ld.global.nc)
+#else
     P.stage_doubles = (LA + LB <= 32) ? lay.dev_row_doubles : 0;    // matches kStaged in history_kernel: longer loci read their rows through L1
+#endif
     P.maskA = maskA; P.maskB = maskB;
     P.perm_const = perm;
     P.pow2negLA = std::ldexp(1.0, -LA); P.pow2negLB = std::ldexp(1.0, -LB); P.pow2negL = std::ldexp(1.0, -(LA + LB));

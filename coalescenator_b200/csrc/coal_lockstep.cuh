@@ -53,7 +53,7 @@ struct LsDesc {                    // event descriptor of one history and step (
     double mA1, mA2, mB1, mB2;     // results of one-locus queries 0 and 1 on the two rows (A/B chosen: mA1 = pi0)
     double pi0c;                   // C chosen: pi(x | H')
     double rate, wait, hap_num, hap_den, nn, aa, dtheta_e, drho_e;
-    int valid, xg, ns, n, np, nm, nq, Lx, offb, pg;
+    int valid, xg, ns, n, np, nm, nq, Lx, offb, pg, sx;
     int Ac, Bc, Cc;
     unsigned int own, ownC, Cij, Ci, Cj, Ai, Bj, cn, nc_alt, tma_parity;
 };
@@ -78,8 +78,12 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvma
     auto place_store = [&o, &og, gstore](size_t bytes) { unsigned int& c = gstore ? og : o; const unsigned int at = c; c += (unsigned int)((bytes + 15) & ~(size_t)15); return at; };
     const int nsum = Ltot + 2;
     L.rowbuf = place((size_t)NH * stage_doubles * 8);
+#ifdef COAL_TMA_ROWS
     L.wbuf = place((size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8);
     L.mbar = place((size_t)NH * 8);
+#else
+    L.wbuf = L.mbar = 0;
+#endif
     L.pv = place_store((size_t)NH * pvmax * 8);
     L.aux = place_store((size_t)NH * kmax * 8);
     L.words = place_store((size_t)NH * kmax * (narrow ? 4 : 8));
@@ -198,22 +202,105 @@ __device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, MD>&, int h, LsHist
     return r;
 }
 
-// Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot (the canonical order
-// rule shared with the oracle's CANONICAL mode). Scanning downwards visits the empty slots in that order,
-// and everything above the scan position is already non-empty.
+// The two type changes of a backward move (ProposalEngine.cpp:242-294, 342-371, 418-448: at most two addType / removeType
+// calls) in ONE pass over the stored types: exactly ls_adjust_core(op 0) followed by ls_adjust_core(op 1) -- op 1 sees the
+// count op 0 left in its slot and the slot op 0 appended --, with one walk, one pair of loads per slot and two independent
+// match computations per iteration instead of two dependent walks. An op without work passes active = false.
+// Returns slot 0 | slot 1 << 32 (each as ls_adjust_core returns it).
 template <int NH, int NT, int MD>
-__device__ __forceinline__ void ls_commit(const LsCta<NH, NT, MD>& m, int h, LsHist& s) {
+__device__ __noinline__ unsigned long long ls_adjust2_core(int h, int ns, int g0, unsigned long long w0_64, int delta0, bool act0,
+                                                            int g1, unsigned long long w1_64, int delta1, bool act1) {
     typedef LsCta<NH, NT, MD> C;
+    typedef typename C::WO WO;
+    typedef typename WO::T W;
+    C m; m.bind();
+    const W maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB), ones = (W)~(W)0;
+    const W w0 = WO::narrow(w0_64), w1 = WO::narrow(w1_64);
+    // match rules as in ls_adjust_core; an inactive op gets class 7, which no slot has
+    const int G0 = act0 ? g0 : 7, G1 = act1 ? g1 : 7;
+    const int t1a = !act0 ? 7 : (g0 == GC ? GA : GC), t2a = !act0 ? 7 : (g0 == GC ? GB : 7);
+    const int t1b = !act1 ? 7 : (g1 == GC ? GA : GC), t2b = !act1 ? 7 : (g1 == GC ? GB : 7);
+    const W m1a = (g0 == GA) ? maskA : (g0 == GB) ? maskB : ones, m1b = (g1 == GA) ? maskA : (g1 == GB) ? maskB : ones;
+    const W k1a = (g0 == GC) ? (w0 & maskA) : w0, k2a = w0 & maskB, k1b = (g1 == GC) ? (w1 & maskA) : w1, k2b = w1 & maskB;
+    const unsigned int d1a = (g0 == GB) ? (unsigned int)(delta0 * 65536) : (unsigned int)delta0, d2a = (unsigned int)delta0;
+    const unsigned int d1b = (g1 == GB) ? (unsigned int)(delta1 * 65536) : (unsigned int)delta1, d2b = (unsigned int)delta1;
+    int found0 = -1, found1 = -1;
+    unsigned int newxc0 = 0, newxc1 = 0;
+    const int nloop = (act0 || act1) ? ns : 0;
+#pragma unroll kLsUnrollS
+    for (int j = 0; j < nloop; j++) {
+        const W wj = m.words[C::at(j, h)];
+        const unsigned int cgj = m.cg[C::at(j, h)];
+        const int gj = (int)(cgj >> 30);
+        const unsigned int cj = cgj & kCntMask;
+        const bool f0 = (gj == G0) && (wj == w0);
+        if (f0) found0 = j;
+        const bool h1a = (gj == t1a) && ((wj & m1a) == k1a), h2a = (gj == t2a) && (wj == k2a);
+        newxc0 += (h1a ? cj : 0u) + (h2a ? (cj << 16) : 0u);
+        const unsigned int cj1 = cj + (f0 ? (unsigned int)delta0 : 0u);          // the count op 1 sees
+        if ((gj == G1) && (wj == w1)) found1 = j;
+        const bool h1b = (gj == t1b) && ((wj & m1b) == k1b), h2b = (gj == t2b) && (wj == k2b);
+        newxc1 += (h1b ? cj1 : 0u) + (h2b ? (cj1 << 16) : 0u);
+        const unsigned int xadd = (h1a ? d1a : 0u) + (h2a ? d2a : 0u) + (h1b ? d1b : 0u) + (h2b ? d2b : 0u);
+        if (xadd) m.xc[C::at(j, h)] += xadd;
+    }
+    unsigned int r0 = 0xfffffffeu, r1 = 0xfffffffeu;       // -2: no op
+    if (act0) {
+        r0 = (unsigned int)found0;
+        if (found0 < 0) {
+            if (ns >= sP.kmax) return 0xffffffffffffffffull;          // store full
+            found0 = ns++;
+            // the appended slot as op 1 sees it: class g0, haplotype w0, count delta0
+            const unsigned int c1 = (unsigned int)delta0;
+            if (g0 == G1 && w0 == w1) found1 = found0;
+            const bool h1b = (g0 == t1b) && ((w0 & m1b) == k1b), h2b = (g0 == t2b) && (w0 == k2b);
+            newxc1 += (h1b ? c1 : 0u) + (h2b ? (c1 << 16) : 0u);
+            m.words[C::at(found0, h)] = w0; m.cg[C::at(found0, h)] = (unsigned int)g0 << 30;
+            m.xc[C::at(found0, h)] = newxc0 + (h1b ? d1b : 0u) + (h2b ? d2b : 0u);
+            r0 = (unsigned int)(found0 | kAppended);
+        }
+        m.cg[C::at(found0, h)] += (unsigned int)delta0;
+    }
+    if (act1) {
+        r1 = (unsigned int)found1;
+        if (found1 < 0) {
+            if (ns >= sP.kmax) return 0xffffffffffffffffull;
+            found1 = ns++;
+            m.words[C::at(found1, h)] = w1; m.cg[C::at(found1, h)] = (unsigned int)g1 << 30; m.xc[C::at(found1, h)] = newxc1;
+            r1 = (unsigned int)(found1 | kAppended);
+        }
+        m.cg[C::at(found1, h)] += (unsigned int)delta1;
+    }
+    return (unsigned long long)r0 | ((unsigned long long)r1 << 32);
+}
+
+// Drop empty slots at the end of an event: highest empty slot first, overwritten by the last slot (the canonical order
+// rule shared with the oracle's CANONICAL mode). A slot can only have run empty where the event took a
+// lineage away: the chosen lineage's slot and the slots of the move's (at most two) type changes -- three candidates,
+// visited in descending order, which is the order a downward scan over all slots would meet them in (everything above the
+// candidate being visited is non-empty by then).
+template <int NH, int NT, int MD>
+__device__ __forceinline__ void ls_commit(const LsCta<NH, NT, MD>& m, int h, LsHist& s, int c0, int c1, int c2) {
+    typedef LsCta<NH, NT, MD> C;
+    // sort descending (3-element network); duplicates and -1 (no candidate) are skipped below
+    int t;
+    if (c0 < c1) { t = c0; c0 = c1; c1 = t; }
+    if (c1 < c2) { t = c1; c1 = c2; c2 = t; }
+    if (c0 < c1) { t = c0; c0 = c1; c1 = t; }
     int ns = s.nslots;
-#pragma unroll 1
-    for (int j = ns - 1; j >= 0; j--) {
-        if ((m.cg[C::at(j, h)] & kCntMask) == 0) {
+    int prev = -1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i == 0) ? c0 : (i == 1) ? c1 : c2;
+        if (j >= 0 && j != prev && (m.cg[C::at(j, h)] & kCntMask) == 0) {
+            LS_ASSERT(j < ns);
             const int last = ns - 1;
             if (j != last) {
                 m.words[C::at(j, h)] = m.words[C::at(last, h)]; m.cg[C::at(j, h)] = m.cg[C::at(last, h)]; m.xc[C::at(j, h)] = m.xc[C::at(last, h)];
             }
             ns = last;
         }
+        prev = j;
     }
     s.nslots = ns;
 }
@@ -315,29 +402,34 @@ __device__ __forceinline__ void run_lockstep() {
                 const double inv_pi0 = 1.0 / pi0;
                 int ncand;
                 double ptot = 0.0;               // sum of the candidate probabilities, index order (vectorSum, ProposalEngine.cpp:585-594)
-                if (isC) {
-                    // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
-                    const double pj = 0.5 * D.mA1 * D.mB2 + 0.5 * D.mB1 * D.mA2;
-                    const double f = D.dtheta_e * (double)Cij;
+                // One instruction sequence for the three classes of the chosen lineage (the histories of a warp finish events of
+                // different classes in the same step): the mutation candidates scaled by f / pi0 (f = 1 for a one-locus lineage:
+                // 1.0 * x is exact), the A^B_k coalescences of a one-locus lineage (none for C), the coalescence within the class,
+                // and the three further candidates of a two-locus lineage.
+                {
+                    const double f = isC ? D.dtheta_e * (double)Cij : 1.0;
 #pragma unroll kLsUnrollS
-                    for (int k = 0; k < Ltot; k++) { const double v = f * m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
-                    const double v0 = (Cij > 1) ? (double)(Cij * (Cij - 1)) * inv_pi0 : 0.0;
-                    const double v1 = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
-                    const double v2 = (Bj > 0) ? (double)(Bj * Cij) / D.mB1 : 0.0;
-                    const double v3 = D.drho_e * (double)Cij * pj * inv_pi0;
-                    m.pv[C::at(Ltot, h)] = v0; m.pv[C::at(Ltot + 1, h)] = v1; m.pv[C::at(Ltot + 2, h)] = v2; m.pv[C::at(Ltot + 3, h)] = v3;
-                    ptot += v0; ptot += v1; ptot += v2; ptot += v3;
-                    ncand = Ltot + 4;
-                    s.npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
-                } else {
+                    for (int k = 0; k < Lx; k++) { const double v = f * m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
+                    const int npp = isC ? 0 : np;
 #pragma unroll kLsUnrollS
-                    for (int k = 0; k < Lx; k++) { const double v = m.pv[C::at(k, h)] * inv_pi0; m.pv[C::at(k, h)] = v; ptot += v; }
-#pragma unroll kLsUnrollS
-                    for (int k = 0; k < np; k++) ptot += m.pv[C::at(Lx + k, h)];
-                    const double v0 = (own > 1 || ownC > 0) ? (double)(own * (own - 1 + ownC)) * inv_pi0 : 0.0;
-                    m.pv[C::at(Lx + np, h)] = v0; ptot += v0;
-                    ncand = Lx + np + 1;
-                    s.npi += (unsigned int)(1 + Lx + 5 * np);
+                    for (int k = 0; k < npp; k++) ptot += m.pv[C::at(Lx + k, h)];
+                    const unsigned int cw = isC ? Cij * (Cij - 1) : own * (own - 1 + ownC);
+                    const double v0 = (isC ? (Cij > 1) : (own > 1 || ownC > 0)) ? (double)cw * inv_pi0 : 0.0;
+                    m.pv[C::at(Lx + npp, h)] = v0; ptot += v0;
+                    ncand = Lx + npp + 1;
+                    if (isC) {
+                        // 0.5 [pi(a|H') pi(b|H'+a) + pi(b|H') pi(a|H'+b)]   (piSMCJointly :120-132)
+                        const double pj = 0.5 * D.mA1 * D.mB2 + 0.5 * D.mB1 * D.mA2;
+                        const double v1 = (Ai > 0) ? (double)(Ai * Cij) / D.mA1 : 0.0;   // pi(xa | H'+x-xa) == pi(xa | H')
+                        const double v2 = (Bj > 0) ? (double)(Bj * Cij) / D.mB1 : 0.0;
+                        const double v3 = D.drho_e * (double)Cij * pj * inv_pi0;
+                        m.pv[C::at(Ltot + 1, h)] = v1; m.pv[C::at(Ltot + 2, h)] = v2; m.pv[C::at(Ltot + 3, h)] = v3;
+                        ptot += v1; ptot += v2; ptot += v3;
+                        ncand = Ltot + 4;
+                        s.npi += (unsigned int)(Ltot + 1) + 4u + (Ai > 0 ? 1u : 0u) + (Bj > 0 ? 1u : 0u);
+                    } else {
+                        s.npi += (unsigned int)(1 + Lx + 5 * np);
+                    }
                 }
                 LS_ASSERT(ncand <= sP.pvmax);
                 if (sA.score_off) {
@@ -381,13 +473,29 @@ __device__ __forceinline__ void run_lockstep() {
                     evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
                 }
                 double after0 = 1.0, after1 = 1.0;
-                { const int slot = ls_adjust<NH, NT, MD>(m, h, s, og0, ow0, od0, nops > 0); if (slot >= 0) after0 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
-                { const int slot = ls_adjust<NH, NT, MD>(m, h, s, og1, ow1, od1, nops > 1); if (slot >= 0) after1 = (double)(m.cg[C::at(slot, h)] & kCntMask); }
+                int slot0 = -1, slot1 = -1;
+                {
+                    const unsigned long long r = ls_adjust2_core<NH, NT, MD>(h, s.nslots, og0, ow0, od0, nops > 0, og1, ow1, od1, nops > 1);
+                    if (r == 0xffffffffffffffffull) s.overflow = true;
+                    else {
+                        const int r0 = (int)(unsigned int)r, r1 = (int)(unsigned int)(r >> 32);
+                        if (nops > 0) {
+                            slot0 = r0 & ~kAppended; if (r0 & kAppended) s.nslots++;
+                            if (og0 == GA) s.nA += od0; else if (og0 == GB) s.nB += od0; else s.nC += od0;
+                            after0 = (double)(m.cg[C::at(slot0, h)] & kCntMask);
+                        }
+                        if (nops > 1) {
+                            slot1 = r1 & ~kAppended; if (r1 & kAppended) s.nslots++;
+                            if (og1 == GA) s.nA += od1; else if (og1 == GB) s.nB += od1; else s.nC += od1;
+                            after1 = (double)(m.cg[C::at(slot1, h)] & kCntMask);
+                        }
+                    }
+                }
                 if (ev_kind == 0) evc = after0;
                 else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
                 else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
                 const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
-                ls_commit<NH, NT, MD>(m, h, s);
+                ls_commit<NH, NT, MD>(m, h, s, D.sx, slot0, slot1);
                 if (s.tracing && s.nev < sA.max_events) {
                     coalgpu_event& r = sA.events[(unsigned long long)s.h * sA.max_events + s.nev];
                     r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
@@ -604,7 +712,7 @@ __device__ __forceinline__ void run_lockstep() {
                         m.cg[C::at(sx, h)] -= 1u;
                         if (isC) s.nC--; else if (isA) s.nA--; else s.nB--;
                     }
-                    D.xw = xw; D.xg = xg; D.ns = ns; D.n = n; D.np = np; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = pg;
+                    D.xw = xw; D.xg = xg; D.sx = sx; D.ns = ns; D.n = n; D.np = np; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = pg;
                     D.nm = isC ? 2 : 1 + Lx + np;
                     D.nq = isC ? Ltot + 1 : np;
                     D.own = isA ? Ai : Bj; D.ownC = isA ? Ci : Cj;
