@@ -284,8 +284,8 @@ int prepare_host(const coalgpu_problem* p, uint32_t Q, int table_threads, HostPr
     P.pvmax = (P.pvmax + 1) & ~1;
     P.row_doubles = lay.dev_row_doubles;
     P.SB = lay.dev_sb; P.off_wEA = lay.dev_off_wEA; P.off_wEB = lay.dev_off_wEB;
-#ifdef COAL_NO_TMA
-    P.stage_doubles = 0;                                            // comparison build: every table row is read through L1 (ld.global.nc)
+#ifndef COAL_TMA_ROWS
+    P.stage_doubles = 0;                                            // default build: every table row is read through L1 (ld.global.nc)
 #else
     P.stage_doubles = (LA + LB <= 32) ? lay.dev_row_doubles : 0;    // matches kStaged in history_kernel: longer loci read their rows through L1
 #endif
@@ -535,7 +535,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
 extern "C" {
 
 const char* coalgpu_last_error(void) { return g_err.c_str(); }
-#ifndef COAL_NO_TMA
+#ifdef COAL_TMA_ROWS
 const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged table rows)"; }
 #else
 const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }

@@ -14,8 +14,13 @@ namespace {
 constexpr int GA = COALGPU_GAMMA_A, GB = COALGPU_GAMMA_B, GC = COALGPU_GAMMA_C;
 constexpr unsigned int kCntMask = 0x3fffffffu;
 constexpr int kAppended = 0x40000000;
-#if !defined(COAL_NO_TMA) && !defined(COAL_TMA_ROWS)
-#define COAL_TMA_ROWS 1     // table rows staged into shared memory by cp.async.bulk (+5 % over ld.global.nc, profiles/r1_kernel_iterations.md)
+// Table rows: read through L1 (ld.global.nc) by default. -DCOAL_TMA builds the variant that stages the rows an event reads
+// into shared memory with cp.async.bulk + mbarrier (round 1's default: +5 % for the group form at equal occupancy). For the
+// lockstep form the staging buffers are what limits the CTAs per SM and what takes the shared-memory carve-out away from
+// L1: measured on one B200, 24-pair cfg2 mix 927 k (L1) vs 769 k (TMA) histories/s, cfg3 644 k vs 558 k, cfg4 179 k vs
+// 141 k (profiles/r2_kernel_iterations.md).
+#if defined(COAL_TMA) && !defined(COAL_TMA_ROWS)
+#define COAL_TMA_ROWS 1
 #endif
 #ifndef COAL_SLOT_UNROLL
 #define COAL_SLOT_UNROLL 1
