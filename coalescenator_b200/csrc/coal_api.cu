@@ -68,6 +68,9 @@ int ensure_kernel_attributes(int device) {
     if (done.load() & bit) return 0;
     int optin = 0;
     CU_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // tuning knob: shared-memory carve-out of the lockstep kernels in percent (the rest of the 256 KB is L1); default: the driver's choice
+    int carve = -1;
+    if (const char* c = std::getenv("COALGPU_CARVEOUT")) carve = std::max(0, std::min(100, std::atoi(c)));
     for (int W : {8, 16, 32}) for (int narrow = 0; narrow < 2; narrow++) {
         const void* fn = (const void*)history_kernel_select(W, narrow != 0);
         cudaFuncAttributes fa;
@@ -79,6 +82,7 @@ int ensure_kernel_attributes(int device) {
         cudaFuncAttributes fa;
         CU_OK(cudaFuncGetAttributes(&fa, fn));
         CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        if (carve >= 0) CU_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     }
     done.fetch_or(bit);
     return 0;
