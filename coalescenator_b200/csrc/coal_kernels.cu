@@ -7,6 +7,8 @@
 #include "coal_device.cuh"
 #include "coal_math.h"
 
+#include <cstdio>      // device printf of the -DCOAL_DEBUG_BOUNDS build
+
 namespace coalgpu {
 
 namespace {

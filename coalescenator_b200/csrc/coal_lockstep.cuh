@@ -813,6 +813,7 @@ __device__ __forceinline__ void run_lockstep() {
                 const int hh = ls_find<NH>(pre1, it);
                 const int qi = it - pre1[hh];
                 const LsDesc& D = m.desc[hh];
+                LS_ASSERT(hh < NH && qi >= 0 && qi < D.nm && D.valid);
 #ifdef COAL_TMA_ROWS
                 mbar_wait(m.mbar + hh, D.tma_parity);
 #endif
@@ -839,6 +840,7 @@ __device__ __forceinline__ void run_lockstep() {
                     const bool rel = (gj == qg) || (gj == GC);
                     const unsigned int c = rel ? (cgj & kCntMask) - ((excl && gj == qg && wj == qw) ? 1u : 0u) : 0u;
                     const int d = WO::popc((wj ^ qw) & mask);
+                    LS_ASSERT(d <= ((qg == GA) ? LA : LB));
                     const double cf = (double)c;
                     num1 += cf * tab_ld(wE1 + d);
                     num2 += cf * tab_ld(wE2 + d);
@@ -876,7 +878,7 @@ __device__ __forceinline__ void run_lockstep() {
                 // ---- class list (TypeContainer::getDifferences for a C query, TypeContainer.cpp:802-886) ----
                 unsigned long long qw64 = D.xw, delw64 = 0ull; int delg = -1; int pslot = 0;
                 if (isC) { if (qi > 0) qw64 = D.xw ^ (1ull << (qi - 1)); }
-                else { pslot = (int)m.plist[C::at(qi, hh)]; delw64 = (unsigned long long)m.words[C::at(pslot, hh)]; delg = D.pg; qw64 = D.xw | delw64; }
+                else { LS_ASSERT(qi < D.np); pslot = (int)m.plist[C::at(qi, hh)]; LS_ASSERT(pslot < ns); delw64 = (unsigned long long)m.words[C::at(pslot, hh)]; delg = D.pg; qw64 = D.xw | delw64; }
                 const typename WO::T qw = WO::narrow(qw64), delw = WO::narrow(delw64);
 #pragma unroll 1
                 for (int sidx = 0; sidx < nsum; sidx++) mine[sidx * NT] = 0xffff0000u;
@@ -921,6 +923,7 @@ __device__ __forceinline__ void run_lockstep() {
                             const unsigned int rep = v >> 16;
                             int dA, dB;
                             if (rep == 0) { dA = sidx; dB = -1; } else if (rep == 1) { dA = -1; dB = sidx; } else { dA = (int)rep - 2; dB = sidx - 1 - dA; }
+                            LS_ASSERT(dA <= LA && dB <= LB && (dA >= 0 || dB >= 0));
                             nH++;
                             tot.n += cnt;
                             if (dA >= 0) { tot.ncompA += cnt; vecA[dA * NT] += cnt | (dB < 0 ? cnt << 16 : 0u); }

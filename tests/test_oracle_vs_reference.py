@@ -67,6 +67,26 @@ def test_canonical_mode_agrees_statistically(oracle):
     assert abs(a - b) < 5 * np.hypot(sa, sb) + 0.05, (est)
 
 
+@pytest.mark.parametrize("name,n", [("cfg1_pair0", 4000), ("missing_pair3", 6000)])
+def test_canonical_mode_against_20000_reference_histories(oracle, name, n):
+    """The same link against a large run of the compiled reference itself (tests/golden/<name>.big_result.json, 20,000
+    histories, effective sample size 237 / 569): CANONICAL mode's log mean weight within 4 combined standard errors."""
+    import json, os
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, name + ".big_result.json")))
+    p, _, _ = load_golden(name)
+    r = oracle.run(p, n, 31337, mode=oracle.MODE_CANONICAL)
+    lw = r["weights"][:, 0]
+    m = lw.max()
+    w = np.exp(lw - m)
+    mine, se_mine = np.log(w.mean()) + m, np.sqrt(max((w ** 2).sum() / w.sum() ** 2 - 1.0 / n, 0))
+    rl, rl2, n_ref = ref["likelihood"][0], ref["likelihoodSq"][0], ref["n_samples"]
+    ref_like, ref_se = rl - np.log(n_ref), np.sqrt(max(np.exp(rl2 - 2 * rl) - 1.0 / n_ref, 0))
+    z = (mine - ref_like) / np.hypot(se_mine, ref_se)
+    print(name, "log mean w: CANONICAL", mine, "reference", ref_like, "z", z)
+    assert abs(z) < 4.0
+
+
 def test_philox_known_answer(oracle):
     # Philox4x32-10 known-answer test from the Random123 distribution (kat_vectors):
     # counter = key = 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
