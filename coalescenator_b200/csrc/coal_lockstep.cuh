@@ -203,17 +203,21 @@ __device__ __forceinline__ int ls_adjust(const LsCta<NH, NT, MD>&, int h, LsHist
 }
 
 // The two type changes of a backward move (ProposalEngine.cpp:242-294, 342-371, 418-448: at most two addType / removeType
-// calls) in ONE pass over the stored types: exactly ls_adjust_core(op 0) followed by ls_adjust_core(op 1) -- op 1 sees the
-// count op 0 left in its slot and the slot op 0 appended --, with one walk, one pair of loads per slot and two independent
-// match computations per iteration instead of two dependent walks. An op without work passes active = false.
-// Returns slot 0 | slot 1 << 32 (each as ls_adjust_core returns it).
-template <int NH, int NT, int MD>
-__device__ __noinline__ unsigned long long ls_adjust2_core(int h, int ns, int g0, unsigned long long w0_64, int delta0, bool act0,
-                                                            int g1, unsigned long long w1_64, int delta1, bool act1) {
+// calls) in ONE cooperative pass over the stored types: exactly ls_adjust_core(op 0) followed by ls_adjust_core(op 1) -- op 1
+// sees the count op 0 left in its slot and the slot op 0 appended. Called by ALL lanes of a warp at a convergent point: the
+// LPH lanes of a history (its serial thread is the first of them) walk the store LPH slots at a time and combine what they
+// found with shuffles; the serial thread then appends what is not stored yet. Arguments are those of the lane's history
+// (already broadcast from its serial thread); op: bit 0 / 1 = op 0 / 1 has work, bits 2-3 / 4-5 their classes.
+// Returns slot 0 | slot 1 << 32 (each as ls_adjust_core returns it; valid on the serial thread).
+template <int NH, int NT, int MD, int LPH>
+__device__ __noinline__ unsigned long long ls_adjust2_coop(int h, int sub, int ns, int op, unsigned long long w0_64, int delta0,
+                                                            unsigned long long w1_64, int delta1) {
     typedef LsCta<NH, NT, MD> C;
     typedef typename C::WO WO;
     typedef typename WO::T W;
     C m; m.bind();
+    const bool act0 = (op & 1) != 0, act1 = (op & 2) != 0;
+    const int g0 = (op >> 2) & 3, g1 = (op >> 4) & 3;
     const W maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB), ones = (W)~(W)0;
     const W w0 = WO::narrow(w0_64), w1 = WO::narrow(w1_64);
     // match rules as in ls_adjust_core; an inactive op gets class 7, which no slot has
@@ -227,8 +231,8 @@ __device__ __noinline__ unsigned long long ls_adjust2_core(int h, int ns, int g0
     int found0 = -1, found1 = -1;
     unsigned int newxc0 = 0, newxc1 = 0;
     const int nloop = (act0 || act1) ? ns : 0;
-#pragma unroll kLsUnrollS
-    for (int j = 0; j < nloop; j++) {
+#pragma unroll 1
+    for (int j = sub; j < nloop; j += LPH) {
         const W wj = m.words[C::at(j, h)];
         const unsigned int cgj = m.cg[C::at(j, h)];
         const int gj = (int)(cgj >> 30);
@@ -244,6 +248,14 @@ __device__ __noinline__ unsigned long long ls_adjust2_core(int h, int ns, int g0
         const unsigned int xadd = (h1a ? d1a : 0u) + (h2a ? d2a : 0u) + (h1b ? d1b : 0u) + (h2b ? d2b : 0u);
         if (xadd) m.xc[C::at(j, h)] += xadd;
     }
+    // combine over the lanes of the history (a type is stored at most once: max picks the slot)
+#pragma unroll
+    for (int o = 1; o < LPH; o <<= 1) {
+        found0 = max(found0, __shfl_xor_sync(kFull, found0, o)); found1 = max(found1, __shfl_xor_sync(kFull, found1, o));
+        newxc0 += __shfl_xor_sync(kFull, newxc0, o); newxc1 += __shfl_xor_sync(kFull, newxc1, o);
+    }
+    __syncwarp();                                           // the cross-count updates above are visible to the serial thread
+    if (sub != 0) return 0ull;
     unsigned int r0 = 0xfffffffeu, r1 = 0xfffffffeu;       // -2: no op
     if (act0) {
         r0 = (unsigned int)found0;
@@ -337,16 +349,17 @@ __device__ __forceinline__ void run_lockstep() {
     typedef typename C::WO WO;
     C m; m.bind();
     const int tid = threadIdx.x;
-    // Serial threads: the histories of the CTA are dealt to its warps (NH / warps each, the first lanes of every warp),
-    // so the warps run their serial phases side by side and fewer histories share -- and serialise -- one warp's branches.
-#ifndef COAL_LS_SPREAD
-#define COAL_LS_SPREAD 1
-#endif
+    // The histories of the CTA are dealt to its warps (HPW = NH / warps each), so the warps run their serial phases side by
+    // side and fewer histories share -- and serialise -- one warp's branches. Within a warp a history owns LPH = 32 / HPW
+    // consecutive lanes: the first is its serial thread, all of them walk its type store in the cooperative passes.
     constexpr int kWarps = NT / 32;
-    constexpr int HPW = COAL_LS_SPREAD ? NH / kWarps : NH;           // histories per serial warp
+    constexpr int HPW = NH / kWarps;                                 // histories per warp
+    constexpr int LPH = 32 / HPW;                                    // lanes per history in the cooperative passes
+    static_assert(HPW * kWarps == NH && LPH * HPW == 32 && LPH >= 1, "lockstep shape");
     const int lane = tid & 31, warp = tid >> 5;
-    const bool serial = COAL_LS_SPREAD ? (lane < HPW) : (tid < NH);
-    const int h = COAL_LS_SPREAD ? warp * HPW + lane : tid;          // history slot of a serial thread
+    const int sub = lane & (LPH - 1), leader = lane & ~(LPH - 1);
+    const bool serial = (sub == 0);
+    const int h = warp * HPW + lane / LPH;                           // history slot of this lane (its serial thread: lane `leader`)
     int* const pre1 = m.pre1 + warp * (NH + 1);
     int* const pre2 = m.pre2 + warp * (NH + 1);
     const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
@@ -386,9 +399,13 @@ __device__ __forceinline__ void run_lockstep() {
     for (;;) {
         int snap_flags = 0;
         // =================================== S: one thread per history ===================================
+        // values that cross from the first serial section (S1) over the cooperative store pass into the second (S2)
+        bool end_now = false;
+        int mv_op = 0, mv_d0 = 0, mv_d1 = 0, mv_kind = 1;          // op bits as ls_adjust2_coop takes them; event kind
+        unsigned long long mv_w0 = 0ull, mv_w1 = 0ull;
+        double mv_evc = 1.0;
         if (serial && !s.done) {
             LsDesc& D = m.desc[h];
-            bool end_now = false;
             // ---- finish the event of the previous step (ProposalEngine.cpp:241-294, 341-371, 417-448, 455-546) ----
             if (s.pending) {
                 s.pending = false;
@@ -472,51 +489,71 @@ __device__ __forceinline__ void run_lockstep() {
                 } else {
                     evc = isA ? (double)((unsigned int)Ac * (Ai + Ci - 1)) : (double)((unsigned int)Bc * (Bj + Cj - 1));
                 }
-                double after0 = 1.0, after1 = 1.0;
-                int slot0 = -1, slot1 = -1;
-                {
-                    const unsigned long long r = ls_adjust2_core<NH, NT, MD>(h, s.nslots, og0, ow0, od0, nops > 0, og1, ow1, od1, nops > 1);
-                    if (r == 0xffffffffffffffffull) s.overflow = true;
-                    else {
-                        const int r0 = (int)(unsigned int)r, r1 = (int)(unsigned int)(r >> 32);
-                        if (nops > 0) {
-                            slot0 = r0 & ~kAppended; if (r0 & kAppended) s.nslots++;
-                            if (og0 == GA) s.nA += od0; else if (og0 == GB) s.nB += od0; else s.nC += od0;
-                            after0 = (double)(m.cg[C::at(slot0, h)] & kCntMask);
-                        }
-                        if (nops > 1) {
-                            slot1 = r1 & ~kAppended; if (r1 & kAppended) s.nslots++;
-                            if (og1 == GA) s.nA += od1; else if (og1 == GB) s.nB += od1; else s.nC += od1;
-                            after1 = (double)(m.cg[C::at(slot1, h)] & kCntMask);
-                        }
-                    }
-                }
-                if (ev_kind == 0) evc = after0;
-                else if (ev_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
-                else if (ev_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
-                const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
-                ls_commit<NH, NT, MD>(m, h, s, D.sx, slot0, slot1);
+                // bookkeeping that does not depend on the store (:457-546); the type changes follow in the cooperative pass
                 if (s.tracing && s.nev < sA.max_events) {
                     coalgpu_event& r = sA.events[(unsigned long long)s.h * sA.max_events + s.nev];
                     r.chosen_word = xw; r.aux_word = ev_aux; r.chosen_gamma = (uint8_t)xg; r.kind = (uint8_t)ev_kind;
                     r.epoch = (uint8_t)s.e; r.site = (uint8_t)ev_site; r.n_before = (uint32_t)n;
                 }
                 s.nev++;
-                // ---- target density bookkeeping (:457-546) ----
                 s.tsum += D.wait;
-                if (ns_event > s.peak) s.peak = ns_event;
                 s.qsum += -D.rate * D.wait;
                 s.qprod.mul(qfac);
-                s.evprod.mul(evc);
                 s.st.s_nn += D.nn * D.wait; s.st.s_a += D.aa * D.wait; s.st.s_c += (double)Cc * D.wait;
                 if (kind == 1) s.st.n_mut++; else if (kind == 2) s.st.n_rec++;
                 if (s.post) { s.st.has_post = 1; s.st.post_nn = D.nn; s.st.post_a = D.aa; s.st.post_c = (double)Cc; }
                 else s.st.n_rate++;
                 s.post = false;
-                if (s.nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
-                end_now = s.overflow;
+                mv_op = (nops > 0 ? 1 : 0) | (nops > 1 ? 2 : 0) | (og0 << 2) | (og1 << 4) | 64;      // bit 6: a move was drawn
+                mv_w0 = ow0; mv_w1 = ow1; mv_d0 = od0; mv_d1 = od1; mv_kind = ev_kind; mv_evc = evc;
                 }
             }
+        }
+        // =================================== W1: the move's type changes, LPH lanes per history ===================================
+        {
+            const int opq = __shfl_sync(kFull, mv_op, leader);
+            const int nsq = __shfl_sync(kFull, s.nslots, leader);
+            const unsigned long long w0q = __shfl_sync(kFull, mv_w0, leader), w1q = __shfl_sync(kFull, mv_w1, leader);
+            const int d0q = __shfl_sync(kFull, mv_d0, leader), d1q = __shfl_sync(kFull, mv_d1, leader);
+            unsigned long long r = 0ull;
+            if (__any_sync(kFull, (opq & 3) != 0)) r = ls_adjust2_coop<NH, NT, MD, LPH>(h, sub, nsq, opq, w0q, d0q, w1q, d1q);
+            if (serial && (mv_op & 64)) {
+                LsDesc& D = m.desc[h];
+                const int og0 = (mv_op >> 2) & 3, og1 = (mv_op >> 4) & 3;
+                const int Ac = D.Ac, Bc = D.Bc, Cc = D.Cc;
+                double after0 = 1.0, after1 = 1.0;
+                int slot0 = -1, slot1 = -1;
+                if ((mv_op & 3) != 0) {
+                    if (r == 0xffffffffffffffffull) s.overflow = true;
+                    else {
+                        const int r0 = (int)(unsigned int)r, r1 = (int)(unsigned int)(r >> 32);
+                        if (mv_op & 1) {
+                            slot0 = r0 & ~kAppended; if (r0 & kAppended) s.nslots++;
+                            if (og0 == GA) s.nA += mv_d0; else if (og0 == GB) s.nB += mv_d0; else s.nC += mv_d0;
+                            after0 = (double)(m.cg[C::at(slot0, h)] & kCntMask);
+                        }
+                        if (mv_op & 2) {
+                            slot1 = r1 & ~kAppended; if (r1 & kAppended) s.nslots++;
+                            if (og1 == GA) s.nA += mv_d1; else if (og1 == GB) s.nB += mv_d1; else s.nC += mv_d1;
+                            after1 = (double)(m.cg[C::at(slot1, h)] & kCntMask);
+                        }
+                    }
+                }
+                double evc = mv_evc;
+                if (mv_kind == 0) evc = after0;
+                else if (mv_kind == 4) evc = (double)Cc * after0 * after1 / (((double)Ac + 1.0) * ((double)Bc + 1.0));
+                else if (mv_kind == 5) evc = (double)((unsigned int)Ac * (unsigned int)Bc) * after1 / ((double)Cc + 1.0);
+                const int ns_event = s.nslots;      // slots in use before the empty ones are dropped: the event's peak
+                ls_commit<NH, NT, MD>(m, h, s, D.sx, slot0, slot1);
+                if (ns_event > s.peak) s.peak = ns_event;
+                s.evprod.mul(evc);
+                if (s.nev >= (1u << 18)) s.overflow = true;   // runaway guard: histories have O(10^2-10^3) events
+                end_now = s.overflow;
+            }
+        }
+        // =================================== S2: one thread per history ===================================
+        if (serial && !s.done) {
+            LsDesc& D = m.desc[h];
             D.valid = 0; D.nm = 0; D.nq = 0;
 
             // ---- fetch the next history ----
