@@ -609,31 +609,50 @@ __device__ __forceinline__ void run_lockstep() {
                 end_now = s.overflow;
             }
 
+        }
+        // =================================== W2: lineage-chooser weights, LPH lanes per history ===================================
+        // (TypeContainer::sampleType, TypeContainer.cpp:641-721): pv[j] = weight of slot j; summed in slot order by
+        // the serial thread below (the order of the sum is part of the canonical arithmetic)
+        {
+            __syncwarp();                  // the store as the serial threads left it (appended slots, injected types)
+            const int actq = __shfl_sync(kFull, (serial && !s.done && !end_now) ? 1 : 0, leader);
+            const int nsq = __shfl_sync(kFull, s.nslots, leader), eq = __shfl_sync(kFull, s.e, leader);
+            const unsigned int nAq = (unsigned int)__shfl_sync(kFull, s.nA, leader), nBq = (unsigned int)__shfl_sync(kFull, s.nB, leader);
+            const EpochConst* __restrict__ ecq = sP.ep + eq;
+            const double dthA = __ldg(&ecq->dthA), dthB = __ldg(&ecq->dthB), drho_e = __ldg(&ecq->drho);
+            const int nl = actq ? nsq : 0;
+#pragma unroll 1
+            for (int j = sub; j < nl; j += LPH) {
+                const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
+                const unsigned int c = cgj & kCntMask;
+                const int gj = (int)(cgj >> 30);
+                // one instruction sequence for the three classes (adding 0.0 to a non-negative sum is exact):
+                //   C: (c-1 + thA+thB + rho + cA + cB) c     A: (c-1 + nB + cCa + thA) c     B: (c-1 + nA + cCb + thB) c
+                const bool jC = (gj == GC);
+                const unsigned int ti = c - 1 + (jC ? 0u : ((gj == GA ? nBq : nAq) + xcj));
+                double v = (double)ti + (jC ? (dthA + dthB) : (gj == GA ? dthA : dthB));
+                v = v + (jC ? drho_e : 0.0);
+                v = v + (jC ? (double)(xcj & 0xffffu) : 0.0);
+                v = v + (jC ? (double)(xcj >> 16) : 0.0);
+                m.pv[C::at(j, h)] = v * (double)c;
+            }
+            __syncwarp();
+        }
+        // =================================== S3: one thread per history ===================================
+        // values that cross from S3 over the cooperative removal pass into S4
+        int rm_op = 0, rm_sx = 0;                  // bit 0: an event is being set up; bits 1-2: class of the chosen lineage
+        unsigned long long rm_xw = 0ull;
+        if (serial && !s.done) {
+            LsDesc& D = m.desc[h];
             bool finish = false;
-            if (!s.done && !end_now) {
+            if (!end_now) {
                 // ---- choose a lineage and a waiting time (ProposalEngine.cpp:672-687 / 703-716) ----
                 const EpochConst* __restrict__ ecp = sP.ep + s.e;
                 const double dthA = __ldg(&ecp->dthA), dthB = __ldg(&ecp->dthB), drho_e = __ldg(&ecp->drho);
-                // lineage-chooser weights (TypeContainer::sampleType, TypeContainer.cpp:641-721)
                 const int ns0 = s.nslots;
                 double hap_den = 0.0;
 #pragma unroll kLsUnrollS
-                for (int j = 0; j < ns0; j++) {
-                    const unsigned int cgj = m.cg[C::at(j, h)], xcj = m.xc[C::at(j, h)];
-                    const unsigned int c = cgj & kCntMask;
-                    const int gj = (int)(cgj >> 30);
-                    // one instruction sequence for the three classes (adding 0.0 to a non-negative sum is exact):
-                    //   C: (c-1 + thA+thB + rho + cA + cB) c     A: (c-1 + nB + cCa + thA) c     B: (c-1 + nA + cCb + thB) c
-                    const bool jC = (gj == GC);
-                    const unsigned int ti = c - 1 + (jC ? 0u : ((gj == GA ? (unsigned int)s.nB : (unsigned int)s.nA) + xcj));
-                    double v = (double)ti + (jC ? (dthA + dthB) : (gj == GA ? dthA : dthB));
-                    v = v + (jC ? drho_e : 0.0);
-                    v = v + (jC ? (double)(xcj & 0xffffu) : 0.0);
-                    v = v + (jC ? (double)(xcj >> 16) : 0.0);
-                    const double wgt = v * (double)c;
-                    m.pv[C::at(j, h)] = wgt;
-                    hap_den += wgt;
-                }
+                for (int j = 0; j < ns0; j++) hap_den += m.pv[C::at(j, h)];
                 double hap_num;
                 int sx;
                 if (sA.score_off) {          // score mode: the given lineage
@@ -686,8 +705,6 @@ __device__ __forceinline__ void run_lockstep() {
                     const int xg = (int)(xcg >> 30);
                     const unsigned int xcount = xcg & kCntMask;
                     const bool isC = (xg == GC), isA = (xg == GA);
-                    const typename WO::T xa = WO::narrow(xw & sP.maskA), xb = WO::narrow(xw & sP.maskB);
-                    const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
                     unsigned int Cij = 0, Ci = 0, Cj = 0, Ai = 0, Bj = 0;
                     if (isC) { Cij = xcount; Ai = xxc & 0xffffu; Bj = xxc >> 16; }
                     else if (isA) { Ai = xcount; Ci = xxc; } else { Bj = xcount; Cj = xxc; }
@@ -717,54 +734,90 @@ __device__ __forceinline__ void run_lockstep() {
                     D.crow = isC ? D.row_m1 : D.row_alt;
                     D.tma_parity = 0;
 #endif
-                    // ONE pass over the stored types: H' = H - x (:168; the cross counts of the related slots follow, as in
-                    // ls_adjust_core with delta = -1 -- x is stored, nothing is appended), the counts of the C types that share
-                    // x's A part / B part BEFORE the removal (:149-158), and the partner list = stored types of the other
-                    // one-locus class, slot order (:300 / :377; the removal does not touch that class).
-                    const int ns = ns0;
+                    // what of the descriptor does not depend on the removal pass
                     const int Lx = isC ? Ltot : (isA ? LA : LB);
-                    const int pg = isA ? GB : GA;
-                    int np = 0;
-                    {
-                        const typename WO::T xwn = WO::narrow(xw);
-                        // match rules of the removal (see ls_adjust_core): which slots' cross counts lose one
-                        const int t1 = isC ? GA : GC, t2 = isC ? GB : 3;
-                        const typename WO::T m1 = isA ? maskA : (isC ? (typename WO::T)~(typename WO::T)0 : maskB);
-                        const typename WO::T k1 = isC ? xa : xwn;
-                        const unsigned int d1 = (!isC && !isA) ? 65536u : 1u;
-#pragma unroll kLsUnrollS
-                        for (int j = 0; j < ns; j++) {
-                            const typename WO::T wj = m.words[C::at(j, h)];
-                            const unsigned int cgj = m.cg[C::at(j, h)];
-                            const int gj = (int)(cgj >> 30);
-                            const unsigned int cj = cgj & kCntMask;
-                            const bool jC = (gj == GC);
-                            Ci += (isC && jC && (wj & maskA) == xa) ? cj : 0u;
-                            Cj += (isC && jC && (wj & maskB) == xb) ? cj : 0u;
-                            const bool h1 = (gj == t1) && ((wj & m1) == k1), h2 = (gj == t2) && (wj == xb);
-                            const unsigned int xsub = (h1 ? d1 : 0u) + (h2 ? 1u : 0u);
-                            if (xsub) m.xc[C::at(j, h)] -= xsub;
-                            if (!isC && gj == pg && cj > 0) { m.plist[C::at(np, h)] = (unsigned short)j; np++; }
-                        }
-                        m.cg[C::at(sx, h)] -= 1u;
-                        if (isC) s.nC--; else if (isA) s.nA--; else s.nB--;
-                    }
-                    D.xw = xw; D.xg = xg; D.sx = sx; D.ns = ns; D.n = n; D.np = np; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = pg;
-                    D.nm = isC ? 2 : 1 + Lx + np;
-                    D.nq = isC ? Ltot + 1 : np;
-                    D.own = isA ? Ai : Bj; D.ownC = isA ? Ci : Cj;
-                    D.Cij = Cij; D.Ci = Ci; D.Cj = Cj; D.Ai = Ai; D.Bj = Bj; D.Ac = Ac; D.Bc = Bc; D.Cc = Cc;
+                    D.xw = xw; D.xg = xg; D.sx = sx; D.ns = ns0; D.n = n; D.Lx = Lx; D.offb = (xg == GB) ? LA : 0; D.pg = isA ? GB : GA;
+                    D.Cij = Cij; D.Ai = Ai; D.Bj = Bj; D.Ac = Ac; D.Bc = Bc; D.Cc = Cc;
+                    D.Ci = Ci; D.Cj = Cj;          // one-locus lineage: from its cross count; two-locus: counted by the pass
                     D.cn = isC ? (unsigned int)(n - 1) : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
                     D.nc_alt = isC ? (unsigned int)n : (unsigned int)(n - 2 < 0 ? 0 : n - 2);
                     D.dtheta_e = __ldg(&ecp->dtheta); D.drho_e = drho_e;
-                    D.dtheta_own = D.dtheta_e * (double)D.own;
+                    D.dtheta_own = D.dtheta_e * (double)(isA ? Ai : Bj);
                     D.rate = rate; D.wait = wait; D.hap_num = hap_num; D.hap_den = hap_den; D.nn = nn; D.aa = aa;
+                    rm_op = 1 | (xg << 1); rm_sx = sx; rm_xw = xw;
+                }
+            }
+        }
+        // =================================== W3: remove the chosen lineage, LPH lanes per history ===================================
+        // ONE pass over the stored types: H' = H - x (:168; the cross counts of the related slots follow, as in ls_adjust_core
+        // with delta = -1 -- x is stored, nothing is appended), the counts of the C types that share x's A part / B part BEFORE
+        // the removal (:149-158), and the partner list = stored types of the other one-locus class in slot order (:300 / :377;
+        // the removal does not touch that class): the lanes of a history take LPH consecutive slots per round and rank their
+        // partners with a ballot.
+        {
+            const int opq = __shfl_sync(kFull, rm_op, leader);
+            if (__any_sync(kFull, opq != 0)) {
+                const unsigned long long xwq = __shfl_sync(kFull, rm_xw, leader);
+                const int nsq = __shfl_sync(kFull, s.nslots, leader);
+                const int nl = (opq & 1) ? nsq : 0;
+                const int xg = opq >> 1;
+                const bool isC = (xg == GC), isA = (xg == GA);
+                const int pg = isA ? GB : GA;
+                const typename WO::T maskA = WO::narrow(sP.maskA), maskB = WO::narrow(sP.maskB);
+                const typename WO::T xwn = WO::narrow(xwq), xa = xwn & maskA, xb = xwn & maskB;
+                // match rules of the removal (see ls_adjust_core): which slots' cross counts lose one
+                const int t1 = isC ? GA : GC, t2 = isC ? GB : 3;
+                const typename WO::T m1 = isA ? maskA : (isC ? (typename WO::T)~(typename WO::T)0 : maskB);
+                const typename WO::T k1 = isC ? xa : xwn;
+                const unsigned int d1 = (!isC && !isA) ? 65536u : 1u;
+                unsigned int Ci = 0, Cj = 0;
+                int np = 0;
+                const int nrounds = (__reduce_max_sync(kFull, nl) + LPH - 1) / LPH;
+                const unsigned int below = (1u << sub) - 1u, mine_mask = (LPH == 32) ? 0xffffffffu : ((1u << LPH) - 1u);
+#pragma unroll 1
+                for (int i = 0; i < nrounds; i++) {
+                    const int j = i * LPH + sub;
+                    bool partner = false;
+                    if (j < nl) {
+                        const typename WO::T wj = m.words[C::at(j, h)];
+                        const unsigned int cgj = m.cg[C::at(j, h)];
+                        const int gj = (int)(cgj >> 30);
+                        const unsigned int cj = cgj & kCntMask;
+                        const bool jC = (gj == GC);
+                        Ci += (isC && jC && (wj & maskA) == xa) ? cj : 0u;
+                        Cj += (isC && jC && (wj & maskB) == xb) ? cj : 0u;
+                        const bool h1 = (gj == t1) && ((wj & m1) == k1), h2 = (gj == t2) && (wj == xb);
+                        const unsigned int xsub = (h1 ? d1 : 0u) + (h2 ? 1u : 0u);
+                        if (xsub) m.xc[C::at(j, h)] -= xsub;
+                        partner = !isC && gj == pg && cj > 0;
+                    }
+                    const unsigned int bits = (__ballot_sync(kFull, partner) >> leader) & mine_mask;
+                    if (partner) m.plist[C::at(np + __popc(bits & below), h)] = (unsigned short)j;
+                    np += __popc(bits);
+                }
+#pragma unroll
+                for (int o = 1; o < LPH; o <<= 1) { Ci += __shfl_xor_sync(kFull, Ci, o); Cj += __shfl_xor_sync(kFull, Cj, o); }
+                __syncwarp();
+                // ---- S4: publish the event (ProposalEngine.cpp:134-238, 298-338, 375-414) ----
+                if (serial && (rm_op & 1)) {
+                    LsDesc& D = m.desc[h];
+                    m.cg[C::at(rm_sx, h)] -= 1u;
+                    if (isC) s.nC--; else if (isA) s.nA--; else s.nB--;
+                    if (isC) { D.Ci = Ci; D.Cj = Cj; }
+                    D.np = np;
+                    D.nm = isC ? 2 : 1 + D.Lx + np;
+                    D.nq = isC ? Ltot + 1 : np;
+                    D.own = isA ? D.Ai : D.Bj; D.ownC = isA ? D.Ci : D.Cj;
                     D.valid = 1;
                     s.pending = true;
                     s.ncq += (unsigned int)D.nq;
-                    LS_ASSERT(Lx + np + 1 <= sP.pvmax && np <= sP.kmax);
+                    LS_ASSERT(D.Lx + np + 1 <= sP.pvmax && np <= sP.kmax);
                 }
             }
+        }
+        // =================================== S5: histories that end in this step ===================================
+        if (serial && !s.done) {
+            LsDesc& D = m.desc[h];
 
             if (end_now) {
                 // ---- final weight (ProposalEngine.cpp:817-858) ----
@@ -788,8 +841,8 @@ __device__ __forceinline__ void run_lockstep() {
                 s.have = false; s.pending = false;
                 D.valid = 0; D.nm = 0; D.nq = 0;
             }
-            m.snap[h].flags = snap_flags;
         }
+        if (serial) m.snap[h].flags = snap_flags;      // also by a thread that just ran out of histories: a stale flag would be scored again
         const int alive = __syncthreads_or((serial && !s.done) ? 1 : 0);
         LS_TICK(tS);
         if (!alive) break;
