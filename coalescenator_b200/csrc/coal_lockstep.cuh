@@ -585,30 +585,52 @@ __device__ __forceinline__ void run_lockstep() {
                 }
             }
 
-            if (!s.done && !end_now && s.injecting) {
-                // TypeContainer::addTypeMap :525-591 + probabilityCombinatorics ProposalEngine.cpp:66-86
+        }
+        // =================================== W0: injections, LPH lanes per history ===================================
+        // TypeContainer::addTypeMap :525-591 + probabilityCombinatorics ProposalEngine.cpp:66-86. The sampled types of a
+        // collection enter the store one after the other (the order fixes the slot order); each is one cooperative pass of the
+        // history's lanes, and the histories of a warp that inject in the same step share the rounds.
+        {
+            const bool inj = serial && !s.done && !end_now && s.injecting;
+            const int injq = __shfl_sync(kFull, inj ? 1 : 0, leader);
+            if (__any_sync(kFull, injq != 0)) {
+                const int loq = __shfl_sync(kFull, s.inj_lo, leader), hiq = __shfl_sync(kFull, s.inj_hi, leader);
+                const int nrounds = __reduce_max_sync(kFull, injq ? hiq - loq : 0);
                 const int a0 = s.nA, b0 = s.nB, c0 = s.nC;
                 double comb = 0.0;
 #pragma unroll 1
-                for (int k = s.inj_lo; k < s.inj_hi; k++) {
-                    const unsigned int cgk = sP.type_cg[k];
-                    const int add = (int)(cgk & kCntMask);
-                    const int slot = ls_adjust<NH, NT, MD>(m, h, s, (int)(cgk >> 30), sP.type_w[k], add);
-                    if (slot < 0) break;
-                    const int now = (int)(m.cg[C::at(slot, h)] & kCntMask);
-                    comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
+                for (int r = 0; r < nrounds; r++) {
+                    const int k = loq + r;
+                    const int nsq = __shfl_sync(kFull, s.nslots, leader);
+                    const int stopq = __shfl_sync(kFull, s.overflow ? 1 : 0, leader);
+                    const bool act = injq && k < hiq && !stopq;
+                    const unsigned int cgk = act ? __ldg(sP.type_cg + k) : 0u;
+                    const unsigned long long wk = act ? __ldg(sP.type_w + k) : 0ull;
+                    const int add = (int)(cgk & kCntMask), gk = (int)(cgk >> 30);
+                    const unsigned long long rr = ls_adjust2_coop<NH, NT, MD, LPH>(h, sub, nsq, act ? (1 | (gk << 2)) : 0, wk, add, 0ull, 0);
+                    if (serial && act) {
+                        if (rr == 0xffffffffffffffffull) s.overflow = true;
+                        else {
+                            const int r0 = (int)(unsigned int)rr;
+                            const int slot = r0 & ~kAppended; if (r0 & kAppended) s.nslots++;
+                            if (gk == GA) s.nA += add; else if (gk == GB) s.nB += add; else s.nC += add;
+                            const int now = (int)(m.cg[C::at(slot, h)] & kCntMask);
+                            comb += sP.lfact[now] - sP.lfact[add] - sP.lfact[now - add];
+                        }
+                    }
                 }
-                if (s.e > 0 && !s.overflow) {
-                    comb -= sP.lfact[s.nA] - sP.lfact[s.nA - a0] - sP.lfact[a0];
-                    comb -= sP.lfact[s.nB] - sP.lfact[s.nB - b0] - sP.lfact[b0];
-                    comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
-                    s.consts += comb;
+                if (inj) {
+                    if (s.e > 0 && !s.overflow) {
+                        comb -= sP.lfact[s.nA] - sP.lfact[s.nA - a0] - sP.lfact[a0];
+                        comb -= sP.lfact[s.nB] - sP.lfact[s.nB - b0] - sP.lfact[b0];
+                        comb -= sP.lfact[s.nC] - sP.lfact[s.nC - c0] - sP.lfact[c0];
+                        s.consts += comb;
+                    }
+                    if (s.nslots > s.peak) s.peak = s.nslots;
+                    s.injecting = false;
+                    end_now = s.overflow;
                 }
-                if (s.nslots > s.peak) s.peak = s.nslots;
-                s.injecting = false;
-                end_now = s.overflow;
             }
-
         }
         // =================================== W2: lineage-chooser weights, LPH lanes per history ===================================
         // (TypeContainer::sampleType, TypeContainer.cpp:641-721): pv[j] = weight of slot j; summed in slot order by
