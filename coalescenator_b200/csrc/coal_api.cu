@@ -109,6 +109,7 @@ struct coalgpu_sampler {
     int inj_max = 0, sm_count = 0;    // most input types of one sampling time; SMs of the device
     int type_estimate = 0;            // HostPrep::type_estimate
     bool rows_on_device_only = false; // emission parts were built on the device: coalgpu_tables fetches the rows first
+    bool pilot_useful = false;        // choose_geometry: a measured peak could still raise the histories per SM
     bool fast = false, fast_forced = false;   // forced: COALGPU_KMAX_FAST > 0 (tests), two passes whatever the launch size
     DevProblem P_fast{};
     int fast_grid = 0, fast_group = 32;
@@ -403,6 +404,16 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
         const int need = peak > 0 ? peak : s->type_estimate + 4;
         cand.push_back(std::max(32, ((need + std::max(4, need / 8) + 7) / 8) * 8));
         allow8 = need <= 44;
+        if (peak == 0 && want_lockstep()) {
+            // An ESTIMATED need is an upper bound more often than not (measured peaks are 0.64-1.1x of it). When the store sized
+            // for it costs a CTA per SM against the smallest store, take the largest store that does not -- as long as that
+            // still covers three quarters of the estimate; a history that needs more is deferred to the full store, not lost.
+            const int kmin = std::min(32, P.kmax);
+            const int best = geometry_for(P, kmin, pv_for(kmin), false).per_sm;
+            int k = std::min(cand[0], P.kmax);
+            while (k > kmin && geometry_for(P, k, pv_for(k), false).per_sm < best) k -= 8;
+            if (k < cand[0] && 4 * k >= 3 * need) cand[0] = k;
+        }
         for (int kf : {256, 128, 64}) if (kf > cand[0] && kf >= 2 * s->inj_max + 8) cand.push_back(kf);   // larger stores that still raise the occupancy
     }
     auto pick = [&](bool with8, DevProblem& Pout, int& grid, int& group, size_t& smem, bool& ls) -> bool {
@@ -424,6 +435,15 @@ int choose_geometry(coalgpu_sampler* s, int peak) {
     s->fast = pick(allow8, s->P_fast, s->fast_grid, s->fast_group, s->fast_smem, s->fast_ls);
     s->fast_forced = s->fast && forced > 0;
     s->wide = pick(false, s->P_wide, s->wide_grid, s->wide_group, s->wide_smem, s->wide_ls);
+    // Would knowing the histories' real need (coalgpu_tune after a pilot chunk) put more histories on an SM than the
+    // input-based estimate does? Only then is a pilot worth one history's latency (coalgpu_run_sampler). With the lockstep
+    // form the register file caps the CTAs per SM long before a 32-48 slot store does, so usually it is not.
+    {
+        const int kmin = std::min(32, P.kmax);
+        const Geometry gmin = geometry_for(P, kmin, pv_for(kmin), true);
+        const int now = s->fast ? (s->fast_grid / std::max(1, s->sm_count)) * geo_hist_per_cta(s->fast_group, s->fast_ls) : full.per_sm;
+        s->pilot_useful = peak == 0 && forced == 0 && gmin.per_sm > now;
+    }
     return 0;
 }
 
@@ -875,7 +895,7 @@ static int sample_range(coalgpu_sampler* s, uint64_t seed, uint64_t first0, uint
     // A long run starts with a pilot chunk; the reduced type store and the geometry of the rest are sized from what the
     // pilot histories needed (coalgpu_tune) instead of the input-based estimate. The pilot drains the device once, about
     // one history's latency: worth it from ~16x what the device holds in flight.
-    const uint64_t pilot = count >= 16 * (uint64_t)s->grid * geo_hist_per_cta(s->group, s->ls) ? 1024 : 0;
+    const uint64_t pilot = (s->pilot_useful && count >= 16 * (uint64_t)s->grid * geo_hist_per_cta(s->group, s->ls)) ? 1024 : 0;
     uint64_t n = 0;
     for (uint64_t done = 0; done < count; done += n) {
         const uint64_t first = first0 + done;
