@@ -1,16 +1,20 @@
 // Device-side data layout and kernels of the importance-sampling likelihood path (sm_100a).
 //
-// One GROUP of W lanes (W = 8, 16 or 32: four, two or one histories per warp) draws one coalescent history
-// (ProposalEngine::calculateLikelihood, /root/reference/src/ProposalEngine.cpp:643-861). The ancestral
-// configuration (TypeContainer, TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed
-// haplotypes; the candidate backward moves of one event (ProposalEngine.cpp:134-566) are scored across the lanes:
+// K1 draws coalescent histories (ProposalEngine::calculateLikelihood, /root/reference/src/ProposalEngine.cpp:643-861). Its
+// shipped form is the lockstep kernel of coal_lockstep.cuh: a CTA advances 16 histories in lockstep -- serial sections with
+// one thread per history, cooperative passes with 4 lanes per history over its type store, and query phases with one lane
+// per conditional-sampling query of ANY of the CTA's histories. coal_kernels.cu keeps the group form (one group of W = 8, 16
+// or 32 lanes per history) as the fallback. Common to both: the ancestral configuration (TypeContainer,
+// TypeContainer.cpp:42-591) lives in shared memory as a slot array of bit-packed haplotypes; the candidate backward moves
+// of one event (ProposalEngine.cpp:134-566) are scored across lanes:
 //  * marginal (one-locus) conditional sampling probabilities collapse to a dot product of a distance
 //    histogram with a precomputed weight vector (ConditionalSamplingHMM.cpp:332-370),
 //  * two-locus ones (the 16-interval forward pass, ConditionalSamplingHMM.cpp:372-424) are bilinear forms over the
 //    class distances with two small per-row matrices in which the interval axis is already summed out (coal_math.h),
 //    one query per lane,
-//  * the table rows an event reads are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier).
-// fp64 throughout; no tensor cores (the recursion is a diagonal + rank-1 update, not a contraction).
+//  * table rows are read through L1 (ld.global.nc); the -DCOAL_TMA build stages the rows an event reads into shared
+//    memory by TMA bulk copies (cp.async.bulk + mbarrier) instead -- measured slower for the lockstep form (coal_kernels.cu).
+// fp64 throughout; no tensor cores (per query the contraction is (LA+1) x (LB+1) with per-lane count vectors).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -37,7 +41,7 @@ struct DevProblem {
     int T, LA, LB, Ltot, G;
     int n_max, kmax, row_doubles, pvmax, warp_bytes;
     int SB, off_wEA, off_wEB;     // device row (coal_tables.h): MY[(LA+2)][SB = LB+2][2] | wEA[LA+1] | wEB[LB+1], row_doubles in all
-    int stage_doubles;            // doubles of a row staged into shared memory per event by TMA (row_doubles, or 0: rows too large, read through L1)
+    int stage_doubles;            // -DCOAL_TMA build: doubles of a row staged into shared memory per event by TMA; 0: rows are read through L1
     unsigned long long maskA, maskB;
     double perm_const;        // sum_t probabilitySamplePermutation (ProposalEngine.cpp:88-118,822-828)
     double pow2negLA, pow2negLB, pow2negL, wsum;

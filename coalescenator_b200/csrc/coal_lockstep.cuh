@@ -1,29 +1,38 @@
 // K1, lockstep form: a CTA of NT threads advances NH coalescent histories (NH <= 32 <= NT) in lockstep, one "step" (an injection,
-// a collection boundary, or one backward event of ProposalEngine.cpp:134-566) per history and iteration, in phases
-// separated by CTA barriers:
+// a collection boundary, or one backward event of ProposalEngine.cpp:134-566) per history and iteration. The histories of the
+// CTA are dealt to its warps (HPW = NH / warps each); within a warp a history owns LPH = 32 / HPW consecutive lanes, the first
+// of which is its SERIAL THREAD. A step is, per warp and without CTA barriers in between (only __syncwarp / shuffles: a warp
+// touches the state of its own histories only),
 //
-//   S  (serial, ONE THREAD PER HISTORY: the first NH threads of the CTA)  finish the event of the previous step -- assemble
-//      the candidate probabilities, draw the move (sampleFromVector, ProposalEngine.cpp:568-583), apply it to the type
-//      store, book the target-density statistics --, then fetch / inject / choose the next lineage and waiting time
-//      (TypeContainer::sampleType, TypeContainer.cpp:641-745), handle a collection boundary, remove the chosen lineage,
-//      list the coalescence partners, issue the TMA copies of the table rows the event's queries read, and publish the
-//      event descriptor;
-//   G  (all threads, only in steps where some history closed an epoch or ended) the per-grid-point target density of the
-//      epoch from its sufficient statistics (coal_math.h: epoch_log_density), lanes over grid points;
-//   Q1 (all threads, ONE LANE PER (history, one-locus query)) the flattened list of all one-locus conditional sampling
-//      probabilities of the CTA's events (ConditionalSamplingHMM.cpp:332-370 as a dot product);
-//   Q2 (all threads, ONE LANE PER (history, two-locus query)) class list of the query (TypeContainer::getDifferences with
-//      the dA+dB collapse, TypeContainer.cpp:802-886) + its pi_SMC as a bilinear form (coal_math.h).
+//   S1  (serial threads) finish the event of the previous step: assemble the candidate probabilities, draw the move
+//       (sampleFromVector, ProposalEngine.cpp:568-583), book the target-density statistics;
+//   W1  (all lanes, LPH per history) the move's type changes on the store (TypeContainer::addType / removeType) as ONE
+//       cooperative walk, then (serial) append what was not stored, drop the slots the event emptied, event constant;
+//   S2  (serial) fetch the next history when the slot is free;
+//   W0  (all lanes, only when a history injects) the sampled types of a collection enter the store, one walk per type;
+//   W2  (all lanes) lineage-chooser weights of every stored type (TypeContainer::sampleType, TypeContainer.cpp:641-745);
+//   S3  (serial) sum the weights in slot order, draw the lineage and the waiting time, handle a collection boundary or the end
+//       of the history, start the event descriptor;
+//   W3  (all lanes) remove the chosen lineage: cross counts, C-type counts, partner list in slot order (ballot rank);
+//   S4/S5 (serial) publish the descriptor / write out a history that ended;
+//
+// and then, across the CTA and separated by CTA barriers,
+//
+//   G   (all threads, only in steps where some history closed an epoch or ended) the per-grid-point target density of the
+//       epoch from its sufficient statistics (coal_math.h: epoch_log_density), lanes over grid points;
+//   Q1  (all threads, ONE LANE PER (history, one-locus query)) the flattened list of all one-locus conditional sampling
+//       probabilities of the CTA's events (ConditionalSamplingHMM.cpp:332-370 as a dot product);
+//   Q2  (all threads, ONE LANE PER (history, two-locus query)) class list of the query (TypeContainer::getDifferences with
+//       the dA+dB collapse, TypeContainer.cpp:802-886) + its pi_SMC as a bilinear form (coal_math.h).
 //
 // Why: the group form of the kernel (coal_kernels.cu: a group of 8-32 lanes per history, every group its own control
 // flow) keeps 40-64 independent instruction streams per SM wandering through ~70 KB of code -- ncu: 3.9 stalled-for-
-// instruction-fetch warps per issue at 16 warps/SM, 15 of 32 lanes active (profiles/r2_v7_*). Here a warp instruction
-// serves 16-32 histories in the serial phase (one instruction stream per CTA and phase, each phase a small loop), and
-// the query phases run one query per lane over the queries of ALL histories of the CTA, so lanes are full whatever the
-// number of candidate moves of one event is. The type store is laid out slot-major / history-minor ([slot][NH]): in the
-// serial phase lane h touches bank h, in the query phases lanes of different histories touch different banks and lanes
-// of one history broadcast. Results are those of the group form: same canonical slot order, same draws, partial sums
-// of the categorical draws in plain index order (exactly the oracle's order).
+// instruction-fetch warps per issue at 16 warps/SM, 15 of 32 lanes active (profiles/r2_v7_*). Here the serial sections are
+// short scalar code shared by the histories of a warp, every walk over a type store uses all lanes of the warp, and the
+// query phases run one query per lane over the queries of ALL histories of the CTA, so lanes are full whatever the number
+// of candidate moves of one event is. The type store is laid out slot-major / history-minor ([slot][NH]). Results are those
+// of the group form: same canonical slot order, same draws, partial sums of the categorical draws in plain index order
+// (exactly the oracle's order). History of the form: profiles/r2_kernel_iterations.md.
 #pragma once
 
 namespace {
