@@ -25,6 +25,7 @@ constexpr int kCounters = 16;     // device counters per sampler (SampleArgs::co
 thread_local std::string g_err;
 std::atomic<int> g_emission_mode{COALGPU_EMISSION_REFERENCE};   // API value (coalgpu_set_emission_mode)
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};      // bytes the drop-in entry points copied (coalgpu_transfer_bytes)
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -483,7 +484,7 @@ int finish_device(HostPrep& h, int device, cudaStream_t up, coalgpu_sampler** ou
     }
     s->allocs.push_back(base);
     cudaError_t ue = cudaSuccess;
-    auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes && ue == cudaSuccess) ue = cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, up); };
+    auto put = [&](size_t o, const void* src, size_t bytes) { if (bytes && ue == cudaSuccess) { ue = cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, up); g_h2d_bytes += bytes; } };
     if (!h.device_emission) put(o_rows, s->tab.dev_rows.data(), dev_rows_doubles * sizeof(double));
     put(o_set, s->tab.set_of_epoch.data(), s->tab.set_of_epoch.size() * sizeof(int));
     put(o_times, h.times.data(), h.times.size() * sizeof(double));
@@ -565,6 +566,7 @@ const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a, TMA-staged tab
 const char* coalgpu_version(void) { return "coalgpu 0.1 (sm_100a)"; }
 #endif
 uint64_t coalgpu_launch_count(void) { return g_launches.load(); }
+void coalgpu_transfer_bytes(uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = g_h2d_bytes.load(); if (d2h) *d2h = g_d2h_bytes.load(); }
 
 int coalgpu_set_emission_mode(int mode) {
     if (mode != COALGPU_EMISSION_REFERENCE && mode != COALGPU_EMISSION_STABLE && mode != COALGPU_EMISSION_STABLE_HOST) return fail(COALGPU_EINVAL, "unknown emission mode");
@@ -670,6 +672,7 @@ int coalgpu_counters(coalgpu_sampler* s, uint64_t* n_events, uint64_t* n_pismc, 
     CU_OK(cudaSetDevice(s->device));
     unsigned long long h[kCounters];
     CU_OK(cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    g_d2h_bytes += sizeof h;
     s->n_nan_seen = h[9];
     if (n_events) *n_events = h[1];
     if (n_pismc) *n_pismc = h[2];
@@ -906,13 +909,14 @@ static int sample_range(coalgpu_sampler* s, uint64_t seed, uint64_t first0, uint
             if (!d_defer) RS_OK(dev_alloc((void**)&d_defer, chunk * sizeof(unsigned long long)));
             rc = sample_pass(s, 1, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, d_defer, 0);
             unsigned long long n_def = 0;
-            if (!rc) RS_OK(cudaMemcpy(&n_def, s->d_counters + 6, sizeof n_def, cudaMemcpyDeviceToHost));
+            if (!rc) { RS_OK(cudaMemcpy(&n_def, s->d_counters + 6, sizeof n_def, cudaMemcpyDeviceToHost)); g_d2h_bytes += sizeof n_def; }
             if (!rc && n_def) rc = sample_pass(s, 2, seed, first, n, 0, d_w, d_t, d_l, nullptr, nullptr, nullptr, 0, 0, d_defer, n_def);
             n_deferred_total += n_def;
         }
         if (!rc) rc = coalgpu_partials(s, n, nullptr, d_w, d_t, d_l, d_p);
         if (rc) { std::string m = g_err; cleanup(); return fail(rc, m); }
         RS_OK(cudaMemcpy(hp.data(), d_p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        g_d2h_bytes += hp.size() * sizeof(double);
         for (size_t i = 0; i < acc.size(); i += 2) {   // (max, sum) merge
             const double m1 = acc[i], m2 = hp[i], mm = std::max(m1, m2);
             if (mm > -INFINITY) acc[i + 1] = acc[i + 1] * std::exp(m1 - mm) + hp[i + 1] * std::exp(m2 - mm);

@@ -54,7 +54,7 @@ _lib = None
 
 EXPORTS = ["coalgpu_run_sampler", "coalgpu_run_sampler_batch", "coalgpu_create", "coalgpu_destroy", "coalgpu_sample", "coalgpu_partials",
            "coalgpu_finalize", "coalgpu_counters", "coalgpu_tables", "coalgpu_pismc_classes",
-           "coalgpu_launch_count", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
+           "coalgpu_launch_count", "coalgpu_transfer_bytes", "coalgpu_last_error", "coalgpu_version", "coalgpu_work_counters", "coalgpu_fp64_peak",
            "coalgpu_capacity_stats", "coalgpu_tune", "coalgpu_set_emission_mode",
            "coalgpu_comm_init", "coalgpu_comm_finalize", "coalgpu_comm_size", "coalgpu_run_sampler_comm",
            "coalgpu_run_sampler_multi", "coalgpu_multi_shutdown", "coalgpu_nccl_calls", "coalgpu_score_events"]
@@ -401,6 +401,13 @@ def fp64_peak_tflops(device: int = 0) -> float:
 
 def launch_count() -> int:
     return int(load_library().coalgpu_launch_count())
+
+
+def transfer_bytes():
+    """(host -> device, device -> host) bytes the drop-in entry points have copied in this process so far."""
+    a, b = C.c_uint64(), C.c_uint64()
+    load_library().coalgpu_transfer_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 def nccl_calls() -> int:

@@ -219,6 +219,9 @@ int coalgpu_score_events(coalgpu_sampler* s, int64_t n_cfg, const int32_t* cfg_o
 
 /* Kernel launches issued by this library on the calling process so far (bench.py's gpu_launches). */
 uint64_t coalgpu_launch_count(void);
+/* Bytes the drop-in entry points (coalgpu_create / coalgpu_run_sampler*) have copied host -> device (problem, tables, constants)
+ * and device -> host (partials, counters) on the calling process so far: bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step. */
+void coalgpu_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 const char* coalgpu_last_error(void);
 const char* coalgpu_version(void);
 
