@@ -373,7 +373,9 @@ __device__ __forceinline__ void run_lockstep() {
     int* const pre2 = m.pre2 + warp * (NH + 1);
     const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
     const int nsum = Ltot + 2;
+#ifdef COAL_TMA_ROWS
     const int wlen = ((Ltot + 2) + 1) & ~1;
+#endif
     constexpr bool kStaged =
 #ifdef COAL_TMA_ROWS
         C::N32;
