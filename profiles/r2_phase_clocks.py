@@ -1,5 +1,10 @@
+"""Phase clocks of the lockstep kernel (cycles between the CTA barriers as seen by thread 0: serial + cooperative sections S, grid
+phase G, one-locus queries Q1, two-locus queries Q2), per lockstep step. Needs a library built with -DCOAL_LS_TIMING:
+    COALGPU_LIB=variants/timing.so COALGPU_DEFS=-DCOAL_LS_TIMING python -m coalescenator_b200.build
+    COALGPU_LIB=variants/timing.so python profiles/r2_phase_clocks.py 16 2 11 20      # bench pair indices
+Results of the round: profiles/r2_kernel_iterations.md."""
 import sys, ctypes as C
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch, bench
 import coalescenator_b200 as cb
 probs = bench.bench_problems()
