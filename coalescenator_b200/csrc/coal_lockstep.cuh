@@ -78,7 +78,7 @@ struct LsSnap {                    // what the G phase needs of a history that c
 // 34 bytes per slot and history -- live in the CTA's slice of a global-memory arena instead (gtotal bytes per CTA,
 // offsets relative to the slice): histories with thousands of lineages (TypeContainer has no size limit,
 // TypeContainer.cpp:409-522) then run at L2 speed instead of not at all. Everything per event stays in shared memory.
-struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, total; size_t gtotal; };
+struct LsLayout { unsigned int words, cg, xc, plist, pv, aux, rowbuf, wbuf, mbar, scratch, desc, snap, pre1, pre2, rbuf, total; size_t gtotal; };
 
 __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvmax, int Ltot, int stage_doubles, bool narrow, bool gstore = false) {
     LsLayout L;
@@ -104,6 +104,7 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvma
     L.snap = place((size_t)NH * sizeof(LsSnap));
     L.pre1 = place((size_t)(NT / 32) * (NH + 1) * 4);     // one copy of the work-list prefixes per warp
     L.pre2 = place((size_t)(NT / 32) * (NH + 1) * 4);
+    L.rbuf = place((size_t)NT * 16);                      // Philox blocks drawn ahead: NT / NH per history
     L.total = o;
     L.gtotal = ((size_t)og + 255) & ~(size_t)255;
     return L;
@@ -123,7 +124,7 @@ struct LsCta {
     typedef typename WO::T WordT;
     static constexpr int NT = NT_;
     WordT* words; unsigned int* cg; unsigned int* xc; unsigned short* plist; double* pv; double* aux;
-    double* rowbuf; double* wbuf; unsigned long long* mbar; unsigned int* scratch; LsDesc* desc; LsSnap* snap; int* pre1; int* pre2;
+    double* rowbuf; double* wbuf; unsigned long long* mbar; unsigned int* scratch; LsDesc* desc; LsSnap* snap; int* pre1; int* pre2; uint4* rbuf;
 
     __device__ __forceinline__ void bind() {
         const LsLayout L = ls_layout(NH, NT, sP.kmax, sP.pvmax, sP.Ltot, sP.stage_doubles, N32, GS);
@@ -133,7 +134,7 @@ struct LsCta {
         plist = reinterpret_cast<unsigned short*>(sb + L.plist); pv = reinterpret_cast<double*>(sb + L.pv); aux = reinterpret_cast<double*>(sb + L.aux);
         rowbuf = reinterpret_cast<double*>(b + L.rowbuf); wbuf = reinterpret_cast<double*>(b + L.wbuf); mbar = reinterpret_cast<unsigned long long*>(b + L.mbar);
         scratch = reinterpret_cast<unsigned int*>(b + L.scratch); desc = reinterpret_cast<LsDesc*>(b + L.desc); snap = reinterpret_cast<LsSnap*>(b + L.snap);
-        pre1 = reinterpret_cast<int*>(b + L.pre1); pre2 = reinterpret_cast<int*>(b + L.pre2);
+        pre1 = reinterpret_cast<int*>(b + L.pre1); pre2 = reinterpret_cast<int*>(b + L.pre2); rbuf = reinterpret_cast<uint4*>(b + L.rbuf);
     }
     // slot-major / history-minor: element j of history h
     static __device__ __forceinline__ int at(int j, int h) { return j * NH + h; }
@@ -142,7 +143,7 @@ struct LsCta {
 // Per-history state of the serial phase: lives in the registers of the history's thread across steps.
 struct LsHist {
     unsigned long long h;
-    PhiloxStream rng;
+    unsigned long long rk, rb0;      // Philox4x32-10 stream of the history: next draw k (block k >> 1, half k & 1); first block held in rbuf
     EpochStats st;
     LogProd qprod, evprod;
     double qsum, consts, tsum;
@@ -387,10 +388,19 @@ __device__ __forceinline__ void run_lockstep() {
     const unsigned long long n_todo = sA.list ? *sA.list_count : sA.n;
 
     LsHist s;
-    s.h = 0; s.rng.init(0, 0); epoch_stats_clear(s.st); s.qprod.clear(); s.evprod.clear(); s.qsum = s.consts = s.tsum = 0.0;
+    s.h = 0; s.rk = 0; s.rb0 = ~0ull; epoch_stats_clear(s.st); s.qprod.clear(); s.evprod.clear(); s.qsum = s.consts = s.tsum = 0.0;
     s.nslots = s.nA = s.nB = s.nC = 0; s.inj_lo = s.inj_hi = 0; s.e = 0; s.tset = 0; s.peak = 0;
     s.nev = s.npi = s.ncq = 0; s.tma_phase = 0;
     s.have = false; s.done = !serial; s.injecting = false; s.post = true; s.tracing = false; s.overflow = false; s.wfirst = true; s.pending = false;
+    // Draw k of a history = half k & 1 of Philox block k >> 1 (as PhiloxStream, coal_device.cuh). The blocks are computed AHEAD,
+    // LPH at a time by the LPH lanes of the history at a convergent point of the step (before S3: the two draws of S3 and the
+    // move draw of the next S1 are then in the buffer), instead of by the serial thread inside its divergent sections.
+    auto next_u = [&]() {
+        const uint4 blk = m.rbuf[h * LPH + (int)((s.rk >> 1) - s.rb0)];
+        const double u = (s.rk & 1) ? u52(blk.z, blk.w) : u52(blk.x, blk.y);
+        s.rk++;
+        return u;
+    };
     if (serial) {
         m.desc[h].valid = 0; m.desc[h].nm = 0; m.desc[h].nq = 0;
         m.snap[h].flags = 0;
@@ -474,7 +484,7 @@ __device__ __forceinline__ void run_lockstep() {
                 } else {
                 // ---- sample the move (sampleFromVector :568-583) ----
                 double pidx;
-                const int idx = ls_scan<NH, NT, MD>(m, h, ncand, s.rng.next() * ptot, false, pidx);
+                const int idx = ls_scan<NH, NT, MD>(m, h, ncand, next_u() * ptot, false, pidx);
                 // proposal density of the event: waiting time, lineage choice, move (:696-698, :455)
                 const double qfac = (D.rate * D.hap_num * pidx) / (D.hap_den * ptot);
                 // ---- apply the move, event constant (:242-294, :342-371, :418-448) ----
@@ -575,7 +585,7 @@ __device__ __forceinline__ void run_lockstep() {
                 } else {
                     if (sA.list) hx = sA.list[hx];
                     s.h = hx; s.have = true;
-                    s.rng.init(sA.seed, sA.first + hx);
+                    s.rk = 0; s.rb0 = ~0ull;
                     s.nslots = 0; s.nA = s.nB = s.nC = 0; s.overflow = false;
                     s.tracing = sA.events != nullptr && hx < sA.n_trace;
                     s.nev = 0; s.npi = 0; s.ncq = 0;
@@ -671,6 +681,17 @@ __device__ __forceinline__ void run_lockstep() {
             }
             __syncwarp();
         }
+        // =================================== R: Philox blocks ahead, LPH lanes per history ===================================
+        {
+            const bool act = serial && !s.done && !end_now && !sA.score_off;
+            const bool need = act && (s.rb0 == ~0ull || ((s.rk + 2) >> 1) >= s.rb0 + LPH);
+            if (__any_sync(kFull, need)) {      // every history of the warp draws ahead from where it stands: fewer refill rounds
+                const unsigned long long kq = __shfl_sync(kFull, s.rk, leader), hq = __shfl_sync(kFull, s.h, leader);
+                m.rbuf[h * LPH + sub] = philox_block(sA.seed, sA.first + hq, (kq >> 1) + (unsigned long long)sub);
+                if (act) s.rb0 = s.rk >> 1;
+                __syncwarp();
+            }
+        }
         // =================================== S3: one thread per history ===================================
         // values that cross from S3 over the cooperative removal pass into S4
         int rm_op = 0, rm_sx = 0;                  // bit 0: an event is being set up; bits 1-2: class of the chosen lineage
@@ -694,14 +715,14 @@ __device__ __forceinline__ void run_lockstep() {
 #pragma unroll 1
                     for (int j = 0; j < ns0; j++) if (m.words[C::at(j, h)] == cw && (m.cg[C::at(j, h)] >> 30) == cgx) sx = j;
                 } else {
-                    sx = ls_scan<NH, NT, MD>(m, h, ns0, s.rng.next() * hap_den, true, hap_num);
+                    sx = ls_scan<NH, NT, MD>(m, h, ns0, next_u() * hap_den, true, hap_num);
                 }
                 const int n = s.nA + s.nB + s.nC, Ac = s.nA, Bc = s.nB, Cc = s.nC;
                 const double nn = (double)((unsigned int)n * (unsigned int)(n - 1));
                 const double Dd = nn + (double)(Ac + Cc) * dthA + (double)(Bc + Cc) * dthB + drho_e * (double)Cc;
                 const double rate = Dd * __ldg(&ecp->inv2Ntau);
                 const double tsum = s.tsum;
-                const double wait = sA.score_off ? 1.0 : -dlog(s.rng.next()) / rate;
+                const double wait = sA.score_off ? 1.0 : -dlog(next_u()) / rate;
                 const double aa = (double)((Ac + Cc) * LA + (Bc + Cc) * LB);
 
                 // ---- collection boundary (ProposalEngine.cpp:721-783) or end of the history (:792, :817-858) ----
