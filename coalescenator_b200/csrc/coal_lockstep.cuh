@@ -91,7 +91,7 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvma
     L.wbuf = place((size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8);
     L.mbar = place((size_t)NH * 8);
 #else
-    L.wbuf = L.mbar = 0;
+    L.wbuf = L.mbar = 0;                                  // wbuf: see below (aliases the query scratch)
 #endif
     L.pv = place_store((size_t)NH * pvmax * 8);
     L.aux = place_store((size_t)NH * kmax * 8);
@@ -99,7 +99,21 @@ __host__ __device__ inline LsLayout ls_layout(int NH, int NT, int kmax, int pvma
     L.cg = place_store((size_t)NH * kmax * 4);
     L.xc = place_store((size_t)NH * kmax * 4);
     L.plist = place_store((size_t)NH * kmax * 2);
-    L.scratch = place((size_t)NT * 2 * nsum * 4);      // per thread: class histogram / class list [nsum] + the distance vectors of the dense form [nsum]
+    // per thread: class histogram / class list [nsum] + the distance vectors of the dense form [nsum] (Q2). Without TMA staging
+    // the same bytes first hold the one-locus weight vectors of the step: the wEA | wEB tails of the two table rows an event's
+    // one-locus queries read (2 * wlen doubles per history), copied here by the history's lanes in the removal pass and read by
+    // Q1 with 32-bit shared-memory addressing; Q2 overwrites them after Q1's barrier.
+    {
+        size_t sb = (size_t)NT * 2 * nsum * 4;
+#ifndef COAL_TMA_ROWS
+        const size_t wb = (size_t)NH * 2 * (((Ltot + 2) + 1) & ~1) * 8;
+        if (wb > sb) sb = wb;
+#endif
+        L.scratch = place(sb);
+    }
+#ifndef COAL_TMA_ROWS
+    L.wbuf = L.scratch;
+#endif
     L.desc = place((size_t)NH * sizeof(LsDesc));
     L.snap = place((size_t)NH * sizeof(LsSnap));
     L.pre1 = place((size_t)(NT / 32) * (NH + 1) * 4);     // one copy of the work-list prefixes per warp
@@ -374,9 +388,7 @@ __device__ __forceinline__ void run_lockstep() {
     int* const pre2 = m.pre2 + warp * (NH + 1);
     const int T = sP.T, LA = sP.LA, LB = sP.LB, Ltot = sP.Ltot, NG = sP.G;
     const int nsum = Ltot + 2;
-#ifdef COAL_TMA_ROWS
-    const int wlen = ((Ltot + 2) + 1) & ~1;
-#endif
+    const int wlen = ((Ltot + 2) + 1) & ~1;            // doubles per staged weight tail (wEA | wEB), even
     constexpr bool kStaged =
 #ifdef COAL_TMA_ROWS
         C::N32;
@@ -809,6 +821,7 @@ __device__ __forceinline__ void run_lockstep() {
         // the removal does not touch that class): the lanes of a history take LPH consecutive slots per round and rank their
         // partners with a ballot.
         {
+            __syncwarp();                  // the descriptors as the serial threads started them
             const int opq = __shfl_sync(kFull, rm_op, leader);
             if (__any_sync(kFull, opq != 0)) {
                 const unsigned long long xwq = __shfl_sync(kFull, rm_xw, leader);
@@ -851,6 +864,18 @@ __device__ __forceinline__ void run_lockstep() {
                 }
 #pragma unroll
                 for (int o = 1; o < LPH; o <<= 1) { Ci += __shfl_xor_sync(kFull, Ci, o); Cj += __shfl_xor_sync(kFull, Cj, o); }
+#ifndef COAL_TMA_ROWS
+                // stage the one-locus weight vectors of the event's two table rows for Q1 (the rows were chosen in S3: the
+                // descriptor is visible after the __syncwarp at the head of this pass)
+                if (opq & 1) {
+                    const double* __restrict__ g1 = m.desc[h].row_m1 + sP.off_wEA;
+                    const double* __restrict__ g2 = m.desc[h].row_alt + sP.off_wEA;
+                    double* dst = m.wbuf + (size_t)h * 2 * wlen;
+                    const int tl = sP.row_doubles - sP.off_wEA;
+#pragma unroll 1
+                    for (int i = sub; i < tl; i += LPH) { dst[i] = __ldg(g1 + i); dst[wlen + i] = __ldg(g2 + i); }
+                }
+#endif
                 __syncwarp();
                 // ---- S4: publish the event (ProposalEngine.cpp:134-238, 298-338, 375-414) ----
                 if (serial && (rm_op & 1)) {
@@ -970,8 +995,8 @@ __device__ __forceinline__ void run_lockstep() {
                 else { qg = xg; qw64 = (qi >= 1) ? (D.xw ^ (1ull << (D.offb + qi - 1))) : D.xw; }
                 const int offw = (qg == GA) ? sP.off_wEA : sP.off_wEB;
                 const double powl = (qg == GA) ? sP.pow2negLA : sP.pow2negLB;
-                const double* __restrict__ wE1 = D.row_m1 + offw;
-                const double* __restrict__ wE2 = D.row_alt + offw;
+                const double* __restrict__ wE1 = m.wbuf + (size_t)hh * 2 * wlen + (offw - sP.off_wEA);   // staged tails of rows n-1 and n / n-2
+                const double* __restrict__ wE2 = wE1 + wlen;
                 const typename WO::T mask = WO::narrow((qg == GA) ? sP.maskA : sP.maskB), qw = WO::narrow(qw64);
                 double num1 = 0.0, num2 = 0.0; unsigned int ncomp = 0;
                 // branch-free: the lanes of a warp walk the slots of different histories (different classes at the same j); a
@@ -986,8 +1011,8 @@ __device__ __forceinline__ void run_lockstep() {
                     const int d = WO::popc((wj ^ qw) & mask);
                     LS_ASSERT(d <= ((qg == GA) ? LA : LB));
                     const double cf = (double)c;
-                    num1 += cf * tab_ld(wE1 + d);
-                    num2 += cf * tab_ld(wE2 + d);
+                    num1 += cf * wE1[d];
+                    num2 += cf * wE2[d];
                     ncomp += c;
                 }
                 // fp64 division is a ~25-instruction sequence: reciprocals of lineage counts come from a table
