@@ -350,10 +350,24 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             tb1 = transfer_bytes()
             passes.append((per_pair * npairs * world / float(te.item()), dt, e2e_dev, tb1[0] - tb0[0], tb1[1] - tb0[1]))
+        # For information: the same pairs through ONE coalgpu_run_sampler_batch call (what replaces the reference's whole pair loop,
+        # main.cpp:242-311: pairs on streams, host preparation overlapped; the drain of one pair's launch is covered by the next
+        # pair's). Not the headline: `value` above is the per-pair drop-in call, the smaller change for a maintainer.
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        cb.ImportanceSampler().run_sampler_batch(probs, per_pair, seed=4242 + rank, device=local)
+        torch.cuda.synchronize()
+        tb = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        batch_value = per_pair * npairs * world / float(tb.item())
         # bytes per step: MEASURED by the library (coalgpu_transfer_bytes: every cudaMemcpy of the drop-in call counts its bytes),
         # this rank, warm pass; `bytes_model` is the closed-form count of problem_bytes() for comparison
         e2e = {"value": passes[1][0], "unit": "histories/s", "h2d_bytes_per_step": int(passes[1][3]), "d2h_bytes_per_step": int(passes[1][4]),
                "bytes": "measured by the library (coalgpu_transfer_bytes), rank 0, warm pass", "bytes_model": [int(h2d), int(d2h)],
+               "batch_call_value": batch_value,
                "histories": per_pair * npairs * world, "cold_value": passes[0][0], "warm_value": passes[1][0],
                "wall_s_rank0": passes[1][1], "device_s_rank0": passes[1][2]}
 
