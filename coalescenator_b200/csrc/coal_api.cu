@@ -1069,6 +1069,7 @@ static int run_sampler_batch_impl(int32_t n_problems, const coalgpu_problem* pro
                     if (rc) err = g_err;
                     WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, kCounters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, j.st));
                     WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + kCounters) * sizeof(double), cudaMemcpyDeviceToHost, j.st));
+                    g_d2h_bytes += (j.np + kCounters) * sizeof(double);
                     WB_OK(cudaStreamSynchronize(j.st));
                 }
             }
@@ -1160,6 +1161,7 @@ static int run_sampler_batch_impl(int32_t n_problems, const coalgpu_problem* pro
         if (rc) { err = g_err; break; }
         WB_OK(cudaMemcpyAsync(j.d_p + j.np, j.s->d_counters, kCounters * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         WB_OK(cudaMemcpyAsync(j.h_p, j.d_p, (j.np + kCounters) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        g_d2h_bytes += (j.np + kCounters) * sizeof(double);
         WB_OK(cudaEventRecord(j.e1, st));
         t_launch += tick() - t0;
     }
